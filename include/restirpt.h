@@ -1,0 +1,278 @@
+/*
+ * restirpt.h — C ABI of the B200 (sm_100a) ReSTIR PT device library (librestirpt.so).
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b): the reference's host (Renderer / Scene / Camera) reaches
+ * its device code through "create pipeline / execute(extent, bindings, push-constant)" pass objects
+ * (reference src/RayTracing.h:27-48).  Every entry point below names the reference interface it replaces.
+ * Plain pointers and sizes only; no C++ / torch types.  All structs are byte-identical to the reference's
+ * std430 layouts (reference src/shader/layouts.glsl) so host code written against the reference keeps working.
+ *
+ * Conventions: every function returns 0 on success or a negative RptStatus; rpt_last_error() gives the
+ * message.  Handles are opaque, not thread-safe, and bound to one CUDA device.  All passes enqueue on the
+ * frame's CUDA stream in call order (stream order replaces the reference's pipeline barriers,
+ * reference src/GRISReSTIR.cpp:33-47); rpt_sync() blocks.  There is NO CPU fallback: without a CUDA device
+ * rpt_ctx_create fails with RPT_ERR_NO_DEVICE.
+ */
+#ifndef RESTIRPT_H
+#define RESTIRPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum RptStatus {
+	RPT_OK = 0,
+	RPT_ERR_INVALID = -1,    /* bad argument / bad handle */
+	RPT_ERR_NO_DEVICE = -2,  /* no CUDA device: the library never falls back to the CPU */
+	RPT_ERR_CUDA = -3,       /* sticky CUDA error, see rpt_last_error */
+	RPT_ERR_OOM = -4,
+	RPT_ERR_UNSUPPORTED = -5
+} RptStatus;
+
+/* ---- data layouts (reference src/shader/layouts.glsl, host mirrors in the src headers) ------------------------- */
+
+/* layouts.glsl:6-25 with RESTIR_PT_MATERIAL=1, host src/Material.h:14-38.  32 B */
+typedef struct RptMaterial {
+	float baseColor[3];
+	uint32_t type;        /* 1 Lambert, 2 MetallicWorkflow, 3 Metal, 4 Dielectric, 6 Fake (material.glsl:13-20) */
+	uint32_t textureIdx;  /* 0xffffffff = none */
+	float metallic;
+	float roughness;
+	float ior;
+} RptMaterial;
+
+/* layouts.glsl:53-58, src/Model.h:15-33.  32 B */
+typedef struct RptMeshVertex {
+	float pos[3];
+	float uvx;
+	float norm[3];
+	float uvy;
+} RptMeshVertex;
+
+/* layouts.glsl:60-72, src/Scene.h:15-27.  224 B.  Matrices are column-major (glm). */
+typedef struct RptObjectInstance {
+	float transform[16];
+	float transformInv[16];
+	float transformInvT[16];
+	float radiance[3];
+	float pad0;
+	uint32_t indexOffset;
+	uint32_t indexCount;
+	uint32_t matIndex;   /* unused by the shaders; host pad */
+	float pad2;
+} RptObjectInstance;
+
+/* layouts.glsl:74-83, src/Scene.h:29-38.  64 B, world space */
+typedef struct RptTriangleLight {
+	float v0[3]; float nx;
+	float v1[3]; float ny;
+	float v2[3]; float nz;
+	float radiance[3]; float area;
+} RptTriangleLight;
+
+/* layouts.glsl:85-88, src/util/AliasTable.h:7-10.  8 B; N+1 entries, [0] = {sum power, N}; failId is 1-based */
+typedef struct RptLightSampleTableElement {
+	float prob;
+	uint32_t failId;
+} RptLightSampleTableElement;
+
+/* layouts.glsl:27-51; the reference memcpy's its Camera object as the UBO (src/Camera.h:47-69,
+ * src/Renderer.cpp:359-360).  352 B */
+typedef struct RptCamera {
+	float view[16];
+	float proj[16];
+	float projView[16];
+	float lastProjView[16];
+	float pos[3];   float FOV;
+	float angle[3]; float nearZ;
+	float front[3]; float farZ;
+	float right[3]; float lensRadius;
+	float up[3];    float focalDist;
+	uint32_t filmSize[2];
+	uint32_t frameIndex;   /* bit 31 = clear flag (camera.glsl:6-7) */
+	uint32_t seed;
+} RptCamera;
+
+/* layouts.glsl:90-94.  16 B.  instanceIdx 0 = light, i+1 = object instance i,
+ * 0xffffffff invalid, 0xfffffffe "special" = primary hit (ray_layouts.glsl:12-13) */
+typedef struct RptIntersection {
+	float bary[2];
+	uint32_t instanceIdx;
+	uint32_t triangleIdx;
+} RptIntersection;
+
+/* layouts.glsl:96-115.  64 B */
+typedef struct RptDIReservoir {
+	RptIntersection isec;
+	float Li[3]; float pad0;
+	float jacobian; float samplePdf; uint32_t rng; uint32_t isLightSample;
+	uint32_t sampleCount; float resampleWeight; float contribWeight; float weight;
+} RptDIReservoir;
+
+/* layouts.glsl:117-130.  48 B */
+typedef struct RptGIReservoir {
+	RptIntersection rcIsec;
+	float rcLo[3]; uint32_t rcPrevCoord;
+	uint32_t sampleCount; float resampleWeight; float contribWeight; float pad0;
+} RptGIReservoir;
+
+/* layouts.glsl:132-156.  96 B (GLSL stride; the reference host over-allocates 112, src/Renderer.cpp:35) */
+typedef struct RptGRISReservoir {
+	RptIntersection rcIsec;
+	float rcLi[3]; uint32_t rcRng;
+	float rcWi[3]; uint32_t flags;   /* bits 0-7 rcVertexId, 8-15 pathLength, 16-23 rcVertexType */
+	float pad[2]; float rcPrevSamplePdf; float rcJacobian;
+	float F[3]; uint32_t primaryRng;
+	float sampleCount; float resampleWeight; float contribWeight; float pad0;
+} RptGRISReservoir;
+
+/* push constants */
+typedef struct RptDISettings {   /* src/TestReSTIR.h:12-17, default {Reconnection, Light, 0, 1} */
+	uint32_t shiftType;          /* 0 Reconnection, 1 Replay, 2 Hybrid (no-op for DI) */
+	uint32_t sampleType;         /* 0 Light, 1 BSDF, 2 Both */
+	uint32_t temporalReuse;
+	uint32_t spatialReuse;
+} RptDISettings;
+
+typedef struct RptGRISSettings { /* src/GRISReSTIR.h:11-17, default {Hybrid, 1, 0, 1, 20} */
+	uint32_t shiftType;
+	float rrScale;
+	uint32_t temporalReuse;
+	uint32_t spatialReuse;
+	uint32_t cap;
+} RptGRISSettings;
+
+typedef struct RptPostSettings { /* src/PostProcessFrag.h:7-12 */
+	uint32_t toneMapping;        /* 0 none, 1 filmic, 2 ACES */
+	uint32_t correctGamma;
+	uint32_t noDirect;
+	uint32_t noIndirect;
+} RptPostSettings;
+
+/* One RGBA8 texture; texels are sRGB-encoded (reference zvk/core/HostImage.cpp:22), sampled bilinear or
+ * nearest with REPEAT addressing (zvk/core/Memory.cpp:75-92) */
+typedef struct RptTextureDesc {
+	const uint8_t* rgba8;
+	uint32_t width, height;
+	uint32_t filter;             /* 0 linear, 1 nearest */
+} RptTextureDesc;
+
+/* What DeviceScene uploads (reference src/Scene.cpp:368-446) and what its acceleration-structure build
+ * consumes (src/Scene.cpp:448-547).  Host memory is borrowed for the duration of the call only. */
+typedef struct RptSceneDesc {
+	const RptMeshVertex* vertices;           uint32_t numVertices;
+	const uint32_t* indices;                 uint32_t numIndices;        /* absolute into vertices[] */
+	const RptMaterial* materials;            uint32_t numMaterials;
+	const int32_t* materialIndices;          uint32_t numMaterialIndices;/* one per object triangle */
+	const RptObjectInstance* instances;      uint32_t numInstances;
+	const RptTriangleLight* triangleLights;  uint32_t numTriangleLights;
+	const RptLightSampleTableElement* lightSampleTable;                  /* numTriangleLights + 1 entries */
+	const RptTextureDesc* textures;          uint32_t numTextures;
+} RptSceneDesc;
+
+typedef enum RptBufferId {
+	RPT_BUF_DIRECT_OUTPUT = 0,    /* float4 / px   (layouts.glsl:180)      */
+	RPT_BUF_INDIRECT_OUTPUT = 1,  /* float4 / px   (layouts.glsl:181)      */
+	RPT_BUF_DEPTH_NORMAL = 2,     /* float4 / px, current frame (binding 2)*/
+	RPT_BUF_DEPTH_NORMAL_PREV = 3,
+	RPT_BUF_ALBEDO_MATID = 4,     /* uint2 / px                            */
+	RPT_BUF_ALBEDO_MATID_PREV = 5,
+	RPT_BUF_MOTION = 6,           /* float2 / px, values rounded through fp16 (RG16F target) */
+	RPT_BUF_DI_THIS = 7, RPT_BUF_DI_PREV = 8, RPT_BUF_DI_TEMP = 9,          /* 64 B / px */
+	RPT_BUF_GI_THIS = 10, RPT_BUF_GI_PREV = 11,                             /* 48 B / px */
+	RPT_BUF_GRIS_THIS = 12, RPT_BUF_GRIS_PREV = 13, RPT_BUF_GRIS_TEMP = 14, /* 96 B / px */
+	RPT_BUF_PRIMARY_ISEC = 15,    /* RptIntersection / px of the G-buffer primary ray (parity aid, new) */
+	RPT_BUF_COUNT = 16
+} RptBufferId;
+
+/* ray / traversal counters accumulated since rpt_counters_reset (new; needed for Mrays/s and
+ * bytes-per-ray).  Only maintained when counting is enabled. */
+typedef struct RptCounters {
+	uint64_t closestRays;
+	uint64_t shadowRays;
+	uint64_t nodeVisits;     /* CWBVH nodes fetched (80 B each)  */
+	uint64_t triTests;       /* triangles fetched (48 B each)    */
+	uint64_t shadedHits;     /* loadSurfaceInfo gathers (272 B)  */
+} RptCounters;
+
+typedef struct RptBvhStats {
+	uint32_t numTriangles;
+	uint32_t numNodes;        /* 80-byte CWBVH nodes */
+	uint64_t nodeBytes;
+	uint64_t triBytes;
+	float buildMs;            /* GPU time of the build (CUDA events) */
+	float sahCost;
+} RptBvhStats;
+
+typedef struct RptCtx RptCtx;
+typedef struct RptScene RptScene;
+typedef struct RptFrame RptFrame;
+
+/* ---- context (replaces zvk::Instance/Context creation, reference src/Renderer.cpp:82-109) -------------- */
+int rpt_ctx_create(int cudaDevice, RptCtx** out);
+void rpt_ctx_destroy(RptCtx* ctx);
+const char* rpt_last_error(const RptCtx* ctx);  /* ctx may be NULL: last error of the calling thread */
+int rpt_version(void);
+
+/* ---- scene (replaces DeviceScene ctor, reference src/Scene.cpp:324-330: buffer upload + BLAS/TLAS build).
+ * Builds the flattened world-space compressed wide BVH on the GPU. */
+int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* desc, RptScene** out);
+void rpt_scene_destroy(RptScene* scene);
+int rpt_scene_bvh_stats(const RptScene* scene, RptBvhStats* out);
+
+/* ---- frame resources (replaces Renderer::createRayImage + GBufferPass::createResource,
+ * reference src/Renderer.cpp:193-257, src/GBufferPass.cpp:81-137).
+ * A frame owns the rows [rowBegin, rowEnd) of a fullWidth x fullHeight film plus `halo` guard rows on each
+ * interior edge (multi-GPU strips); single GPU: rowBegin=0,rowEnd=fullHeight,halo=0. */
+int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeight,
+                     uint32_t rowBegin, uint32_t rowEnd, uint32_t halo, RptFrame** out);
+void rpt_frame_destroy(RptFrame* frame);
+int rpt_frame_clear(RptFrame* frame);            /* zero every buffer, reset ping-pong */
+int rpt_frame_flip(RptFrame* frame);             /* mCurFrame ^= 1, reference src/Renderer.cpp:567 */
+void* rpt_frame_stream(RptFrame* frame);         /* cudaStream_t the passes run on (for event timing) */
+
+/* 2 x 352-byte Camera upload, reference src/Renderer.cpp:358-361 */
+int rpt_set_camera(RptFrame* frame, const RptCamera* cur, const RptCamera* prev);
+
+/* ---- passes.  Each replaces one RayTracing::execute / pass ::render call of the reference ------------- */
+int rpt_gbuffer(RptFrame* f, const RptScene* s);                               /* GBufferPass::render, src/GBufferPass.cpp:22-56 */
+int rpt_di_naive(RptFrame* f, const RptScene* s);                              /* mNaiveDIPass,  shader di_naive.comp */
+int rpt_gi_naive(RptFrame* f, const RptScene* s);                              /* mNaiveGIPass,  shader gi_naive.comp */
+int rpt_di_pathgen(RptFrame* f, const RptScene* s, const RptDISettings* st);   /* TestReSTIR::render step 1, src/TestReSTIR.cpp:9-36 */
+int rpt_di_temporal(RptFrame* f, const RptScene* s, const RptDISettings* st);  /*   step 2 */
+int rpt_di_spatial(RptFrame* f, const RptScene* s, const RptDISettings* st);   /*   step 3 */
+int rpt_gi_restir(RptFrame* f, const RptScene* s);                             /* mResampledGIPass, shader gi_resample_temporal.comp */
+int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSettings* st); /* GRISReSTIR::render step 1, src/GRISReSTIR.cpp:9-53 */
+int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSettings* st);  /*   step 2 */
+int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettings* st);   /*   step 3 */
+int rpt_visualize_as(RptFrame* f, const RptScene* s);                          /* as_visualize.comp (triangle tests / primary ray / 100) */
+/* PostProcessFrag::render, src/PostProcessFrag.cpp:156-184.  rgba8Out may be NULL (device-only run);
+ * otherwise it receives ownedRows*fullWidth*4 bytes (R,G,B,A order) after an implicit sync. */
+int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out);
+
+int rpt_sync(RptFrame* f);
+
+/* ---- read-back / upload of any frame buffer (new; parity tests and multi-GPU halo plumbing) ----------- */
+/* Rows are frame-local storage rows: row 0 is film row max(rowBegin-halo,0). */
+size_t rpt_buffer_stride(RptBufferId id);         /* bytes per pixel */
+int rpt_frame_rows(const RptFrame* f, uint32_t* storageRowBegin, uint32_t* storageRowEnd);
+int rpt_read(RptFrame* f, RptBufferId id, void* dst, size_t bytes);      /* whole storage, implicit sync */
+int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes);
+void* rpt_device_ptr(RptFrame* f, RptBufferId id); /* raw device pointer of the storage (P2P / NCCL halo exchange) */
+
+/* ---- ray queries exposed directly (new; closest-hit primitive-ID parity, traversal microbench) -------- */
+/* rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} floats on the HOST; out: n RptIntersection on the host */
+int rpt_trace_closest(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out);
+int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, uint8_t* occludedOut);
+
+int rpt_counters_enable(RptCtx* ctx, int on);
+int rpt_counters_reset(RptCtx* ctx);
+int rpt_counters_read(RptCtx* ctx, RptCounters* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESTIRPT_H */

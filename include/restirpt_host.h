@@ -1,0 +1,69 @@
+/*
+ * restirpt_host.h — C view of the C++ host library (librestirpt_host.so): Scene / Camera / alias table /
+ * headless Renderer, i.e. the host classes of the reference (src/Scene.*, src/Resource.*, src/Model.*,
+ * src/Material.*, src/Camera.*, src/util/AliasTable.h, src/Renderer.*) rebuilt over include/restirpt.h.
+ * It exists so that tests, bench.py and other-language callers can drive the same host code; C++ callers
+ * use vulkan-restir-pt_b200/host/*.h directly.
+ */
+#ifndef RESTIRPT_HOST_H
+#define RESTIRPT_HOST_H
+
+#include "restirpt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RhScene RhScene;
+typedef struct RhRenderer RhRenderer;
+
+const char* rh_last_error(void);
+
+/* Scene::load (reference src/Scene.cpp:104-123); NULL on failure */
+RhScene* rh_scene_load_xml(const char* path);
+/* procedural scenes: BASELINE.json config 1 (Cornell), the VeachAjar stand-in, config 5 (instanced field) */
+RhScene* rh_scene_cornell(void);
+RhScene* rh_scene_room(uint32_t trisTarget, uint32_t seed);
+RhScene* rh_scene_field(uint32_t meshSubdiv, uint32_t gridN, uint32_t seed);
+void rh_scene_destroy(RhScene* s);
+void rh_scene_desc(const RhScene* s, RptSceneDesc* out);   /* pointers stay valid until rh_scene_destroy */
+void rh_scene_camera(const RhScene* s, RptCamera* out);
+uint32_t rh_scene_num_triangles(const RhScene* s);
+
+/* Camera (reference src/Camera.cpp) operating on the raw 352-byte block */
+void rh_camera_init(RptCamera* cam, const float pos[3], const float angleDeg[3], float fovDeg,
+                    uint32_t width, uint32_t height, float nearZ, float farZ);
+void rh_camera_look_at(RptCamera* cam, const float target[3]);
+void rh_camera_set_film(RptCamera* cam, uint32_t width, uint32_t height);
+void rh_camera_set_planes(RptCamera* cam, float nearZ, float farZ);
+void rh_camera_move(RptCamera* cam, const float delta[3]);
+void rh_camera_update(RptCamera* cam);                      /* Camera::update: frameIndex = 0 */
+void rh_camera_next_frame(RptCamera* cam, uint32_t seed);   /* Camera::nextFrame */
+
+/* DiscreteSampler1D<float>::build (reference src/util/AliasTable.h:26-71); out has n+1 entries */
+void rh_build_alias_table(const float* power, uint32_t n, RptLightSampleTableElement* out);
+
+/* headless Renderer (reference src/Renderer.cpp drawFrame path); NULL on failure */
+RhRenderer* rh_renderer_create(const RhScene* s, uint32_t width, uint32_t height, int cudaDevice,
+                               uint32_t rowBegin, uint32_t rowEnd, uint32_t halo);
+void rh_renderer_destroy(RhRenderer* r);
+void rh_renderer_set_methods(RhRenderer* r, int directMethod, int indirectMethod, int toneMapping,
+                             int correctGamma, int accumulate);
+void rh_renderer_set_gris(RhRenderer* r, const RptGRISSettings* st);
+void rh_renderer_set_di(RhRenderer* r, const RptDISettings* st);
+void rh_renderer_clear_reservoirs(RhRenderer* r);
+void rh_renderer_camera_move(RhRenderer* r, const float delta[3]);
+void rh_renderer_camera(RhRenderer* r, RptCamera* out);
+typedef void (*RhHaloExchangeFn)(void* user, RptFrame* frame, RptBufferId buffer);
+void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* user);
+int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out);   /* 0 ok, -1 error */
+RptFrame* rh_renderer_frame(RhRenderer* r);
+RptScene* rh_renderer_scene(RhRenderer* r);
+RptCtx* rh_renderer_ctx(RhRenderer* r);
+
+int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

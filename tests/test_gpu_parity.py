@@ -1,0 +1,150 @@
+"""GPU parity tests proper: the CUDA library (through its C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): closest-hit primitive IDs bit-exact; every G-buffer / reservoir / output buffer
+is compared BIT-EXACTLY as well, because both sides implement the same fp32 numeric contract (DESIGN.md
+§numerics).  The only toleranced comparison is the 8-bit post-process output (pow() comes from two different
+libms): at most 1 LSB.
+"""
+import numpy as np
+import pytest
+
+import restirpt
+from restirpt import DISettings, GRISSettings, PostSettings
+from common import Backend, run_frames, bitwise_mismatch, camera_rays, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def device(built):
+    dev = restirpt.Device(0)
+    yield dev
+
+
+SCENES = {
+    "cornell": lambda: restirpt.HostScene.cornell(),
+    "room": lambda: restirpt.HostScene.room(6000, 7),
+    "field": lambda: restirpt.HostScene.field(1, 3, 42),
+}
+
+
+@pytest.fixture(scope="module", params=list(SCENES))
+def pair(request, device):
+    sc = SCENES[request.param]()
+    w, h = 96, 54
+    gpu = Backend("cuda", sc, w, h, device)
+    cpu = Backend("oracle", sc, w, h)
+    yield request.param, sc, gpu, cpu
+    gpu.close()
+    cpu.close()
+
+
+def test_closest_hit_ids_random_rays(pair):
+    name, sc, gpu, cpu = pair
+    rng = np.random.default_rng(1234)
+    rays = random_rays(rng, 20000, -3.0, 3.0)
+    a, b = gpu.trace_closest(rays), cpu.trace_closest(rays)
+    assert np.array_equal(a["instanceIdx"], b["instanceIdx"])
+    assert np.array_equal(a["triangleIdx"], b["triangleIdx"])
+    hit = a["instanceIdx"] != 0xffffffff
+    assert hit.mean() > 0.3
+    assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32))
+
+
+def test_shadow_rays(pair):
+    name, sc, gpu, cpu = pair
+    rng = np.random.default_rng(99)
+    rays = random_rays(rng, 20000, -2.5, 2.5, tmax=1.5)
+    a, b = gpu.trace_shadow(rays), cpu.trace_shadow(rays)
+    assert np.array_equal(a, b)
+    assert 0.02 < a.mean() < 0.98
+
+
+def test_oracle_bvh_equals_brute_force(pair):
+    """pins the oracle's own accelerator against its brute-force definition"""
+    name, sc, gpu, cpu = pair
+    rng = np.random.default_rng(5)
+    rays = random_rays(rng, 1500, -3.0, 3.0)
+    fast = cpu.trace_closest(rays)
+    cpu.lib.orc_scene_set_brute_force(cpu.scene, 1)
+    slow = cpu.trace_closest(rays)
+    cpu.lib.orc_scene_set_brute_force(cpu.scene, 0)
+    assert np.array_equal(fast, slow)
+
+
+PASS_BUFFERS = {
+    "gbuffer": ["DEPTH_NORMAL", "ALBEDO_MATID", "MOTION", "PRIMARY_ISEC"],
+    "di_naive": ["DIRECT_OUTPUT"], "gi_naive": ["INDIRECT_OUTPUT"],
+    "di_pathgen": ["DI_THIS"], "di_temporal": ["DI_TEMP"], "di_spatial": ["DI_THIS", "DIRECT_OUTPUT"],
+    "gi_restir": ["GI_THIS", "INDIRECT_OUTPUT"],
+    "gris_pathtrace": ["GRIS_THIS"], "gris_temporal": ["GRIS_TEMP"], "gris_spatial": ["GRIS_THIS", "INDIRECT_OUTPUT"],
+}
+
+
+def _compare_method(pair, method, frames, moves=None, **kw):
+    name, sc, gpu, cpu = pair
+    cam = sc.camera(gpu.w, gpu.h)
+    shots = {"cuda": {}, "oracle": {}}
+
+    def snap(i, pass_name, backend):
+        for buf in PASS_BUFFERS[pass_name]:
+            shots[backend.kind][(i, pass_name, buf)] = backend.read(buf)
+
+    for b in (gpu, cpu):
+        b.clear()
+        run_frames(b, cam, method, frames, moves=moves, snapshot=snap, **kw)
+    assert shots["cuda"].keys() == shots["oracle"].keys()
+    bad = {k: bitwise_mismatch(shots["cuda"][k], shots["oracle"][k]) for k in shots["cuda"]}
+    bad = {k: v for k, v in bad.items() if v}
+    assert not bad, f"{name}/{method}: pixels differing per (frame, pass, buffer): {bad}"
+    return shots["cuda"]
+
+
+DOLLY = [(0.0, 0.0, 0.0), (0.01, 0.02, 0.0), (0.01, 0.02, 0.005), (0.0, 0.0, 0.0)]
+
+
+def test_gbuffer_and_naive_passes_bit_exact(pair):
+    shots = _compare_method(pair, "naive", 2)
+    depth = shots[(0, "gbuffer", "DEPTH_NORMAL")][..., 0]
+    assert (depth > 0).mean() > 0.3
+    out = shots[(1, "gi_naive", "INDIRECT_OUTPUT")]
+    assert np.isfinite(out).all() and out[..., :3].mean() > 0
+
+
+@pytest.mark.parametrize("shift,sample", [(0, 0), (0, 2), (1, 2)])
+def test_restir_di_bit_exact(pair, shift, sample):
+    _compare_method(pair, "di", 4, moves=DOLLY, di=DISettings(shift, sample, 1, 1))
+
+
+def test_restir_gi_bit_exact(pair):
+    _compare_method(pair, "gi", 4, moves=DOLLY)
+
+
+@pytest.mark.parametrize("shift,temporal,spatial", [(2, 1, 1), (0, 1, 1), (2, 0, 1), (2, 1, 0)])
+def test_restir_pt_gris_bit_exact(pair, shift, temporal, spatial):
+    shots = _compare_method(pair, "gris", 4, moves=DOLLY, gris=GRISSettings(shift, 1.0, temporal, spatial, 20))
+    r = shots[(3, "gris_spatial", "GRIS_THIS")]
+    assert (r["rcIsec"]["instanceIdx"] != 0xffffffff).mean() > 0.05
+
+
+def test_postprocess_within_one_lsb(pair):
+    name, sc, gpu, cpu = pair
+    cam = sc.camera(gpu.w, gpu.h)
+    for b in (gpu, cpu):
+        b.clear()
+        run_frames(b, cam, "naive", 1)
+    for tm in (0, 1, 2):
+        st = PostSettings(tm, 1, 0, 0)
+        a, b = gpu.postprocess(st).astype(np.int32), cpu.postprocess(st).astype(np.int32)
+        assert np.abs(a - b).max() <= 1
+        assert a[..., :3].mean() > 1
+
+
+def test_visualize_as(pair):
+    name, sc, gpu, cpu = pair
+    cam = sc.camera(gpu.w, gpu.h)
+    for b in (gpu, cpu):
+        b.clear()
+        b.set_camera(cam, cam)
+        b.run("visualize_as")
+    assert bitwise_mismatch(gpu.read("DIRECT_OUTPUT"), cpu.read("DIRECT_OUTPUT")) == 0

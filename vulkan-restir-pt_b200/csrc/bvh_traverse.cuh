@@ -1,0 +1,189 @@
+// Ray traversal over the compressed 8-wide BVH.  Replaces rayQueryEXT closest-hit / any-hit traversal of the
+// reference (src/shader/ray_query.glsl:6-70, driver BVH + RT cores) with hand-written sm_100a code.
+//
+// Semantics (identical to the CPU oracle's brute-force definition):
+//   * triangle test: Möller–Trumbore on (v0, e1, e2) with a fixed operation order and a BaryEps tolerance on
+//     the barycentric bounds; accepted iff tmin < t < tmax;
+//   * closest hit: minimum t, ties broken towards the lower flattened triangle index — so the answer does not
+//     depend on traversal order;
+//   * the box tests are conservative (error-padded slabs, outward-rounded quantisation), so the BVH never
+//     culls a triangle the test above accepts.
+#pragma once
+#include "rt_math.cuh"
+#include "rt_types.cuh"
+
+namespace rt {
+
+struct Hit {
+	float u, v;
+	uint32_t instanceIdx, triangleIdx;
+};
+
+enum TraceMode { TraceClosest = 0, TraceAny = 1, TraceClosestNoLights = 2, TraceCount = 3 };
+
+constexpr int TraversalStackSize = 48;
+
+// one 4-child half of a node: accumulate hit bits for children j = 0..3 of the half
+RT_DEV uint32_t slabHits4(uint32_t meta4, uint32_t octinv4,
+                          uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy, uint32_t qfz,
+                          float sx, float sy, float sz, float nx, float ny, float nz, float fx, float fy, float fz,
+                          float tmin, float tmax) {
+	uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+	uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+	uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+	uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+	uint32_t hits = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const int sh = 8 * j;
+		float tnx = fma_(__uint2float_rn((qnx >> sh) & 0xffu), sx, nx);
+		float tny = fma_(__uint2float_rn((qny >> sh) & 0xffu), sy, ny);
+		float tnz = fma_(__uint2float_rn((qnz >> sh) & 0xffu), sz, nz);
+		float tfx = fma_(__uint2float_rn((qfx >> sh) & 0xffu), sx, fx);
+		float tfy = fma_(__uint2float_rn((qfy >> sh) & 0xffu), sy, fy);
+		float tfz = fma_(__uint2float_rn((qfz >> sh) & 0xffu), sz, fz);
+		float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+		float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+		if (tn <= tf) {
+			hits |= ((childBits4 >> sh) & 0xffu) << ((bitIndex4 >> sh) & 0xffu);
+		}
+	}
+	return hits;
+}
+
+template <int MODE>
+RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tmax, uint32_t* candidateCount = nullptr) {
+	Hit best;
+	best.u = 0.0f; best.v = 0.0f;
+	best.instanceIdx = InvalidHitIndex;
+	best.triangleIdx = 0;
+	float bestT = tmax;
+	uint32_t bestFlat = 0xffffffffu;
+	uint32_t nodeVisits = 0, triTests = 0, count = 0;
+
+	// reciprocal direction; components too close to zero are pushed away from it so 1/d stays finite
+	const float tiny = 1e-20f;
+	float idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+	float idy = 1.0f / (abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+	float idz = 1.0f / (abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+	const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
+	const uint32_t octinv = 7u ^ ((negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u));
+	const uint32_t octinv4 = octinv * 0x01010101u;
+
+	uint2 stack[TraversalStackSize];
+	int sp = 0;
+	uint2 ngroup = make_uint2(0u, 0x80000000u);
+
+	for (;;) {
+		uint32_t triBase = 0, triHits = 0;
+		if (ngroup.y > 0x00ffffffu) {
+			const uint32_t hits = ngroup.y;
+			const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
+			ngroup.y &= ~(1u << bit);
+			if (ngroup.y > 0x00ffffffu && sp < TraversalStackSize) stack[sp++] = ngroup;
+			const uint32_t slot = (bit - 24u) ^ octinv;
+			const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
+			const float4* np = reinterpret_cast<const float4*>(s.nodes + (ngroup.x + rel));
+			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			nodeVisits++;
+
+			const uint32_t ebits = __float_as_uint(n0.w);
+			// 2^(e-127) per axis times 1/d, and (p - o)/d, padded by a bound on their rounding error so the
+			// slab interval can only grow
+			const float ex = __uint_as_float((ebits & 0xffu) << 23);
+			const float ey = __uint_as_float(((ebits >> 8) & 0xffu) << 23);
+			const float ez = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
+			const float sx = ex * idx, sy = ey * idy, sz = ez * idz;
+			const float hx = (n0.x - o.x) * idx, hy = (n0.y - o.y) * idy, hz = (n0.z - o.z) * idz;
+			const float padx = fma_(abs_(sx), 255.0f, abs_(hx)) * 1e-6f;
+			const float pady = fma_(abs_(sy), 255.0f, abs_(hy)) * 1e-6f;
+			const float padz = fma_(abs_(sz), 255.0f, abs_(hz)) * 1e-6f;
+			const float nx = hx - padx, ny = hy - pady, nz = hz - padz;
+			const float fx = hx + padx, fy = hy + pady, fz = hz + padz;
+
+			const uint32_t qlox0 = __float_as_uint(n2.x), qlox1 = __float_as_uint(n2.y);
+			const uint32_t qloy0 = __float_as_uint(n2.z), qloy1 = __float_as_uint(n2.w);
+			const uint32_t qloz0 = __float_as_uint(n3.x), qloz1 = __float_as_uint(n3.y);
+			const uint32_t qhix0 = __float_as_uint(n3.z), qhix1 = __float_as_uint(n3.w);
+			const uint32_t qhiy0 = __float_as_uint(n4.x), qhiy1 = __float_as_uint(n4.y);
+			const uint32_t qhiz0 = __float_as_uint(n4.z), qhiz1 = __float_as_uint(n4.w);
+
+			uint32_t hitmask = slabHits4(__float_as_uint(n1.z), octinv4,
+				negx ? qhix0 : qlox0, negy ? qhiy0 : qloy0, negz ? qhiz0 : qloz0,
+				negx ? qlox0 : qhix0, negy ? qloy0 : qhiy0, negz ? qloz0 : qhiz0,
+				sx, sy, sz, nx, ny, nz, fx, fy, fz, tmin, bestT);
+			hitmask |= slabHits4(__float_as_uint(n1.w), octinv4,
+				negx ? qhix1 : qlox1, negy ? qhiy1 : qloy1, negz ? qhiz1 : qloz1,
+				negx ? qlox1 : qhix1, negy ? qloy1 : qhiy1, negz ? qloz1 : qhiz1,
+				sx, sy, sz, nx, ny, nz, fx, fy, fz, tmin, bestT);
+
+			ngroup.x = __float_as_uint(n1.x);
+			ngroup.y = (hitmask & 0xff000000u) | (ebits >> 24);
+			triBase = __float_as_uint(n1.y);
+			triHits = hitmask & 0x00ffffffu;
+		}
+
+		while (triHits) {
+			const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
+			triHits &= triHits - 1u;
+			const float4* tp = reinterpret_cast<const float4*>(s.tris + (triBase + i));
+			const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+			triTests++;
+			const float3 v0 = f3(t0), e1 = f3(t1), e2 = f3(t2);
+			const float3 p = cross(d, e2);
+			const float det = dot(e1, p);
+			const float inv = 1.0f / det;
+			const float3 sv = o - v0;
+			const float u = dot(sv, p) * inv;
+			const float3 q = cross(sv, e1);
+			const float v = dot(d, q) * inv;
+			const float t = dot(e2, q) * inv;
+			if (u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > tmin && t < tmax) {
+				const uint32_t inst = __float_as_uint(t0.w);
+				if (MODE == TraceAny) {
+					best.instanceIdx = inst;
+					best.triangleIdx = __float_as_uint(t1.w);
+					goto done;
+				}
+				if (MODE == TraceCount) {
+					count++;
+					continue;
+				}
+				if (MODE == TraceClosestNoLights && inst == 0u) continue;
+				const uint32_t flat = __float_as_uint(t2.w);
+				if (t < bestT || (t == bestT && flat < bestFlat)) {
+					bestT = t; bestFlat = flat;
+					best.u = u; best.v = v;
+					best.instanceIdx = inst;
+					best.triangleIdx = __float_as_uint(t1.w);
+				}
+			}
+		}
+
+		if (ngroup.y <= 0x00ffffffu) {
+			if (sp == 0) break;
+			ngroup = stack[--sp];
+		}
+	}
+done:
+	if (s.counters != nullptr) {
+		atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
+		atomicAdd(&s.counters[3], (unsigned long long)triTests);
+	}
+	if (MODE == TraceCount && candidateCount) *candidateCount = count;
+	return best;
+}
+
+// wrappers with the reference's names (ray_query.glsl:6-70)
+RT_DEV Hit traceClosestHit(const SceneView& s, float3 o, float tmin, float3 d, float tmax) {
+	return traceRay<TraceClosest>(s, o, tmin, d, tmax);
+}
+RT_DEV bool traceShadow(const SceneView& s, float3 o, float tmin, float3 d, float tmax) {
+	return traceRay<TraceAny>(s, o, tmin, d, tmax).instanceIdx != InvalidHitIndex;
+}
+RT_DEV bool traceVisibility(const SceneView& s, float3 from, float3 to) {   // ray_query.glsl:27-38
+	return !traceShadow(s, from, MinRayDistance, normalize(to - from), distance(to, from) - MinRayDistance);
+}
+
+} // namespace rt

@@ -1,0 +1,435 @@
+// C ABI of librestirpt.so (include/restirpt.h): contexts, scene upload + BVH build, frame buffers with the
+// reference's ping-pong wiring (src/Renderer.cpp:324-347), pass dispatch, read-back.  No CPU fallback exists:
+// every entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/restirpt.h"
+#include "bvh_build.h"
+#include "passes.h"
+
+#define RPT_API extern "C" __attribute__((visibility("default")))
+
+using namespace rt;
+
+struct RptCtx {
+	int device = 0;
+	std::string lastError;
+	cudaStream_t stream = nullptr;         // scene builds and raw ray queries
+	unsigned long long* counters = nullptr;
+	bool countersOn = false;
+};
+
+struct RptScene {
+	RptCtx* ctx = nullptr;
+	SceneView view{};
+	std::vector<void*> allocations;
+	RptBvhStats stats{};
+};
+
+struct RptFrame {
+	RptCtx* ctx = nullptr;
+	uint32_t width = 0, height = 0, rowBegin = 0, rowEnd = 0, storeBegin = 0, storeEnd = 0;
+	uint32_t cur = 0;
+	cudaStream_t stream = nullptr;
+	float4 *directOutput = nullptr, *indirectOutput = nullptr, *depthNormal[2] = { nullptr, nullptr };
+	uint2* albedoMatId[2] = { nullptr, nullptr };
+	float2* motion = nullptr;
+	RptDIReservoir *di[2] = { nullptr, nullptr }, *diTemp = nullptr;
+	RptGIReservoir* gi[2] = { nullptr, nullptr };
+	RptGRISReservoir *gris[2] = { nullptr, nullptr }, *grisTemp = nullptr;
+	RptIntersection* primaryIsec = nullptr;
+	uchar4* rgba8 = nullptr;
+	RptCamera camera{}, prevCamera{};
+	size_t pixels() const { return size_t(width) * (storeEnd - storeBegin); }
+};
+
+static thread_local std::string gThreadError;
+
+static int fail(RptCtx* ctx, int code, const std::string& msg) {
+	gThreadError = msg;
+	if (ctx) ctx->lastError = msg;
+	return code;
+}
+static int cudaFail(RptCtx* ctx, cudaError_t e, const char* what) {
+	return fail(ctx, e == cudaErrorMemoryAllocation ? RPT_ERR_OOM : RPT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return cudaFail(ctx, e_, #expr); } while (0)
+
+RPT_API int rpt_version(void) { return 1; }
+
+RPT_API const char* rpt_last_error(const RptCtx* ctx) { return ctx ? ctx->lastError.c_str() : gThreadError.c_str(); }
+
+RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
+	if (!out) return fail(nullptr, RPT_ERR_INVALID, "rpt_ctx_create: out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		return fail(nullptr, RPT_ERR_NO_DEVICE, std::string("rpt_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+	}
+	if (cudaDevice < 0 || cudaDevice >= n) return fail(nullptr, RPT_ERR_INVALID, "rpt_ctx_create: device index out of range");
+	RptCtx* ctx = new RptCtx;
+	ctx->device = cudaDevice;
+	CU(ctx, cudaSetDevice(cudaDevice));
+	CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CU(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
+	CU(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
+	*out = ctx;
+	return RPT_OK;
+}
+
+RPT_API void rpt_ctx_destroy(RptCtx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->counters) cudaFree(ctx->counters);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+template <typename T>
+static cudaError_t upload(RptScene* sc, const T* host, size_t n, const T** dev, cudaStream_t st) {
+	void* p = nullptr;
+	cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+	if (e != cudaSuccess) return e;
+	sc->allocations.push_back(p);
+	if (n) e = cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+	*dev = static_cast<const T*>(p);
+	return e;
+}
+
+RPT_API int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* d, RptScene** out) {
+	if (!ctx || !d || !out) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: NULL argument");
+	*out = nullptr;
+	if (d->numTriangleLights == 0) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: the scene needs at least one triangle light (the light sample table divides by its total power)");
+	if (d->numIndices % 3 != 0) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: numIndices must be a multiple of 3");
+	CU(ctx, cudaSetDevice(ctx->device));
+	RptScene* sc = new RptScene;
+	sc->ctx = ctx;
+	cudaStream_t st = ctx->stream;
+	SceneView& v = sc->view;
+	auto bail = [&](cudaError_t e, const char* what) { int r = cudaFail(ctx, e, what); rpt_scene_destroy(sc); return r; };
+	cudaError_t e;
+	if ((e = upload(sc, d->vertices, d->numVertices, &v.vertices, st)) != cudaSuccess) return bail(e, "upload vertices");
+	if ((e = upload(sc, d->indices, d->numIndices, &v.indices, st)) != cudaSuccess) return bail(e, "upload indices");
+	if ((e = upload(sc, d->materials, d->numMaterials, &v.materials, st)) != cudaSuccess) return bail(e, "upload materials");
+	if ((e = upload(sc, d->materialIndices, d->numMaterialIndices, &v.materialIndices, st)) != cudaSuccess) return bail(e, "upload materialIndices");
+	if ((e = upload(sc, d->instances, d->numInstances, &v.instances, st)) != cudaSuccess) return bail(e, "upload instances");
+	if ((e = upload(sc, d->triangleLights, d->numTriangleLights, &v.lights, st)) != cudaSuccess) return bail(e, "upload lights");
+	if ((e = upload(sc, d->lightSampleTable, size_t(d->numTriangleLights) + 1, &v.lightTable, st)) != cudaSuccess) return bail(e, "upload light table");
+	v.numLights = d->numTriangleLights;
+
+	// textures: RGBA8 sRGB texels + a 256-entry decode table (exact EOTF evaluated in double, rounded once)
+	std::vector<TextureView> tv(d->numTextures);
+	for (uint32_t i = 0; i < d->numTextures; i++) {
+		const uchar4* texels = nullptr;
+		const size_t n = size_t(d->textures[i].width) * d->textures[i].height;
+		if ((e = upload(sc, reinterpret_cast<const uchar4*>(d->textures[i].rgba8), n, &texels, st)) != cudaSuccess) return bail(e, "upload texture");
+		tv[i] = TextureView{ texels, d->textures[i].width, d->textures[i].height, d->textures[i].filter, 0 };
+	}
+	if ((e = upload(sc, tv.data(), tv.size(), &v.textures, st)) != cudaSuccess) return bail(e, "upload texture table");
+	float lut[256];
+	for (int i = 0; i < 256; i++) {
+		const double c = i / 255.0;
+		lut[i] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+	}
+	if ((e = upload(sc, lut, 256, &v.srgbToLinear, st)) != cudaSuccess) return bail(e, "upload sRGB table");
+
+	// flattened triangle numbering: lights first (instance 0), then every object instance in order
+	std::vector<uint32_t> triOffsets(size_t(d->numInstances) + 1);
+	uint64_t total = d->numTriangleLights;
+	for (uint32_t k = 0; k < d->numInstances; k++) {
+		triOffsets[k] = uint32_t(total);
+		total += d->instances[k].indexCount / 3;
+	}
+	triOffsets[d->numInstances] = uint32_t(total);
+	if (total > 0x7fffffffull) { rpt_scene_destroy(sc); return fail(ctx, RPT_ERR_UNSUPPORTED, "rpt_scene_create: more than 2^31 triangles"); }
+	const uint32_t* dTriOffsets = nullptr;
+	if ((e = upload(sc, triOffsets.data(), triOffsets.size(), &dTriOffsets, st)) != cudaSuccess) return bail(e, "upload triOffsets");
+
+	BuildInputs in{};
+	in.vertices = v.vertices; in.indices = v.indices; in.instances = v.instances; in.lights = v.lights;
+	in.triOffsets = dTriOffsets; in.numInstances = d->numInstances; in.numLights = d->numTriangleLights; in.numTris = uint32_t(total);
+	BuildOutputs bo;
+	if ((e = buildBvh(in, st, &bo)) != cudaSuccess) {
+		if (bo.nodes) cudaFree(bo.nodes);
+		if (bo.tris) cudaFree(bo.tris);
+		return bail(e, "buildBvh");
+	}
+	sc->allocations.push_back(bo.nodes);
+	sc->allocations.push_back(bo.tris);
+	v.nodes = bo.nodes; v.tris = bo.tris;
+	v.counters = nullptr;
+	sc->stats.numTriangles = bo.numTris;
+	sc->stats.numNodes = bo.numNodes;
+	sc->stats.nodeBytes = uint64_t(bo.numNodes) * sizeof(WideNode);
+	sc->stats.triBytes = uint64_t(bo.numTris) * sizeof(TriRecord);
+	sc->stats.buildMs = bo.buildMs;
+	sc->stats.sahCost = 0.0f;
+	*out = sc;
+	return RPT_OK;
+}
+
+RPT_API void rpt_scene_destroy(RptScene* s) {
+	if (!s) return;
+	cudaSetDevice(s->ctx->device);
+	for (void* p : s->allocations) cudaFree(p);
+	delete s;
+}
+
+RPT_API int rpt_scene_bvh_stats(const RptScene* s, RptBvhStats* out) {
+	if (!s || !out) return fail(nullptr, RPT_ERR_INVALID, "rpt_scene_bvh_stats: NULL argument");
+	*out = s->stats;
+	return RPT_OK;
+}
+
+// ---- frames -------------------------------------------------------------------------------------------------
+RPT_API size_t rpt_buffer_stride(RptBufferId id) {
+	switch (id) {
+	case RPT_BUF_DIRECT_OUTPUT: case RPT_BUF_INDIRECT_OUTPUT: case RPT_BUF_DEPTH_NORMAL: case RPT_BUF_DEPTH_NORMAL_PREV: return 16;
+	case RPT_BUF_ALBEDO_MATID: case RPT_BUF_ALBEDO_MATID_PREV: case RPT_BUF_MOTION: return 8;
+	case RPT_BUF_DI_THIS: case RPT_BUF_DI_PREV: case RPT_BUF_DI_TEMP: return sizeof(RptDIReservoir);
+	case RPT_BUF_GI_THIS: case RPT_BUF_GI_PREV: return sizeof(RptGIReservoir);
+	case RPT_BUF_GRIS_THIS: case RPT_BUF_GRIS_PREV: case RPT_BUF_GRIS_TEMP: return sizeof(RptGRISReservoir);
+	case RPT_BUF_PRIMARY_ISEC: return sizeof(RptIntersection);
+	default: return 0;
+	}
+}
+
+static void* framePtr(RptFrame* f, RptBufferId id) {
+	const uint32_t c = f->cur, p = f->cur ^ 1u;
+	switch (id) {
+	case RPT_BUF_DIRECT_OUTPUT: return f->directOutput;
+	case RPT_BUF_INDIRECT_OUTPUT: return f->indirectOutput;
+	case RPT_BUF_DEPTH_NORMAL: return f->depthNormal[c];
+	case RPT_BUF_DEPTH_NORMAL_PREV: return f->depthNormal[p];
+	case RPT_BUF_ALBEDO_MATID: return f->albedoMatId[c];
+	case RPT_BUF_ALBEDO_MATID_PREV: return f->albedoMatId[p];
+	case RPT_BUF_MOTION: return f->motion;
+	case RPT_BUF_DI_THIS: return f->di[c];
+	case RPT_BUF_DI_PREV: return f->di[p];
+	case RPT_BUF_DI_TEMP: return f->diTemp;
+	case RPT_BUF_GI_THIS: return f->gi[c];
+	case RPT_BUF_GI_PREV: return f->gi[p];
+	case RPT_BUF_GRIS_THIS: return f->gris[c];
+	case RPT_BUF_GRIS_PREV: return f->gris[p];
+	case RPT_BUF_GRIS_TEMP: return f->grisTemp;
+	case RPT_BUF_PRIMARY_ISEC: return f->primaryIsec;
+	default: return nullptr;
+	}
+}
+
+static std::vector<void**> frameSlots(RptFrame* f) {
+	return { (void**)&f->directOutput, (void**)&f->indirectOutput, (void**)&f->depthNormal[0], (void**)&f->depthNormal[1],
+	         (void**)&f->albedoMatId[0], (void**)&f->albedoMatId[1], (void**)&f->motion, (void**)&f->di[0], (void**)&f->di[1],
+	         (void**)&f->diTemp, (void**)&f->gi[0], (void**)&f->gi[1], (void**)&f->gris[0], (void**)&f->gris[1], (void**)&f->grisTemp,
+	         (void**)&f->primaryIsec, (void**)&f->rgba8 };
+}
+static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
+
+RPT_API int rpt_frame_clear(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_clear: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	auto slots = frameSlots(f);
+	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, f->pixels() * kSlotStride[i], f->stream));
+	f->cur = 0;
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeight, uint32_t rowBegin, uint32_t rowEnd, uint32_t halo, RptFrame** out) {
+	if (!ctx || !out) return fail(ctx, RPT_ERR_INVALID, "rpt_frame_create: NULL argument");
+	*out = nullptr;
+	if (fullWidth == 0 || fullHeight == 0 || rowBegin >= rowEnd || rowEnd > fullHeight || fullWidth > 16384 || fullHeight > 16384) {
+		return fail(ctx, RPT_ERR_INVALID, "rpt_frame_create: bad film size or row range");
+	}
+	CU(ctx, cudaSetDevice(ctx->device));
+	RptFrame* f = new RptFrame;
+	f->ctx = ctx;
+	f->width = fullWidth; f->height = fullHeight; f->rowBegin = rowBegin; f->rowEnd = rowEnd;
+	f->storeBegin = rowBegin > halo ? rowBegin - halo : 0;
+	f->storeEnd = std::min(fullHeight, rowEnd + halo);
+	cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { delete f; return cudaFail(ctx, e, "cudaStreamCreate"); }
+	auto slots = frameSlots(f);
+	for (size_t i = 0; i < slots.size(); i++) {
+		e = cudaMalloc(slots[i], f->pixels() * kSlotStride[i]);
+		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc frame buffer"); }
+	}
+	int r = rpt_frame_clear(f);
+	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
+	CU(ctx, cudaStreamSynchronize(f->stream));
+	*out = f;
+	return RPT_OK;
+}
+
+RPT_API void rpt_frame_destroy(RptFrame* f) {
+	if (!f) return;
+	cudaSetDevice(f->ctx->device);
+	if (f->stream) cudaStreamSynchronize(f->stream);
+	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
+	if (f->stream) cudaStreamDestroy(f->stream);
+	delete f;
+}
+
+RPT_API int rpt_frame_flip(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_flip: NULL frame");
+	f->cur ^= 1u;
+	return RPT_OK;
+}
+
+RPT_API void* rpt_frame_stream(RptFrame* f) { return f ? (void*)f->stream : nullptr; }
+
+RPT_API int rpt_set_camera(RptFrame* f, const RptCamera* cur, const RptCamera* prev) {
+	if (!f || !cur || !prev) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_set_camera: NULL argument");
+	if (cur->filmSize[0] != f->width || cur->filmSize[1] != f->height) {
+		return fail(f->ctx, RPT_ERR_INVALID, "rpt_set_camera: camera filmSize does not match the frame");
+	}
+	// the reference memcpy's both cameras into a host-visible UBO; here they travel as kernel parameters
+	f->camera = *cur;
+	f->prevCamera = *prev;
+	return RPT_OK;
+}
+
+static FrameView makeView(RptFrame* f) {
+	FrameView v{};
+	const uint32_t c = f->cur, p = f->cur ^ 1u;
+	v.width = f->width; v.height = f->height; v.rowBegin = f->rowBegin; v.rowEnd = f->rowEnd;
+	v.storeBegin = f->storeBegin; v.storeEnd = f->storeEnd;
+	v.directOutput = f->directOutput; v.indirectOutput = f->indirectOutput;
+	v.depthNormal = f->depthNormal[c]; v.depthNormalPrev = f->depthNormal[p];
+	v.albedoMatId = f->albedoMatId[c]; v.albedoMatIdPrev = f->albedoMatId[p];
+	v.motion = f->motion;
+	v.diThis = f->di[c]; v.diPrev = f->di[p]; v.diTemp = f->diTemp;
+	v.giThis = f->gi[c]; v.giPrev = f->gi[p];
+	v.grisThis = f->gris[c]; v.grisPrev = f->gris[p]; v.grisTemp = f->grisTemp;
+	v.primaryIsec = f->primaryIsec;
+	v.camera = f->camera; v.prevCamera = f->prevCamera;
+	return v;
+}
+
+static SceneView sceneView(const RptScene* s) {
+	SceneView v = s->view;
+	v.counters = s->ctx->countersOn ? s->ctx->counters : nullptr;
+	return v;
+}
+
+#define PASS_PROLOGUE(name) \
+	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, name ": NULL argument"); \
+	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, name ": frame and scene belong to different contexts"); \
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+#define PASS_EPILOGUE(name) \
+	CU(f->ctx, cudaGetLastError()); \
+	return RPT_OK;
+
+RPT_API int rpt_gbuffer(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gbuffer") launchGBuffer(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gbuffer") }
+RPT_API int rpt_di_naive(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_di_naive") launchDINaive(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_di_naive") }
+RPT_API int rpt_gi_naive(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gi_naive") launchGINaive(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gi_naive") }
+RPT_API int rpt_gi_restir(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gi_restir") launchGIReSTIR(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gi_restir") }
+RPT_API int rpt_visualize_as(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_visualize_as") launchVisualizeAS(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_visualize_as") }
+
+#define SETTINGS_PASS(fn, T, launcher) \
+	RPT_API int fn(RptFrame* f, const RptScene* s, const T* st) { \
+		PASS_PROLOGUE(#fn) \
+		if (!st) return fail(f->ctx, RPT_ERR_INVALID, #fn ": NULL settings"); \
+		launcher(makeView(f), sceneView(s), *st, f->stream); \
+		PASS_EPILOGUE(#fn) \
+	}
+SETTINGS_PASS(rpt_di_pathgen, RptDISettings, launchDIPathGen)
+SETTINGS_PASS(rpt_di_temporal, RptDISettings, launchDITemporal)
+SETTINGS_PASS(rpt_di_spatial, RptDISettings, launchDISpatial)
+SETTINGS_PASS(rpt_gris_pathtrace, RptGRISSettings, launchGRISPathTrace)
+SETTINGS_PASS(rpt_gris_temporal, RptGRISSettings, launchGRISTemporal)
+SETTINGS_PASS(rpt_gris_spatial, RptGRISSettings, launchGRISSpatial)
+
+RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
+	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	launchPostProcess(makeView(f), *st, f->rgba8, f->stream);
+	CU(f->ctx, cudaGetLastError());
+	if (rgba8Out) {
+		CU(f->ctx, cudaMemcpyAsync(rgba8Out, f->rgba8, size_t(f->width) * (f->rowEnd - f->rowBegin) * 4, cudaMemcpyDeviceToHost, f->stream));
+		CU(f->ctx, cudaStreamSynchronize(f->stream));
+	}
+	return RPT_OK;
+}
+
+RPT_API int rpt_sync(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_sync: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_rows(const RptFrame* f, uint32_t* b, uint32_t* e) {
+	if (!f || !b || !e) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_rows: NULL argument");
+	*b = f->storeBegin; *e = f->storeEnd;
+	return RPT_OK;
+}
+
+RPT_API int rpt_read(RptFrame* f, RptBufferId id, void* dst, size_t bytes) {
+	if (!f || !dst) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_read: NULL argument");
+	void* p = framePtr(f, id);
+	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_read: bad buffer id or size");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, f->stream));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	return RPT_OK;
+}
+
+RPT_API int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes) {
+	if (!f || !src) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_write: NULL argument");
+	void* p = framePtr(f, id);
+	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_write: bad buffer id or size");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, f->stream));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	return RPT_OK;
+}
+
+RPT_API void* rpt_device_ptr(RptFrame* f, RptBufferId id) { return f ? framePtr(f, id) : nullptr; }
+
+// ---- raw ray queries ------------------------------------------------------------------------------------------
+static int traceCommon(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out, uint8_t* occ) {
+	if (!ctx || !s || (!rays && n) || (!out && !occ)) return fail(ctx, RPT_ERR_INVALID, "rpt_trace: NULL argument");
+	if (n == 0) return RPT_OK;
+	CU(ctx, cudaSetDevice(ctx->device));
+	float4* dRays = nullptr; RptIntersection* dOut = nullptr; uint8_t* dOcc = nullptr;
+	CU(ctx, cudaMalloc(&dRays, size_t(n) * 32));
+	if (out) CU(ctx, cudaMalloc(&dOut, size_t(n) * sizeof(RptIntersection)));
+	if (occ) CU(ctx, cudaMalloc(&dOcc, n));
+	CU(ctx, cudaMemcpyAsync(dRays, rays, size_t(n) * 32, cudaMemcpyHostToDevice, ctx->stream));
+	launchTraceRays(sceneView(s), dRays, n, dOut, dOcc, ctx->stream);
+	CU(ctx, cudaGetLastError());
+	if (out) CU(ctx, cudaMemcpyAsync(out, dOut, size_t(n) * sizeof(RptIntersection), cudaMemcpyDeviceToHost, ctx->stream));
+	if (occ) CU(ctx, cudaMemcpyAsync(occ, dOcc, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(dRays); if (dOut) cudaFree(dOut); if (dOcc) cudaFree(dOcc);
+	return RPT_OK;
+}
+RPT_API int rpt_trace_closest(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out) { return traceCommon(ctx, s, rays, n, out, nullptr); }
+RPT_API int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, uint8_t* occ) { return traceCommon(ctx, s, rays, n, nullptr, occ); }
+
+// ---- counters ---------------------------------------------------------------------------------------------------
+RPT_API int rpt_counters_enable(RptCtx* ctx, int on) {
+	if (!ctx) return fail(nullptr, RPT_ERR_INVALID, "rpt_counters_enable: NULL ctx");
+	ctx->countersOn = on != 0;
+	return RPT_OK;
+}
+RPT_API int rpt_counters_reset(RptCtx* ctx) {
+	if (!ctx) return fail(nullptr, RPT_ERR_INVALID, "rpt_counters_reset: NULL ctx");
+	CU(ctx, cudaSetDevice(ctx->device));
+	CU(ctx, cudaDeviceSynchronize());
+	CU(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
+	return RPT_OK;
+}
+RPT_API int rpt_counters_read(RptCtx* ctx, RptCounters* out) {
+	if (!ctx || !out) return fail(ctx, RPT_ERR_INVALID, "rpt_counters_read: NULL argument");
+	CU(ctx, cudaSetDevice(ctx->device));
+	CU(ctx, cudaDeviceSynchronize());
+	unsigned long long h[8];
+	CU(ctx, cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
+	out->closestRays = h[0]; out->shadowRays = h[1]; out->nodeVisits = h[2]; out->triTests = h[3]; out->shadedHits = h[4];
+	return RPT_OK;
+}

@@ -1,0 +1,28 @@
+// Host launchers of the per-pixel passes (one per reference shader entry point).
+#pragma once
+#include <cuda_runtime.h>
+#include "rt_types.cuh"
+
+namespace rt {
+
+void launchGBuffer(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchVisualizeAS(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchPostProcess(const FrameView& f, const RptPostSettings& p, uchar4* rgba8, cudaStream_t st);
+void launchDINaive(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchGINaive(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchDIPathGen(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
+void launchDITemporal(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
+void launchDISpatial(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
+void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
+void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
+void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
+
+// pixel of this thread for a pass over rows [row0, row1); false when outside the film
+constexpr int PassBlockX = 8, PassBlockY = 8;
+inline dim3 passGrid(uint32_t width, uint32_t rows) {
+	return dim3((width + PassBlockX - 1) / PassBlockX, (rows + PassBlockY - 1) / PassBlockY, 1);
+}
+
+} // namespace rt

@@ -1,0 +1,77 @@
+// Device-side views of the scene and of one frame's buffers, plus the compressed wide BVH node layout.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/restirpt.h"
+
+namespace rt {
+
+constexpr uint32_t InvalidHitIndex = 0xffffffffu;
+constexpr uint32_t SpecialHitIndex = 0xfffffffeu;
+constexpr uint32_t InvalidResourceIdx = 0xffffffffu;
+constexpr float MinRayDistance = 1e-4f;
+constexpr float MaxRayDistance = 1e7f;
+constexpr float BaryEps = 1e-4f;   // tolerance of the triangle test, see bvh_traverse.cuh
+
+// 80-byte compressed 8-wide BVH node (Ylitie, Karras, Laine 2017): child boxes quantised to 8 bits relative
+// to the node origin p with per-axis power-of-two scale 2^(e-127).
+//   n0 = {p.x, p.y, p.z, e.x | e.y<<8 | e.z<<16 | imask<<24}
+//   n1 = {childBase, triBase, meta[0..3], meta[4..7]}
+//   n2 = {qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7]}
+//   n3 = {qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7]}
+//   n4 = {qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7]}
+// meta[i]: empty 0; inner child (001 << 5) | (24 + slot); leaf (unary tri count << 5) | first-triangle offset
+struct __align__(16) WideNode {
+	float4 n0, n1, n2, n3, n4;
+};
+static_assert(sizeof(WideNode) == 80, "CWBVH node must be 80 bytes");
+
+// 48-byte triangle record in leaf order: v0 | e1 = v1-v0 | e2 = v2-v0, ids in the w lanes
+//   t0.w = instanceIdx (0 = light), t1.w = triangleIdx within the instance, t2.w = flattened index (tie order)
+struct __align__(16) TriRecord {
+	float4 t0, t1, t2;
+};
+
+struct TextureView {
+	const uchar4* texels;
+	uint32_t width, height, filter;
+	uint32_t pad;
+};
+
+struct SceneView {
+	const WideNode* nodes;
+	const TriRecord* tris;
+	const RptMeshVertex* vertices;
+	const uint32_t* indices;
+	const RptMaterial* materials;
+	const int32_t* materialIndices;
+	const RptObjectInstance* instances;
+	const RptTriangleLight* lights;
+	const RptLightSampleTableElement* lightTable;
+	const TextureView* textures;
+	const float* srgbToLinear;    // 256 entries
+	uint32_t numLights;
+	unsigned long long* counters; // RptCounters layout, or nullptr when counting is off
+};
+
+struct FrameView {
+	uint32_t width, height;       // full film
+	uint32_t rowBegin, rowEnd;    // rows this frame owns
+	uint32_t storeBegin, storeEnd;// rows held in memory (owned + halo)
+	float4* directOutput;
+	float4* indirectOutput;
+	float4* depthNormal;          // this frame
+	const float4* depthNormalPrev;
+	uint2* albedoMatId;
+	const uint2* albedoMatIdPrev;
+	float2* motion;
+	RptDIReservoir* diThis;  const RptDIReservoir* diPrev;  RptDIReservoir* diTemp;
+	RptGIReservoir* giThis;  const RptGIReservoir* giPrev;
+	RptGRISReservoir* grisThis;  const RptGRISReservoir* grisPrev;  RptGRISReservoir* grisTemp;
+	RptIntersection* primaryIsec;
+	RptCamera camera, prevCamera;
+
+	__device__ __forceinline__ size_t index(uint32_t x, uint32_t y) const { return size_t(y - storeBegin) * width + x; }
+};
+
+} // namespace rt

@@ -1,0 +1,92 @@
+#include "Renderer.h"
+#include <stdexcept>
+
+namespace rpt {
+
+void Renderer::check(int status, const char* what) {
+	if (status != RPT_OK) {
+		throw std::runtime_error(std::string(what) + ": " + rpt_last_error(mCtx));
+	}
+}
+
+Renderer::Renderer(const Scene& scene, uint32_t width, uint32_t height, int cudaDevice,
+                   uint32_t rowBegin, uint32_t rowEnd, uint32_t halo) {
+	if (rowEnd == 0) rowEnd = height;
+	check(rpt_ctx_create(cudaDevice, &mCtx), "rpt_ctx_create");
+	RptSceneDesc desc = scene.desc();
+	check(rpt_scene_create(mCtx, &desc, &mDeviceScene), "rpt_scene_create");
+	check(rpt_frame_create(mCtx, width, height, rowBegin, rowEnd, halo, &mFrame), "rpt_frame_create");
+
+	// reference src/Renderer.cpp:121-125: the window size overrides the XML film size; planes 0.001 / 200
+	mCamera = scene.camera;
+	mCamera.setFilmSize(width, height);
+	mCamera.setPlanes(0.001f, 200.f);
+	std::memcpy(mCamera.data().lastProjView, mCamera.data().projView, 64);
+	mPrevCamera = mCamera;
+}
+
+Renderer::~Renderer() {
+	if (mFrame) rpt_frame_destroy(mFrame);
+	if (mDeviceScene) rpt_scene_destroy(mDeviceScene);
+	if (mCtx) rpt_ctx_destroy(mCtx);
+}
+
+void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
+	// processGUI tail (src/Renderer.cpp:654-660): without accumulation the camera is re-updated every
+	// frame, which zeroes frameIndex so every frame is shown un-accumulated
+	if (!settings.accumulate) {
+		mCamera.update();
+	}
+	if (mClearNext) {
+		mCamera.setClearFlag();
+		mClearNext = false;
+	}
+	// memorySyncHostAndDevice (src/Renderer.cpp:358-368)
+	mCamera.data().seed = seed;
+	check(rpt_set_camera(mFrame, &mCamera.data(), &mPrevCamera.data()), "rpt_set_camera");
+	mPrevCamera = mCamera;
+	mCamera.nextFrame(seed);
+
+	// recordRenderCommand (src/Renderer.cpp:400-503)
+	check(rpt_gbuffer(mFrame, mDeviceScene), "rpt_gbuffer");
+
+	if (settings.directMethod == RayTracingMethod::Naive) {
+		check(rpt_di_naive(mFrame, mDeviceScene), "rpt_di_naive");
+	}
+	else if (settings.directMethod == RayTracingMethod::ResampledDI) {
+		// TestReSTIR::render (src/TestReSTIR.cpp:9-36)
+		check(rpt_di_pathgen(mFrame, mDeviceScene, &diSettings), "rpt_di_pathgen");
+		check(rpt_di_temporal(mFrame, mDeviceScene, &diSettings), "rpt_di_temporal");
+		if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_DI_TEMP);
+		check(rpt_di_spatial(mFrame, mDeviceScene, &diSettings), "rpt_di_spatial");
+	}
+	else if (settings.directMethod == RayTracingMethod::VisualizeAS) {
+		check(rpt_visualize_as(mFrame, mDeviceScene), "rpt_visualize_as");
+	}
+
+	if (settings.indirectMethod == RayTracingMethod::Naive) {
+		check(rpt_gi_naive(mFrame, mDeviceScene), "rpt_gi_naive");
+	}
+	else if (settings.indirectMethod == RayTracingMethod::ResampledGI) {
+		check(rpt_gi_restir(mFrame, mDeviceScene), "rpt_gi_restir");
+	}
+	else if (settings.indirectMethod == RayTracingMethod::ResampledPT) {
+		// GRISReSTIR::render (src/GRISReSTIR.cpp:9-53)
+		check(rpt_gris_pathtrace(mFrame, mDeviceScene, &grisSettings), "rpt_gris_pathtrace");
+		check(rpt_gris_temporal(mFrame, mDeviceScene, &grisSettings), "rpt_gris_temporal");
+		if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_GRIS_TEMP);
+		check(rpt_gris_spatial(mFrame, mDeviceScene, &grisSettings), "rpt_gris_spatial");
+	}
+
+	RptPostSettings post;
+	post.toneMapping = uint32_t(settings.toneMapping);
+	post.correctGamma = settings.correctGamma ? 1u : 0u;
+	post.noDirect = settings.directMethod == RayTracingMethod::None;
+	post.noIndirect = settings.indirectMethod == RayTracingMethod::None;
+	check(rpt_postprocess(mFrame, &post, rgba8Out), "rpt_postprocess");
+
+	check(rpt_frame_flip(mFrame), "rpt_frame_flip");   // mCurFrame ^= 1 (src/Renderer.cpp:567)
+	mFrameCount++;
+}
+
+} // namespace rpt

@@ -1,0 +1,65 @@
+// Headless frame orchestration.  Mirrors the reference Renderer's per-frame sequence
+// (src/Renderer.cpp:400-503 recordRenderCommand, :358-368 memorySyncHostAndDevice, :539-569 drawFrame,
+// :571-577 initSettings) minus window / swapchain / GUI, and the composite passes GRISReSTIR::render
+// (src/GRISReSTIR.cpp:9-53) and TestReSTIR::render (src/TestReSTIR.cpp:9-36).  All device work goes through
+// the C ABI of include/restirpt.h; there is no other path.
+#pragma once
+#include <string>
+#include <vector>
+#include "Scene.h"
+
+namespace rpt {
+
+struct RayTracingMethod {   // reference src/Renderer.h:22-26
+	enum { None = 0, Naive = 1, ResampledDI = 2, ResampledGI = 2, ResampledPT = 3, VisualizeAS = 3 };
+};
+
+struct RendererSettings {   // reference src/Renderer.h:29-36, values after initSettings()
+	int directMethod = RayTracingMethod::None;
+	int indirectMethod = RayTracingMethod::ResampledPT;
+	int toneMapping = 1;
+	bool correctGamma = true;
+	bool accumulate = false;
+};
+
+// called between the temporal and the spatial pass when the frame is one strip of a multi-GPU film:
+// must make the neighbours' boundary rows of the given buffer visible in this frame's halo rows
+typedef void (*HaloExchangeFn)(void* user, RptFrame* frame, RptBufferId buffer);
+
+class Renderer {
+public:
+	Renderer(const Scene& scene, uint32_t width, uint32_t height, int cudaDevice,
+	         uint32_t rowBegin = 0, uint32_t rowEnd = 0, uint32_t halo = 0);
+	~Renderer();
+	Renderer(const Renderer&) = delete;
+	Renderer& operator=(const Renderer&) = delete;
+
+	// one frame; rgba8Out may be null (no read-back).  seed = this frame's Camera::seed
+	void drawFrame(uint32_t seed, uint8_t* rgba8Out);
+	void clearReservoirs() { mClearNext = true; }   // GUI "clear" → Camera::setClearFlag
+	void setHaloExchange(HaloExchangeFn fn, void* user) { mHaloFn = fn; mHaloUser = user; }
+
+	Camera& camera() { return mCamera; }
+	RptFrame* frame() { return mFrame; }
+	RptScene* deviceScene() { return mDeviceScene; }
+	RptCtx* ctx() { return mCtx; }
+	uint32_t frameCount() const { return mFrameCount; }
+
+	RendererSettings settings;
+	RptGRISSettings grisSettings = { 2 /*Hybrid*/, 1.f, 0, 1, 20 };   // src/GRISReSTIR.h:29
+	RptDISettings diSettings = { 0 /*Reconnection*/, 0 /*Light*/, 0, 1 };   // src/TestReSTIR.h:29
+
+private:
+	void check(int status, const char* what);
+
+	RptCtx* mCtx = nullptr;
+	RptScene* mDeviceScene = nullptr;
+	RptFrame* mFrame = nullptr;
+	Camera mCamera, mPrevCamera;
+	bool mClearNext = false;
+	uint32_t mFrameCount = 0;
+	HaloExchangeFn mHaloFn = nullptr;
+	void* mHaloUser = nullptr;
+};
+
+} // namespace rpt

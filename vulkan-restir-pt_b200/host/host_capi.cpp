@@ -1,0 +1,103 @@
+// C view of the host library, see include/restirpt_host.h
+#include "../../include/restirpt_host.h"
+#include "Renderer.h"
+
+#include <exception>
+#include <string>
+
+using namespace rpt;
+
+struct RhScene { Scene scene; };
+struct RhRenderer { Renderer* r; };
+
+static thread_local std::string gLastError;
+
+template <typename F>
+static RhScene* makeScene(F&& fill) {
+	RhScene* s = nullptr;
+	try {
+		s = new RhScene;
+		fill(s->scene);
+		return s;
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		delete s;
+		return nullptr;
+	}
+}
+
+static Camera wrap(const RptCamera* c) { Camera cam; cam.data() = *c; return cam; }
+
+extern "C" {
+
+const char* rh_last_error(void) { return gLastError.c_str(); }
+
+RhScene* rh_scene_load_xml(const char* path) { return makeScene([&](Scene& s) { s.load(path); }); }
+RhScene* rh_scene_cornell(void) { return makeScene([&](Scene& s) { makeCornellBox(s); }); }
+RhScene* rh_scene_room(uint32_t tris, uint32_t seed) { return makeScene([&](Scene& s) { makeAjarLikeRoom(s, tris, seed); }); }
+RhScene* rh_scene_field(uint32_t subdiv, uint32_t gridN, uint32_t seed) { return makeScene([&](Scene& s) { makeInstancedField(s, subdiv, gridN, seed); }); }
+void rh_scene_destroy(RhScene* s) { delete s; }
+void rh_scene_desc(const RhScene* s, RptSceneDesc* out) { *out = s->scene.desc(); }
+void rh_scene_camera(const RhScene* s, RptCamera* out) { *out = s->scene.camera.data(); }
+uint32_t rh_scene_num_triangles(const RhScene* s) { return s->scene.numTriangles(); }
+
+void rh_camera_init(RptCamera* cam, const float pos[3], const float angle[3], float fov,
+                    uint32_t w, uint32_t h, float nearZ, float farZ) {
+	Camera c(vec3(pos[0], pos[1], pos[2]), vec3(angle[0], angle[1], angle[2]));
+	c.setFOV(fov);
+	c.setFilmSize(w, h);
+	c.setPlanes(nearZ, farZ);
+	std::memcpy(c.data().lastProjView, c.data().projView, 64);
+	*cam = c.data();
+}
+void rh_camera_look_at(RptCamera* cam, const float t[3]) { Camera c = wrap(cam); c.lookAt(vec3(t[0], t[1], t[2])); *cam = c.data(); }
+void rh_camera_set_film(RptCamera* cam, uint32_t w, uint32_t h) { Camera c = wrap(cam); c.setFilmSize(w, h); *cam = c.data(); }
+void rh_camera_set_planes(RptCamera* cam, float n, float f) { Camera c = wrap(cam); c.setPlanes(n, f); *cam = c.data(); }
+void rh_camera_move(RptCamera* cam, const float d[3]) { Camera c = wrap(cam); c.move(vec3(d[0], d[1], d[2])); *cam = c.data(); }
+void rh_camera_update(RptCamera* cam) { Camera c = wrap(cam); c.update(); *cam = c.data(); }
+void rh_camera_next_frame(RptCamera* cam, uint32_t seed) { Camera c = wrap(cam); c.nextFrame(seed); *cam = c.data(); }
+
+void rh_build_alias_table(const float* power, uint32_t n, RptLightSampleTableElement* out) {
+	auto t = buildAliasTable(std::vector<float>(power, power + n));
+	std::memcpy(out, t.data(), t.size() * sizeof(RptLightSampleTableElement));
+}
+
+RhRenderer* rh_renderer_create(const RhScene* s, uint32_t w, uint32_t h, int dev,
+                               uint32_t rowBegin, uint32_t rowEnd, uint32_t halo) {
+	try {
+		return new RhRenderer{ new Renderer(s->scene, w, h, dev, rowBegin, rowEnd, halo) };
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		return nullptr;
+	}
+}
+void rh_renderer_destroy(RhRenderer* r) { if (r) { delete r->r; delete r; } }
+void rh_renderer_set_methods(RhRenderer* r, int d, int i, int tm, int gamma, int acc) {
+	r->r->settings.directMethod = d; r->r->settings.indirectMethod = i; r->r->settings.toneMapping = tm;
+	r->r->settings.correctGamma = gamma != 0; r->r->settings.accumulate = acc != 0;
+}
+void rh_renderer_set_gris(RhRenderer* r, const RptGRISSettings* st) { r->r->grisSettings = *st; }
+void rh_renderer_set_di(RhRenderer* r, const RptDISettings* st) { r->r->diSettings = *st; }
+void rh_renderer_clear_reservoirs(RhRenderer* r) { r->r->clearReservoirs(); }
+void rh_renderer_camera_move(RhRenderer* r, const float d[3]) { r->r->camera().move(vec3(d[0], d[1], d[2])); }
+void rh_renderer_camera(RhRenderer* r, RptCamera* out) { *out = r->r->camera().data(); }
+void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* user) { r->r->setHaloExchange(fn, user); }
+int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out) {
+	try {
+		r->r->drawFrame(seed, rgba8Out);
+		return 0;
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		return -1;
+	}
+}
+RptFrame* rh_renderer_frame(RhRenderer* r) { return r->r->frame(); }
+RptScene* rh_renderer_scene(RhRenderer* r) { return r->r->deviceScene(); }
+RptCtx* rh_renderer_ctx(RhRenderer* r) { return r->r->ctx(); }
+
+int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h) { return writePNG(path, rgba8, w, h) ? 0 : -1; }
+
+} // extern "C"
