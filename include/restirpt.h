@@ -207,6 +207,19 @@ typedef struct RptBvhStats {
 	float sahCost;
 } RptBvhStats;
 
+/* per-pass device timing (new): CUDA events recorded on the frame's stream around every pass launch */
+typedef enum RptPassId {
+	RPT_PASS_GBUFFER = 0, RPT_PASS_DI_NAIVE = 1, RPT_PASS_GI_NAIVE = 2, RPT_PASS_DI_PATHGEN = 3,
+	RPT_PASS_DI_TEMPORAL = 4, RPT_PASS_DI_SPATIAL = 5, RPT_PASS_GI_RESTIR = 6, RPT_PASS_GRIS_PATHTRACE = 7,
+	RPT_PASS_GRIS_TEMPORAL = 8, RPT_PASS_GRIS_SPATIAL = 9, RPT_PASS_VISUALIZE_AS = 10, RPT_PASS_POSTPROCESS = 11,
+	RPT_PASS_COUNT = 12
+} RptPassId;
+
+typedef struct RptPassStats {
+	double ms[RPT_PASS_COUNT];         /* accumulated device time per pass since rpt_frame_timing(frame, 1) */
+	uint64_t launches[RPT_PASS_COUNT]; /* kernel launches per pass */
+} RptPassStats;
+
 typedef struct RptCtx RptCtx;
 typedef struct RptScene RptScene;
 typedef struct RptFrame RptFrame;
@@ -255,6 +268,10 @@ int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out);
 
 int rpt_sync(RptFrame* f);
 
+/* enable (1) / disable (0) per-pass event timing; enabling resets the accumulators */
+int rpt_frame_timing(RptFrame* f, int enable);
+int rpt_frame_pass_stats(RptFrame* f, RptPassStats* out);   /* implicit sync */
+
 /* ---- read-back / upload of any frame buffer (new; parity tests and multi-GPU halo plumbing) ----------- */
 /* Rows are frame-local storage rows: row 0 is film row max(rowBegin-halo,0). */
 size_t rpt_buffer_stride(RptBufferId id);         /* bytes per pixel */
@@ -262,6 +279,26 @@ int rpt_frame_rows(const RptFrame* f, uint32_t* storageRowBegin, uint32_t* stora
 int rpt_read(RptFrame* f, RptBufferId id, void* dst, size_t bytes);      /* whole storage, implicit sync */
 int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes);
 void* rpt_device_ptr(RptFrame* f, RptBufferId id); /* raw device pointer of the storage (P2P / NCCL halo exchange) */
+
+/* ---- multi-GPU strips (new) ----------------------------------------------------------------
+ * One frame per GPU owns a horizontal strip plus `halo` guard rows.  After rpt_frame_connect_peers the temporal
+ * passes store the reservoirs of their boundary rows straight into the neighbours' halo rows through NVLink peer
+ * memory (CUDA IPC across processes, plain peer access inside one process), and the hand-over is ordered on the
+ * device by epoch flags in peer memory — no host round trip, no collective.  Temporal reuse stays GPU-local. */
+typedef struct RptPeerInfo {
+	uint8_t grisTempHandle[64];   /* cudaIpcMemHandle_t of the GRIS temp reservoir buffer */
+	uint8_t diTempHandle[64];     /* ... of the DI temp reservoir buffer */
+	uint8_t flagsHandle[64];      /* ... of the epoch flags */
+	uint64_t grisTempPtr, diTempPtr, flagsPtr;   /* raw device pointers, used when pid matches */
+	uint64_t pid;
+	int32_t device;
+	uint32_t rowBegin, rowEnd, storeBegin, storeEnd;
+	uint32_t pad[3];
+} RptPeerInfo;
+int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out);
+/* up = the strip above (smaller rows), down = the strip below; NULL at the film edge */
+int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const RptPeerInfo* down);
+int rpt_frame_peer_error(RptFrame* f);   /* non-zero if a device-side hand-over wait timed out */
 
 /* ---- ray queries exposed directly (new; closest-hit primitive-ID parity, traversal microbench) -------- */
 /* rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} floats on the HOST; out: n RptIntersection on the host */

@@ -1,0 +1,152 @@
+"""CPU-side tests (no GPU): host library (Scene / Camera / alias table / OBJ + XML readers / PNG writer) and the
+shape of the C ABI (every symbol include/*.h declares is exported; no compute without a device)."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import restirpt
+from restirpt import Camera, LightSampleTableElement, P
+
+ROOT = restirpt.REPO_ROOT
+
+
+def test_every_declared_symbol_is_exported(built):
+    dev, host = restirpt.device_lib(), restirpt.host_lib()
+    for header, lib, prefix in (("restirpt.h", dev, "rpt_"), ("restirpt_host.h", host, "rh_")):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        names = set(re.findall(r"\b(%s\w+)\s*\(" % prefix, text))
+        assert len(names) > 20
+        for n in sorted(names):
+            assert hasattr(lib, n), f"{n} declared in include/{header} but not exported"
+    table = set(restirpt.DEVICE_API) | set(restirpt.HOST_API)
+    declared = set(re.findall(r"\b(rpt_\w+|rh_\w+)\s*\(", open(os.path.join(ROOT, "include", "restirpt.h")).read() +
+                              open(os.path.join(ROOT, "include", "restirpt_host.h")).read()))
+    assert declared <= table, f"python binding misses {declared - table}"
+
+
+def test_struct_sizes_match_reference_layouts(built):
+    dev = restirpt.device_lib()
+    want = {0: 16, 1: 16, 2: 16, 3: 16, 4: 8, 5: 8, 6: 8, 7: 64, 8: 64, 9: 64, 10: 48, 11: 48, 12: 96, 13: 96, 14: 96, 15: 16}
+    for k, v in want.items():
+        assert dev.rpt_buffer_stride(k) == v
+        assert restirpt.BUF_DTYPE[k].itemsize == v
+    assert C.sizeof(restirpt.GRISSettings) == 20 and C.sizeof(restirpt.DISettings) == 16 and C.sizeof(restirpt.PostSettings) == 16
+
+
+def test_no_device_means_error_not_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    ctx = P()
+    st = restirpt.device_lib().rpt_ctx_create(0, C.byref(ctx))
+    assert st == -2 and not ctx.value
+    assert b"no CPU path" in restirpt.device_lib().rpt_last_error(None)
+    with pytest.raises(restirpt.RestirptError):
+        restirpt.Device(0)
+
+
+def test_alias_table_matches_distribution(built):
+    host = restirpt.host_lib()
+    rng = np.random.default_rng(1)
+    w = rng.random(37).astype(np.float32) ** 3 + 1e-3
+    table = (LightSampleTableElement * (len(w) + 1))()
+    host.rh_build_alias_table(w.ctypes.data_as(C.POINTER(C.c_float)), len(w), table)
+    assert table[0].failId == len(w) and abs(table[0].prob - w.sum()) < 1e-4
+    # exact reconstruction of the probabilities the shader-side lookup realises (light_sampling.glsl:25-30)
+    p = np.zeros(len(w))
+    for i in range(len(w)):
+        prob, fail = table[i + 1].prob, table[i + 1].failId
+        p[i] += min(prob, 1.0) / len(w)
+        if prob < 1.0:
+            assert 1 <= fail <= len(w)
+            p[fail - 1] += (1.0 - prob) / len(w)
+    assert np.allclose(p, w / w.sum(), atol=2e-6)
+
+
+def test_camera_matches_pinhole_projection(built):
+    host = restirpt.host_lib()
+    cam = Camera()
+    host.rh_camera_init(C.byref(cam), (C.c_float * 3)(1.0, -2.0, 0.5), (C.c_float * 3)(30.0, 10.0, 0.0), 45.0, 640, 360, 0.001, 200.0)
+    assert C.sizeof(cam) == 352 and cam.filmSize[0] == 640 and cam.frameIndex == 0
+    front, right, up = (np.array(v[:]) for v in (cam.front, cam.right, cam.up))
+    assert abs(front @ right) < 1e-6 and abs(front @ up) < 1e-6 and abs(np.linalg.norm(front) - 1) < 1e-6
+    # a point seen through pixel uv must project (projView, y flipped like proj[1][1] *= -1) back to uv
+    pv = np.array(cam.projView[:]).reshape(4, 4).T
+    for u, v in [(0.5, 0.5), (0.1, 0.8), (0.9, 0.2)]:
+        ndc = np.array([2 * u - 1, 2 * (1 - v) - 1])
+        t = math.tan(math.radians(22.5))
+        d = right * ndc[0] * (640 / 360) * t + up * ndc[1] * t + front
+        Pw = np.array(cam.pos[:]) + 3.0 * d / np.linalg.norm(d)
+        clip = pv @ np.append(Pw, 1.0)
+        uv = clip[:2] / clip[3] * 0.5 + 0.5
+        assert abs(uv[0] - u) < 1e-4 and abs(uv[1] - v) < 1e-4
+    host.rh_camera_next_frame(C.byref(cam), 99)
+    assert cam.seed == 99 and cam.frameIndex == 1 and cam.lastProjView[:] == cam.projView[:]
+    host.rh_camera_update(C.byref(cam))
+    assert cam.frameIndex == 0
+
+
+def test_procedural_scenes(built):
+    sc = restirpt.HostScene.cornell()
+    assert sc.num_triangles == 36 and sc.desc.numTriangleLights == 2 and sc.desc.numInstances == 7
+    room = restirpt.HostScene.room(3000, 1)
+    assert room.num_triangles > 2500 and room.desc.numTextures == 1
+    field = restirpt.HostScene.field(1, 3, 42)
+    assert field.desc.numInstances == 10
+
+
+def test_xml_and_obj_loader(tmp_path, built):
+    (tmp_path / "models").mkdir()
+    (tmp_path / "models" / "quad.obj").write_text(
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1 4/4/1\n")
+    (tmp_path / "models" / "light.obj").write_text("v 0 0 2\nv 1 0 2\nv 0 1 2\nvn 0 0 -1\nf 1//1 3//1 2//1\n")
+    (tmp_path / "scene.xml").write_text("""<?xml version="1.0"?>
+<scene name="t"><integrator type="path"><size width="64" height="48" /></integrator>
+<camera type="thinLens"><position value="0.5 -3 0.5" /><lookAt value="0.5 0 0.5" /><fov value="40" /></camera>
+<modelInstances>
+ <modelInstance path="models/light.obj" name="l" type="light"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /><radiance value="10 10 10" /></modelInstance>
+ <modelInstance path="models/quad.obj" name="q" type="object"><transform translate="0 0 1" scale="2 2 2" rotate="0 0 0" />
+  <material type="metalWorkflow"><baseColor value="0.5 0.25 0.125" /><metallic value="1.0" /><roughness value="0.3" /></material></modelInstance>
+ <modelInstance path="models/quad.obj" name="plain" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /></modelInstance>
+</modelInstances></scene>""")
+    sc = restirpt.HostScene.xml(str(tmp_path / "scene.xml"))
+    d = sc.desc
+    assert d.numInstances == 2 and d.numTriangleLights == 1 and d.numIndices == 12 and d.numVertices == 8
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), (d.numMaterials, 8))
+    assert d.numMaterials == 3
+    assert np.allclose(mats[0, :3], [1, 0, 1])                       # magenta placeholder (Resource.cpp:36-40)
+    assert np.allclose(mats[1, :3], [0.5, 0.25, 0.125]) and mats[1].view(np.uint32)[3] == 2
+    assert np.allclose(mats[2, :3], [0.6, 0.6, 0.6]) and mats[2].view(np.uint32)[3] == 1   # OBJ default material
+    verts = np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (d.numVertices, 8))
+    assert np.allclose(sorted(verts[:4, 7]), [0, 0, 1, 1])           # FlipUVs: v -> 1 - v
+    light = np.ctypeslib.as_array(C.cast(d.triangleLights, C.POINTER(C.c_float)), (1, 16))[0]
+    assert abs(light[15] - 0.5) < 1e-6 and np.allclose(light[12:15], 20.0)   # radiance = power / area
+    inst = np.ctypeslib.as_array(C.cast(d.instances, C.POINTER(C.c_float)), (2, 56))
+    M = inst[0, :16].reshape(4, 4).T
+    # T * Rx(90 deg) * S(x, z, y): model +y becomes world +z (Model.cpp:11-21)
+    assert np.allclose((M @ [0, 1, 0, 1])[:3], [0, 0, 3], atol=1e-5)
+    cam = sc.camera()
+    assert np.allclose(cam.front[:], [0, 1, 0], atol=1e-5) and cam.filmSize[0] == 64
+
+
+def test_png_writer_roundtrip(tmp_path, built):
+    from PIL import Image
+    img = (np.random.default_rng(0).random((17, 31, 4)) * 255).astype(np.uint8)
+    path = str(tmp_path / "x.png")
+    assert restirpt.host_lib().rh_write_png(path.encode(), img.ctypes.data_as(P), 31, 17) == 0
+    assert np.array_equal(np.asarray(Image.open(path)), img)
+
+
+def test_film_layout_and_partition():
+    import bench
+    from restirpt.multigpu import partition, storage_rows
+    assert bench.film_for(1) == (1920, 1080) and bench.film_for(2) == (1920, 2160)
+    assert bench.film_for(4) == (3840, 2160) and bench.film_for(8) == (3840, 4320)
+    for h, n in [(1080, 1), (2160, 4), (4320, 8), (1081, 4)]:
+        parts = partition(h, n)
+        assert parts[0][0] == 0 and parts[-1][1] == h and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    assert storage_rows(0, 270, 2160, 21) == (0, 291) and storage_rows(270, 540, 2160, 21) == (249, 561)

@@ -9,6 +9,8 @@
 #include "../../include/restirpt.h"
 #include "bvh_build.h"
 #include "passes.h"
+#include "peer_sync.h"
+#include <unistd.h>
 
 #define RPT_API extern "C" __attribute__((visibility("default")))
 
@@ -44,6 +46,51 @@ struct RptFrame {
 	uchar4* rgba8 = nullptr;
 	RptCamera camera{}, prevCamera{};
 	size_t pixels() const { return size_t(width) * (storeEnd - storeBegin); }
+
+	// multi-GPU strips: neighbours' buffers in peer memory + device-side epoch flags (peer_sync.h)
+	uint32_t halo = 0;
+	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
+	struct Peer {
+		bool connected = false, ipc = false;
+		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
+		uint32_t storeBegin = 0;
+	} up, down;
+	uint32_t grisEpoch = 0, diEpoch = 0;
+
+	// per-pass timing
+	struct Pending { int pass; cudaEvent_t a, b; };
+	bool timing = false;
+	std::vector<Pending> pending;
+	std::vector<cudaEvent_t> eventPool;
+	RptPassStats stats{};
+};
+
+static cudaEvent_t takeEvent(RptFrame* f) {
+	if (!f->eventPool.empty()) { cudaEvent_t e = f->eventPool.back(); f->eventPool.pop_back(); return e; }
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+static void drainTiming(RptFrame* f) {
+	for (auto& p : f->pending) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { f->stats.ms[p.pass] += ms; f->stats.launches[p.pass] += 1; }
+		f->eventPool.push_back(p.a); f->eventPool.push_back(p.b);
+	}
+	f->pending.clear();
+}
+struct PassTimer {
+	RptFrame* f; int pass; cudaEvent_t a = nullptr, b = nullptr;
+	PassTimer(RptFrame* f_, int pass_) : f(f_), pass(pass_) {
+		if (f->timing) { a = takeEvent(f); b = takeEvent(f); cudaEventRecord(a, f->stream); }
+	}
+	~PassTimer() {
+		if (f->timing) {
+			cudaEventRecord(b, f->stream);
+			f->pending.push_back({ pass, a, b });
+			if (f->pending.size() >= 4096) { cudaStreamSynchronize(f->stream); drainTiming(f); }
+		}
+	}
 };
 
 static thread_local std::string gThreadError;
@@ -250,6 +297,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	f->width = fullWidth; f->height = fullHeight; f->rowBegin = rowBegin; f->rowEnd = rowEnd;
 	f->storeBegin = rowBegin > halo ? rowBegin - halo : 0;
 	f->storeEnd = std::min(fullHeight, rowEnd + halo);
+	f->halo = halo;
 	cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { delete f; return cudaFail(ctx, e, "cudaStreamCreate"); }
 	auto slots = frameSlots(f);
@@ -257,6 +305,9 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		e = cudaMalloc(slots[i], f->pixels() * kSlotStride[i]);
 		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc frame buffer"); }
 	}
+	e = cudaMalloc(&f->flags, PeerFlagCount * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMemset(f->flags, 0, PeerFlagCount * sizeof(uint32_t));
+	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc peer flags"); }
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
 	CU(ctx, cudaStreamSynchronize(f->stream));
@@ -268,7 +319,13 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device);
 	if (f->stream) cudaStreamSynchronize(f->stream);
+	for (RptFrame::Peer* p : { &f->up, &f->down }) {
+		if (p->connected && p->ipc) { cudaIpcCloseMemHandle(p->grisTemp); cudaIpcCloseMemHandle(p->diTemp); cudaIpcCloseMemHandle(p->flags); }
+	}
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
+	if (f->flags) cudaFree(f->flags);
+	drainTiming(f);
+	for (cudaEvent_t e : f->eventPool) cudaEventDestroy(e);
 	if (f->stream) cudaStreamDestroy(f->stream);
 	delete f;
 }
@@ -306,6 +363,14 @@ static FrameView makeView(RptFrame* f) {
 	v.grisThis = f->gris[c]; v.grisPrev = f->gris[p]; v.grisTemp = f->grisTemp;
 	v.primaryIsec = f->primaryIsec;
 	v.camera = f->camera; v.prevCamera = f->prevCamera;
+	v.halo = f->halo;
+	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
+	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
+	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;
+	v.peerUpStoreBegin = f->up.storeBegin;
+	v.peerGrisDown = f->down.connected ? f->down.grisTemp : nullptr;
+	v.peerDiDown = f->down.connected ? f->down.diTemp : nullptr;
+	v.peerDownStoreBegin = f->down.storeBegin;
 	return v;
 }
 
@@ -323,30 +388,77 @@ static SceneView sceneView(const RptScene* s) {
 	CU(f->ctx, cudaGetLastError()); \
 	return RPT_OK;
 
-RPT_API int rpt_gbuffer(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gbuffer") launchGBuffer(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gbuffer") }
-RPT_API int rpt_di_naive(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_di_naive") launchDINaive(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_di_naive") }
-RPT_API int rpt_gi_naive(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gi_naive") launchGINaive(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gi_naive") }
-RPT_API int rpt_gi_restir(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_gi_restir") launchGIReSTIR(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_gi_restir") }
-RPT_API int rpt_visualize_as(RptFrame* f, const RptScene* s) { PASS_PROLOGUE("rpt_visualize_as") launchVisualizeAS(makeView(f), sceneView(s), f->stream); PASS_EPILOGUE("rpt_visualize_as") }
+#define SIMPLE_PASS(fn, passId, launcher) \
+	RPT_API int fn(RptFrame* f, const RptScene* s) { \
+		PASS_PROLOGUE(#fn) \
+		{ PassTimer timer(f, passId); launcher(makeView(f), sceneView(s), f->stream); } \
+		PASS_EPILOGUE(#fn) \
+	}
+SIMPLE_PASS(rpt_gbuffer, RPT_PASS_GBUFFER, launchGBuffer)
+SIMPLE_PASS(rpt_di_naive, RPT_PASS_DI_NAIVE, launchDINaive)
+SIMPLE_PASS(rpt_gi_naive, RPT_PASS_GI_NAIVE, launchGINaive)
+SIMPLE_PASS(rpt_gi_restir, RPT_PASS_GI_RESTIR, launchGIReSTIR)
+SIMPLE_PASS(rpt_visualize_as, RPT_PASS_VISUALIZE_AS, launchVisualizeAS)
 
-#define SETTINGS_PASS(fn, T, launcher) \
+// hand-over hooks around the temporal / spatial passes of a striped frame (no-ops without connected peers)
+enum PeerHook { HookNone, HookGrisTemporal, HookGrisSpatial, HookDiTemporal, HookDiSpatial };
+static void peerBefore(RptFrame* f, PeerHook h) {
+	if (!f->up.connected && !f->down.connected) return;
+	uint32_t* err = f->flags + PeerError;
+	const uint32_t* fromUp = f->up.connected ? f->flags : nullptr;
+	const uint32_t* fromDown = f->down.connected ? f->flags : nullptr;
+	switch (h) {
+	case HookGrisTemporal:   // neighbours must have finished reading the halo rows written last frame
+		f->grisEpoch++;
+		launchPeerWait(fromUp ? fromUp + GrisSpatialFromUp : nullptr, fromDown ? fromDown + GrisSpatialFromDown : nullptr, f->grisEpoch - 1, err, f->stream);
+		break;
+	case HookGrisSpatial:    // neighbours' boundary rows of this frame must have landed in our halo rows
+		launchPeerWait(fromUp ? fromUp + GrisTemporalFromUp : nullptr, fromDown ? fromDown + GrisTemporalFromDown : nullptr, f->grisEpoch, err, f->stream);
+		break;
+	case HookDiTemporal:
+		f->diEpoch++;
+		launchPeerWait(fromUp ? fromUp + DiSpatialFromUp : nullptr, fromDown ? fromDown + DiSpatialFromDown : nullptr, f->diEpoch - 1, err, f->stream);
+		break;
+	case HookDiSpatial:
+		launchPeerWait(fromUp ? fromUp + DiTemporalFromUp : nullptr, fromDown ? fromDown + DiTemporalFromDown : nullptr, f->diEpoch, err, f->stream);
+		break;
+	default: break;
+	}
+}
+static void peerAfter(RptFrame* f, PeerHook h) {
+	if (!f->up.connected && !f->down.connected) return;
+	// we are the "down" neighbour of the strip above and the "up" neighbour of the strip below
+	uint32_t* toUp = f->up.connected ? f->up.flags : nullptr;
+	uint32_t* toDown = f->down.connected ? f->down.flags : nullptr;
+	switch (h) {
+	case HookGrisTemporal: launchPeerSignal(toUp ? toUp + GrisTemporalFromDown : nullptr, toDown ? toDown + GrisTemporalFromUp : nullptr, f->grisEpoch, f->stream); break;
+	case HookGrisSpatial: launchPeerSignal(toUp ? toUp + GrisSpatialFromDown : nullptr, toDown ? toDown + GrisSpatialFromUp : nullptr, f->grisEpoch, f->stream); break;
+	case HookDiTemporal: launchPeerSignal(toUp ? toUp + DiTemporalFromDown : nullptr, toDown ? toDown + DiTemporalFromUp : nullptr, f->diEpoch, f->stream); break;
+	case HookDiSpatial: launchPeerSignal(toUp ? toUp + DiSpatialFromDown : nullptr, toDown ? toDown + DiSpatialFromUp : nullptr, f->diEpoch, f->stream); break;
+	default: break;
+	}
+}
+
+#define SETTINGS_PASS(fn, T, passId, launcher, hook) \
 	RPT_API int fn(RptFrame* f, const RptScene* s, const T* st) { \
 		PASS_PROLOGUE(#fn) \
 		if (!st) return fail(f->ctx, RPT_ERR_INVALID, #fn ": NULL settings"); \
-		launcher(makeView(f), sceneView(s), *st, f->stream); \
+		peerBefore(f, hook); \
+		{ PassTimer timer(f, passId); launcher(makeView(f), sceneView(s), *st, f->stream); } \
+		peerAfter(f, hook); \
 		PASS_EPILOGUE(#fn) \
 	}
-SETTINGS_PASS(rpt_di_pathgen, RptDISettings, launchDIPathGen)
-SETTINGS_PASS(rpt_di_temporal, RptDISettings, launchDITemporal)
-SETTINGS_PASS(rpt_di_spatial, RptDISettings, launchDISpatial)
-SETTINGS_PASS(rpt_gris_pathtrace, RptGRISSettings, launchGRISPathTrace)
-SETTINGS_PASS(rpt_gris_temporal, RptGRISSettings, launchGRISTemporal)
-SETTINGS_PASS(rpt_gris_spatial, RptGRISSettings, launchGRISSpatial)
+SETTINGS_PASS(rpt_di_pathgen, RptDISettings, RPT_PASS_DI_PATHGEN, launchDIPathGen, HookNone)
+SETTINGS_PASS(rpt_di_temporal, RptDISettings, RPT_PASS_DI_TEMPORAL, launchDITemporal, HookDiTemporal)
+SETTINGS_PASS(rpt_di_spatial, RptDISettings, RPT_PASS_DI_SPATIAL, launchDISpatial, HookDiSpatial)
+SETTINGS_PASS(rpt_gris_pathtrace, RptGRISSettings, RPT_PASS_GRIS_PATHTRACE, launchGRISPathTrace, HookNone)
+SETTINGS_PASS(rpt_gris_temporal, RptGRISSettings, RPT_PASS_GRIS_TEMPORAL, launchGRISTemporal, HookGrisTemporal)
+SETTINGS_PASS(rpt_gris_spatial, RptGRISSettings, RPT_PASS_GRIS_SPATIAL, launchGRISSpatial, HookGrisSpatial)
 
 RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
 	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
-	launchPostProcess(makeView(f), *st, f->rgba8, f->stream);
+	{ PassTimer timer(f, RPT_PASS_POSTPROCESS); launchPostProcess(makeView(f), *st, f->rgba8, f->stream); }
 	CU(f->ctx, cudaGetLastError());
 	if (rgba8Out) {
 		CU(f->ctx, cudaMemcpyAsync(rgba8Out, f->rgba8, size_t(f->width) * (f->rowEnd - f->rowBegin) * 4, cudaMemcpyDeviceToHost, f->stream));
@@ -359,6 +471,25 @@ RPT_API int rpt_sync(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_sync: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_timing(RptFrame* f, int enable) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_timing: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	drainTiming(f);
+	f->timing = enable != 0;
+	if (enable) f->stats = RptPassStats{};
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_pass_stats(RptFrame* f, RptPassStats* out) {
+	if (!f || !out) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_pass_stats: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	drainTiming(f);
+	*out = f->stats;
 	return RPT_OK;
 }
 
@@ -389,6 +520,73 @@ RPT_API int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes
 }
 
 RPT_API void* rpt_device_ptr(RptFrame* f, RptBufferId id) { return f ? framePtr(f, id) : nullptr; }
+
+// ---- multi-GPU strips ------------------------------------------------------------------------------------------
+RPT_API int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out) {
+	if (!f || !out) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_export_peer: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	std::memset(out, 0, sizeof(*out));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->grisTempHandle), f->grisTemp));
+	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->diTempHandle), f->diTemp));
+	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->flagsHandle), f->flags));
+	out->grisTempPtr = reinterpret_cast<uint64_t>(f->grisTemp);
+	out->diTempPtr = reinterpret_cast<uint64_t>(f->diTemp);
+	out->flagsPtr = reinterpret_cast<uint64_t>(f->flags);
+	out->pid = uint64_t(getpid());
+	out->device = f->ctx->device;
+	out->rowBegin = f->rowBegin; out->rowEnd = f->rowEnd; out->storeBegin = f->storeBegin; out->storeEnd = f->storeEnd;
+	return RPT_OK;
+}
+
+static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
+	p = RptFrame::Peer{};
+	if (!info) return RPT_OK;
+	if (info->pid == uint64_t(getpid())) {
+		// same process: plain pointers, peer access enabled when the neighbour lives on another device
+		if (info->device != f->ctx->device) {
+			int can = 0;
+			CU(f->ctx, cudaDeviceCanAccessPeer(&can, f->ctx->device, info->device));
+			if (!can) return fail(f->ctx, RPT_ERR_UNSUPPORTED, "rpt_frame_connect_peers: no peer access between the two devices");
+			cudaError_t e = cudaDeviceEnablePeerAccess(info->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(f->ctx, e, "cudaDeviceEnablePeerAccess");
+			cudaGetLastError();
+		}
+		p.grisTemp = reinterpret_cast<RptGRISReservoir*>(info->grisTempPtr);
+		p.diTemp = reinterpret_cast<RptDIReservoir*>(info->diTempPtr);
+		p.flags = reinterpret_cast<uint32_t*>(info->flagsPtr);
+	}
+	else {
+		void *a = nullptr, *b = nullptr, *c = nullptr;
+		CU(f->ctx, cudaIpcOpenMemHandle(&a, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->grisTempHandle), cudaIpcMemLazyEnablePeerAccess));
+		CU(f->ctx, cudaIpcOpenMemHandle(&b, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->diTempHandle), cudaIpcMemLazyEnablePeerAccess));
+		CU(f->ctx, cudaIpcOpenMemHandle(&c, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->flagsHandle), cudaIpcMemLazyEnablePeerAccess));
+		p.grisTemp = static_cast<RptGRISReservoir*>(a); p.diTemp = static_cast<RptDIReservoir*>(b); p.flags = static_cast<uint32_t*>(c);
+		p.ipc = true;
+	}
+	p.storeBegin = info->storeBegin;
+	p.connected = true;
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const RptPeerInfo* down) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_connect_peers: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	if (up && (up->rowEnd != f->rowBegin || up->storeEnd < f->rowBegin + f->halo)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: `up` is not the strip directly above with a matching halo");
+	if (down && (down->rowBegin != f->rowEnd || down->storeBegin + f->halo > f->rowEnd)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: `down` is not the strip directly below with a matching halo");
+	int r = connectOne(f, f->up, up);
+	if (r != RPT_OK) return r;
+	return connectOne(f, f->down, down);
+}
+
+RPT_API int rpt_frame_peer_error(RptFrame* f) {
+	if (!f) return 1;
+	cudaSetDevice(f->ctx->device);
+	uint32_t e = 0;
+	if (cudaStreamSynchronize(f->stream) != cudaSuccess) return 1;
+	if (cudaMemcpy(&e, f->flags + PeerError, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+	return int(e);
+}
 
 // ---- raw ray queries ------------------------------------------------------------------------------------------
 static int traceCommon(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out, uint8_t* occ) {

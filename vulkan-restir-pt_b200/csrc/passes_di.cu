@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) diTemporalKernel(const
 	diCap(resv, 40);
 	resv.resetIfInvalid();
 	storeDI(f.diTemp + idx, resv);
+	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
+	if (f.peerDiUp != nullptr && y < f.rowBegin + f.halo) storeDI(f.peerDiUp + (size_t(y - f.peerUpStoreBegin) * f.width + x), resv);
+	if (f.peerDiDown != nullptr && y + f.halo >= f.rowEnd) storeDI(f.peerDiDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
 }
 
 __global__ void __launch_bounds__(PassBlockX* PassBlockY) diSpatialKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptDISettings st) {

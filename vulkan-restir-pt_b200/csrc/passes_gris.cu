@@ -402,6 +402,9 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisTemporalKernel(con
 	}
 	if (!resv.valid()) resv.reset();
 	storeGRIS(f.grisTemp + idx, resv);
+	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
+	if (f.peerGrisUp != nullptr && y < f.rowBegin + f.halo) storeGRIS(f.peerGrisUp + (size_t(y - f.peerUpStoreBegin) * f.width + x), resv);
+	if (f.peerGrisDown != nullptr && y + f.halo >= f.rowEnd) storeGRIS(f.peerGrisDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
 }
 
 // gris_resample_spatial.comp -> spatialReuse

@@ -71,6 +71,13 @@ struct FrameView {
 	RptIntersection* primaryIsec;
 	RptCamera camera, prevCamera;
 
+	// multi-GPU strips: the neighbours' temp reservoir buffers in peer memory (nullptr at a film edge / single GPU)
+	uint32_t halo;
+	uint32_t peerUpStoreBegin, peerDownStoreBegin;
+	RptGRISReservoir* peerGrisUp;  RptGRISReservoir* peerGrisDown;
+	RptDIReservoir* peerDiUp;      RptDIReservoir* peerDiDown;
+	bool striped;                 // true when this frame is one strip of a larger film
+
 	__device__ __forceinline__ size_t index(uint32_t x, uint32_t y) const { return size_t(y - storeBegin) * width + x; }
 };
 

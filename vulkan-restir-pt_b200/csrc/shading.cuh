@@ -413,8 +413,9 @@ RT_DEV Neighbor lookupSurface(const FrameView& f, bool previousFrame, float2 uv)
 	int px = int(uv.x * float(f.width)), py = int(uv.y * float(f.height));
 	if (px > int(f.width) - 1) px = int(f.width) - 1;
 	if (py > int(f.height) - 1) py = int(f.height) - 1;
-	// multi-GPU strips: a lookup that leaves the stored rows fails (documented deviation)
-	if (py < int(f.storeBegin) || py >= int(f.storeEnd)) return nb;
+	// multi-GPU strips: previous-frame reservoirs exist for the owned rows only (temporal
+	// reuse stays GPU-local), current-frame ones for owned + halo rows; a lookup outside fails
+	if (previousFrame ? (py < int(f.rowBegin) || py >= int(f.rowEnd)) : (py < int(f.storeBegin) || py >= int(f.storeEnd))) return nb;
 	const float4 dn = fetchDepthNormalBilinear(f, previousFrame ? f.depthNormalPrev : f.depthNormal, uv);
 	nb.depth = dn.x;
 	if (nb.depth == 0.0f) return nb;

@@ -94,6 +94,21 @@ class Counters(C.Structure):
                 ("triTests", C.c_uint64), ("shadedHits", C.c_uint64)]
 
 
+class PeerInfo(C.Structure):
+    _fields_ = [("grisTempHandle", C.c_uint8 * 64), ("diTempHandle", C.c_uint8 * 64), ("flagsHandle", C.c_uint8 * 64),
+                ("grisTempPtr", C.c_uint64), ("diTempPtr", C.c_uint64), ("flagsPtr", C.c_uint64), ("pid", C.c_uint64),
+                ("device", C.c_int32), ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32), ("storeBegin", C.c_uint32),
+                ("storeEnd", C.c_uint32), ("pad", C.c_uint32 * 3)]
+
+
+class PassStats(C.Structure):
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12)]
+
+
+PASS_NAMES = ["gbuffer", "di_naive", "gi_naive", "di_pathgen", "di_temporal", "di_spatial", "gi_restir",
+              "gris_pathtrace", "gris_temporal", "gris_spatial", "visualize_as", "postprocess"]
+
+
 class BvhStats(C.Structure):
     _fields_ = [("numTriangles", C.c_uint32), ("numNodes", C.c_uint32), ("nodeBytes", C.c_uint64),
                 ("triBytes", C.c_uint64), ("buildMs", C.c_float), ("sahCost", C.c_float)]
@@ -168,6 +183,11 @@ DEVICE_API = {
     "rpt_visualize_as": (C.c_int, [P, P]),
     "rpt_postprocess": (C.c_int, [P, C.POINTER(PostSettings), P]),
     "rpt_sync": (C.c_int, [P]),
+    "rpt_frame_export_peer": (C.c_int, [P, C.POINTER(PeerInfo)]),
+    "rpt_frame_connect_peers": (C.c_int, [P, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
+    "rpt_frame_peer_error": (C.c_int, [P]),
+    "rpt_frame_timing": (C.c_int, [P, C.c_int]),
+    "rpt_frame_pass_stats": (C.c_int, [P, C.POINTER(PassStats)]),
     "rpt_buffer_stride": (C.c_size_t, [C.c_int]),
     "rpt_frame_rows": (C.c_int, [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rpt_read": (C.c_int, [P, C.c_int, P, C.c_size_t]),
