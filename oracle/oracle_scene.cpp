@@ -176,6 +176,13 @@ static inline bool hitBox(const Scene::Node& n, const double o[3], const double 
 	return t0 <= t1 * 1.0000001 + 1e-9;
 }
 
+// NaN / infinite rays and empty intervals cannot pass the triangle test (all comparisons on NaN are false); the
+// accelerated paths skip them instead of walking the whole tree (the NaN-blind slab test would accept every box).
+// The brute-force path keeps testing every triangle, which proves the equivalence in the tests.
+static inline bool degenerateRay(vec3 o, float tmin, vec3 d, float tmax) {
+	return !(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f);
+}
+
 Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool skipLights) const {
 	counters.closestRays.fetch_add(1, std::memory_order_relaxed);
 	Intersection best;
@@ -204,7 +211,7 @@ Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool
 		for (uint32_t i = 0; i < tris.size(); i++) test(i);
 		return best;
 	}
-	if (tris.empty()) return best;
+	if (tris.empty() || degenerateRay(o, tmin, d, tmax)) return best;
 	const double od[3] = { o.x, o.y, o.z };
 	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
 	uint32_t stack[128];
@@ -231,7 +238,7 @@ bool Scene::traceShadow(vec3 o, float tmin, vec3 d, float tmax) const {
 		for (const WorldTri& t : tris) if (intersectTri(t, o, d, tmin, tmax, tt, u, v)) return true;
 		return false;
 	}
-	if (tris.empty()) return false;
+	if (tris.empty() || degenerateRay(o, tmin, d, tmax)) return false;
 	const double od[3] = { o.x, o.y, o.z };
 	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
 	uint32_t stack[128];
@@ -258,7 +265,7 @@ uint32_t Scene::countCandidates(vec3 o, vec3 d) const {
 	float tt, u, v;
 	const double od[3] = { o.x, o.y, o.z };
 	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
-	if (tris.empty()) return 0;
+	if (tris.empty() || degenerateRay(o, MinRayDistance, d, MaxRayDistance)) return 0;
 	uint32_t stack[128];
 	int sp = 0;
 	stack[sp++] = 0;

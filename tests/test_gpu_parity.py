@@ -148,3 +148,21 @@ def test_visualize_as(pair):
         b.set_camera(cam, cam)
         b.run("visualize_as")
     assert bitwise_mismatch(gpu.read("DIRECT_OUTPUT"), cpu.read("DIRECT_OUTPUT")) == 0
+
+
+def test_degenerate_rays_are_misses(pair):
+    """NaN / infinite / zero-length / empty-interval rays: both sides answer 'no hit' (the oracle's brute-force
+    path, which has no early-out, proves that this is what the triangle test itself yields)"""
+    name, sc, gpu, cpu = pair
+    rng = np.random.default_rng(17)
+    rays = random_rays(rng, 64, -1.0, 1.0)
+    nan, inf = np.float32("nan"), np.float32("inf")
+    rays[0, 0] = nan; rays[1, 5] = nan; rays[2, 4:7] = 0.0; rays[3, 3], rays[3, 7] = 5.0, 1.0
+    rays[4, 1] = inf; rays[5, 6] = -inf; rays[6, 7] = nan; rays[7, 0:3] = nan; rays[7, 4:7] = nan
+    a, b = gpu.trace_closest(rays), cpu.trace_closest(rays)
+    cpu.lib.orc_scene_set_brute_force(cpu.scene, 1)
+    c = cpu.trace_closest(rays)
+    cpu.lib.orc_scene_set_brute_force(cpu.scene, 0)
+    assert np.array_equal(a["instanceIdx"], b["instanceIdx"]) and np.array_equal(b["instanceIdx"], c["instanceIdx"])
+    assert (a["instanceIdx"][[0, 1, 3, 4, 5, 6, 7]] == 0xffffffff).all()
+    assert np.array_equal(gpu.trace_shadow(rays), cpu.trace_shadow(rays))

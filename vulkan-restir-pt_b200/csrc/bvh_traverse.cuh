@@ -61,6 +61,16 @@ RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tm
 	uint32_t bestFlat = 0xffffffffu;
 	uint32_t nodeVisits = 0, triTests = 0, count = 0;
 
+	// A ray with a NaN / infinite component or an empty interval can never satisfy the triangle test (every
+	// comparison on NaN is false).  Without this early-out such a ray would walk the whole tree: fmaxf/fminf drop
+	// NaN operands, so every slab test would pass.  The shaders do produce such rays now and then (e.g.
+	// sqrt(1 - |uv|^2) of a disk sample that rounds to |uv| > 1); the result is a miss either way.
+	if (!(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f)) {
+		if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+		if (MODE == TraceCount && candidateCount) *candidateCount = 0;
+		return best;
+	}
+
 	// reciprocal direction; components too close to zero are pushed away from it so 1/d stays finite
 	const float tiny = 1e-20f;
 	float idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));

@@ -275,12 +275,17 @@ static std::vector<void**> frameSlots(RptFrame* f) {
 	         (void**)&f->primaryIsec, (void**)&f->rgba8 };
 }
 static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
+// the two depthNormal images carry two extra rows (film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
+static size_t slotBytes(const RptFrame* f, size_t i) {
+	const size_t extra = (i == 2 || i == 3) ? 2 * size_t(f->width) : 0;
+	return (f->pixels() + extra) * kSlotStride[i];
+}
 
 RPT_API int rpt_frame_clear(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_clear: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	auto slots = frameSlots(f);
-	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, f->pixels() * kSlotStride[i], f->stream));
+	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, slotBytes(f, i), f->stream));
 	f->cur = 0;
 	return RPT_OK;
 }
@@ -302,7 +307,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	if (e != cudaSuccess) { delete f; return cudaFail(ctx, e, "cudaStreamCreate"); }
 	auto slots = frameSlots(f);
 	for (size_t i = 0; i < slots.size(); i++) {
-		e = cudaMalloc(slots[i], f->pixels() * kSlotStride[i]);
+		e = cudaMalloc(slots[i], slotBytes(f, i));
 		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc frame buffer"); }
 	}
 	e = cudaMalloc(&f->flags, PeerFlagCount * sizeof(uint32_t));

@@ -11,18 +11,35 @@ namespace rt {
 
 __global__ void __launch_bounds__(PassBlockX* PassBlockY) gbufferKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s) {
 	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
-	const uint32_t y = f.storeBegin + blockIdx.y * PassBlockY + threadIdx.y;
-	if (x >= f.width || y >= f.storeEnd) return;
-	const size_t i = f.index(x, y);
+	uint32_t y = f.storeBegin + blockIdx.y * PassBlockY + threadIdx.y;
+	if (x >= f.width) return;
+	// two extra rows behind the stored ones: film rows 0 and H-1 of a strip that does not own them (depth/normal only,
+	// for REPEAT-wrapped bilinear taps; see depthNormalRow)
+	bool wrapRowOnly = false;
+	size_t i;
+	if (y >= f.storeEnd) {
+		const uint32_t extra = y - f.storeEnd;
+		if (extra > 1u) return;
+		y = extra == 0u ? 0u : f.height - 1u;
+		if (y >= f.storeBegin && y < f.storeEnd) return;   // already stored
+		wrapRowOnly = true;
+		i = size_t(f.storeEnd - f.storeBegin + extra) * f.width + x;
+	}
+	else {
+		i = f.index(x, y);
+	}
 	const RptCamera& cam = f.camera;
 	const float2 uv = make_float2((float(x) + 0.5f) / float(f.width), (float(y) + 0.5f) / float(f.height));
 	const Ray ray = pinholeCameraSampleRay(cam, make_float2(uv.x, 1.0f - uv.y));
 	const Hit h = traceRay<TraceClosestNoLights>(s, ray.ori, cam.nearZ, ray.dir, MaxRayDistance);
-	RptIntersection pi;
-	pi.bary[0] = h.u; pi.bary[1] = h.v; pi.instanceIdx = h.instanceIdx; pi.triangleIdx = h.triangleIdx;
-	f.primaryIsec[i] = pi;
+	if (!wrapRowOnly) {
+		RptIntersection pi;
+		pi.bary[0] = h.u; pi.bary[1] = h.v; pi.instanceIdx = h.instanceIdx; pi.triangleIdx = h.triangleIdx;
+		f.primaryIsec[i] = pi;
+	}
 	if (h.instanceIdx == InvalidHitIndex) {
 		f.depthNormal[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (wrapRowOnly) return;
 		f.albedoMatId[i] = make_uint2(0u, 0u);
 		f.motion[i] = make_float2(0.f, 0.f);
 		return;
@@ -42,6 +59,10 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) gbufferKernel(const __
 	const float3 n1 = normalize(xformDir(inst->transformInvT, f3(q1)));
 	const float3 n2 = normalize(xformDir(inst->transformInvT, f3(q2)));
 	const float3 N = normalize(interp(n0, n1, n2, bary));
+	if (wrapRowOnly) {
+		f.depthNormal[i] = make_float4(length(f3(cam.pos) - P), N.x, N.y, N.z);
+		return;
+	}
 	const float uvx = interp(p0.w, p1.w, p2.w, bary), uvy = interp(q0.w, q1.w, q2.w, bary);
 	const Mat mat = loadMaterial(s, matIndex);
 	const float3 albedo = (mat.textureIdx == InvalidResourceIdx) ? mat.baseColor : sampleTexture(s, mat.textureIdx, uvx, uvy);
@@ -110,7 +131,8 @@ __global__ void __launch_bounds__(128) traceRaysKernel(const __grid_constant__ S
 }
 
 void launchGBuffer(const FrameView& f, const SceneView& s, cudaStream_t st) {
-	gbufferKernel<<<passGrid(f.width, f.storeEnd - f.storeBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s);
+	const uint32_t extraRows = f.striped ? 2u : 0u;
+	gbufferKernel<<<passGrid(f.width, f.storeEnd - f.storeBegin + extraRows), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s);
 }
 void launchVisualizeAS(const FrameView& f, const SceneView& s, cudaStream_t st) {
 	visualizeASKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s);

@@ -338,10 +338,15 @@ RT_DEV float3 unpackAlbedo(uint32_t p) {
 	return make_float3(float(p & 0xffu) / 255.0f, float((p >> 8) & 0xffu) / 255.0f, float((p >> 16) & 0xffu) / 255.0f);
 }
 
-// rows outside the stored strip (multi-GPU frames only) clamp to the nearest stored row
-RT_DEV uint32_t storedRow(const FrameView& f, int y) {
-	const int lo = int(f.storeBegin), hi = int(f.storeEnd) - 1;
-	return uint32_t(y < lo ? lo : (y > hi ? hi : y));
+// storage row of film row y in the depthNormal images.  A strip of a multi-GPU film additionally keeps film rows 0
+// and H-1 in two extra rows behind its stored rows, because REPEAT addressing lets a bilinear tap at the top / bottom
+// edge of the film wrap around to the other side (reference sampler: zvk/core/Memory.cpp:75-92).
+RT_DEV uint32_t depthNormalRow(const FrameView& f, int y) {
+	const int lo = int(f.storeBegin), hi = int(f.storeEnd);
+	if (y >= lo && y < hi) return uint32_t(y - lo);
+	if (y == 0) return uint32_t(hi - lo);
+	if (y == int(f.height) - 1) return uint32_t(hi - lo) + 1u;
+	return uint32_t((y < lo ? lo : hi - 1) - lo);   // not reachable for lookups within the halo
 }
 
 // texture(uDepthNormal*, uv): bilinear, REPEAT, 8-bit weights
@@ -352,8 +357,8 @@ RT_DEV float4 fetchDepthNormalBilinear(const FrameView& f, const float4* __restr
 	const float ax = floorf((x - fx) * 256.0f + 0.5f) * 0.00390625f;
 	const float ay = floorf((y - fy) * 256.0f + 0.5f) * 0.00390625f;
 	const int x0 = wrapRepeat(int(fx), W), x1 = wrapRepeat(int(fx) + 1, W);
-	const uint32_t y0 = storedRow(f, wrapRepeat(int(fy), H)), y1 = storedRow(f, wrapRepeat(int(fy) + 1, H));
-	const float4 a = img[f.index(x0, y0)], b = img[f.index(x1, y0)], c = img[f.index(x0, y1)], d = img[f.index(x1, y1)];
+	const size_t r0 = size_t(depthNormalRow(f, wrapRepeat(int(fy), H))) * f.width, r1 = size_t(depthNormalRow(f, wrapRepeat(int(fy) + 1, H))) * f.width;
+	const float4 a = img[r0 + x0], b = img[r0 + x1], c = img[r1 + x0], d = img[r1 + x1];
 	auto lerp2 = [&](float p, float q, float r, float t) {
 		const float top = p * (1.0f - ax) + q * ax;
 		const float bot = r * (1.0f - ax) + t * ax;
