@@ -1,0 +1,7 @@
+#!/bin/bash
+# quick GPU iteration: parity tests + per-pass timing (development aid)
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 300 python tools/gpu_quick.py 1920 1080 ajar 30 > gpurun_out/quick_ajar.log 2>&1
+tail -4 gpurun_out/pytest_gpu.log; cat gpurun_out/quick_ajar.log

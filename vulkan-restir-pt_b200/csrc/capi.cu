@@ -50,6 +50,7 @@ struct RptFrame {
 	// multi-GPU strips: neighbours' buffers in peer memory + device-side epoch flags (peer_sync.h)
 	uint32_t halo = 0;
 	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
+	uint32_t* work = nullptr;                  // WorkCounterCount queue heads of the persistent kernels
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
@@ -313,6 +314,9 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	e = cudaMalloc(&f->flags, PeerFlagCount * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(f->flags, 0, PeerFlagCount * sizeof(uint32_t));
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc peer flags"); }
+	e = cudaMalloc(&f->work, WorkCounterCount * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMemset(f->work, 0, WorkCounterCount * sizeof(uint32_t));
+	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc work counters"); }
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
 	CU(ctx, cudaStreamSynchronize(f->stream));
@@ -329,6 +333,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	}
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
+	if (f->work) cudaFree(f->work);
 	drainTiming(f);
 	for (cudaEvent_t e : f->eventPool) cudaEventDestroy(e);
 	if (f->stream) cudaStreamDestroy(f->stream);
@@ -369,6 +374,7 @@ static FrameView makeView(RptFrame* f) {
 	v.primaryIsec = f->primaryIsec;
 	v.camera = f->camera; v.prevCamera = f->prevCamera;
 	v.halo = f->halo;
+	v.work = f->work;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
 	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;

@@ -25,4 +25,13 @@ inline dim3 passGrid(uint32_t width, uint32_t rows) {
 	return dim3((width + PassBlockX - 1) / PassBlockX, (rows + PassBlockY - 1) / PassBlockY, 1);
 }
 
+// grid of a persistent kernel: every SM filled to the kernel's occupancy limit (148 SMs on B200)
+inline int persistentBlocks(const void* kernel, int blockSize) {
+	int dev = 0, sms = 0, perSm = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, blockSize, 0);
+	return (sms > 0 ? sms : 148) * (perSm > 0 ? perSm : 1);
+}
+
 } // namespace rt

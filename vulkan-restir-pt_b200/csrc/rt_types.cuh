@@ -11,6 +11,7 @@ constexpr uint32_t SpecialHitIndex = 0xfffffffeu;
 constexpr uint32_t InvalidResourceIdx = 0xffffffffu;
 constexpr float MinRayDistance = 1e-4f;
 constexpr float MaxRayDistance = 1e7f;
+constexpr int WorkCounterCount = 16;
 constexpr float BaryEps = 1e-4f;   // tolerance of the triangle test, see bvh_traverse.cuh
 
 // 80-byte compressed 8-wide BVH node (Ylitie, Karras, Laine 2017): child boxes quantised to 8 bits relative
@@ -77,6 +78,7 @@ struct FrameView {
 	RptGRISReservoir* peerGrisUp;  RptGRISReservoir* peerGrisDown;
 	RptDIReservoir* peerDiUp;      RptDIReservoir* peerDiDown;
 	bool striped;                 // true when this frame is one strip of a larger film
+	uint32_t* work;               // work-queue heads of the persistent kernels (WorkCounterCount words)
 
 	__device__ __forceinline__ size_t index(uint32_t x, uint32_t y) const { return size_t(y - storeBegin) * width + x; }
 };
