@@ -305,6 +305,12 @@ int rpt_frame_peer_error(RptFrame* f);   /* non-zero if a device-side hand-over 
 int rpt_trace_closest(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out);
 int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, uint8_t* occludedOut);
 
+/* traversal microbenchmark (new): `iterations` timed passes over the same n host rays after two warm-up passes.
+ * anyHit 0 = closest hit (out receives n RptIntersection), 1 = occlusion (occ receives n bytes); out / occ may be NULL.
+ * kernel 0 = one ray per thread run to completion, 1 = persistent queue kernel with dynamic fetch (wavefront passes). */
+int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, int anyHit, int kernel, int iterations,
+                    float* msPerIteration, RptIntersection* out, uint8_t* occludedOut);
+
 int rpt_counters_enable(RptCtx* ctx, int on);
 int rpt_counters_reset(RptCtx* ctx);
 int rpt_counters_read(RptCtx* ctx, RptCounters* out);

@@ -51,35 +51,149 @@ RT_DEV uint32_t slabHits4(uint32_t meta4, uint32_t octinv4,
 	return hits;
 }
 
-template <int MODE>
-RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tmax, uint32_t* candidateCount = nullptr) {
-	Hit best;
-	best.u = 0.0f; best.v = 0.0f;
-	best.instanceIdx = InvalidHitIndex;
-	best.triangleIdx = 0;
-	float bestT = tmax;
-	uint32_t bestFlat = 0xffffffffu;
-	uint32_t nodeVisits = 0, triTests = 0, count = 0;
+// Per-ray constants of a traversal: origin, direction, padded reciprocal direction, octant.
+struct TravRay {
+	float3 o, d;
+	float idx, idy, idz;
+	float tmin;
+	uint32_t octinv;
+};
 
-	// A ray with a NaN / infinite component or an empty interval can never satisfy the triangle test (every
-	// comparison on NaN is false).  Without this early-out such a ray would walk the whole tree: fmaxf/fminf drop
-	// NaN operands, so every slab test would pass.  The shaders do produce such rays now and then (e.g.
-	// sqrt(1 - |uv|^2) of a disk sample that rounds to |uv| > 1); the result is a miss either way.
-	if (!(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f)) {
-		if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
-		if (MODE == TraceCount && candidateCount) *candidateCount = 0;
-		return best;
-	}
+// A ray with a NaN / infinite component or an empty interval can never satisfy the triangle test (every
+// comparison on NaN is false).  Without this early-out such a ray would walk the whole tree: fmaxf/fminf drop
+// NaN operands, so every slab test would pass.  The shaders do produce such rays now and then (e.g.
+// sqrt(1 - |uv|^2) of a disk sample that rounds to |uv| > 1); the result is a miss either way.
+RT_DEV bool rayIsDegenerate(float3 o, float tmin, float3 d, float tmax) {
+	return !(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f);
+}
 
+RT_DEV TravRay makeTravRay(float3 o, float tmin, float3 d) {
+	TravRay r;
+	r.o = o; r.d = d; r.tmin = tmin;
 	// reciprocal direction; components too close to zero are pushed away from it so 1/d stays finite
 	const float tiny = 1e-20f;
-	float idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-	float idy = 1.0f / (abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-	float idz = 1.0f / (abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-	const bool negx = idx < 0.0f, negy = idy < 0.0f, negz = idz < 0.0f;
-	const uint32_t octinv = 7u ^ ((negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u));
-	const uint32_t octinv4 = octinv * 0x01010101u;
+	r.idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+	r.idy = 1.0f / (abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+	r.idz = 1.0f / (abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+	r.octinv = 7u ^ ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
+	return r;
+}
 
+// Pops the nearest-octant child of the node group, tests its 8 child boxes against [tmin, tfar] and returns the
+// new node group (inner children hit) plus the triangle hits of its leaf children.  The remainder of the old
+// group is pushed first.  Precondition: ngroup.y > 0x00ffffff.
+template <typename Stack>
+RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, uint32_t& triBase, uint32_t& triHits) {
+	const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
+	const uint32_t octinv4 = r.octinv * 0x01010101u;
+	const uint32_t hits = ngroup.y;
+	const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
+	ngroup.y &= ~(1u << bit);
+	if (ngroup.y > 0x00ffffffu && sp < TraversalStackSize) stack[sp++] = ngroup;
+	const uint32_t slot = (bit - 24u) ^ r.octinv;
+	const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
+	const float4* np = reinterpret_cast<const float4*>(s.nodes + (ngroup.x + rel));
+	const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+
+	const uint32_t ebits = __float_as_uint(n0.w);
+	// 2^(e-127) per axis times 1/d, and (p - o)/d, padded by a bound on their rounding error so the
+	// slab interval can only grow
+	const float ex = __uint_as_float((ebits & 0xffu) << 23);
+	const float ey = __uint_as_float(((ebits >> 8) & 0xffu) << 23);
+	const float ez = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
+	const float sx = ex * r.idx, sy = ey * r.idy, sz = ez * r.idz;
+	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;
+	const float padx = fma_(abs_(sx), 255.0f, abs_(hx)) * 1e-6f;
+	const float pady = fma_(abs_(sy), 255.0f, abs_(hy)) * 1e-6f;
+	const float padz = fma_(abs_(sz), 255.0f, abs_(hz)) * 1e-6f;
+	const float nx = hx - padx, ny = hy - pady, nz = hz - padz;
+	const float fx = hx + padx, fy = hy + pady, fz = hz + padz;
+
+	const uint32_t qlox0 = __float_as_uint(n2.x), qlox1 = __float_as_uint(n2.y);
+	const uint32_t qloy0 = __float_as_uint(n2.z), qloy1 = __float_as_uint(n2.w);
+	const uint32_t qloz0 = __float_as_uint(n3.x), qloz1 = __float_as_uint(n3.y);
+	const uint32_t qhix0 = __float_as_uint(n3.z), qhix1 = __float_as_uint(n3.w);
+	const uint32_t qhiy0 = __float_as_uint(n4.x), qhiy1 = __float_as_uint(n4.y);
+	const uint32_t qhiz0 = __float_as_uint(n4.z), qhiz1 = __float_as_uint(n4.w);
+
+	uint32_t hitmask = slabHits4(__float_as_uint(n1.z), octinv4,
+		negx ? qhix0 : qlox0, negy ? qhiy0 : qloy0, negz ? qhiz0 : qloz0,
+		negx ? qlox0 : qhix0, negy ? qloy0 : qhiy0, negz ? qloz0 : qhiz0,
+		sx, sy, sz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+	hitmask |= slabHits4(__float_as_uint(n1.w), octinv4,
+		negx ? qhix1 : qlox1, negy ? qhiy1 : qloy1, negz ? qhiz1 : qloz1,
+		negx ? qlox1 : qhix1, negy ? qloy1 : qhiy1, negz ? qloz1 : qhiz1,
+		sx, sy, sz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+
+	ngroup.x = __float_as_uint(n1.x);
+	ngroup.y = (hitmask & 0xff000000u) | (ebits >> 24);
+	triBase = __float_as_uint(n1.y);
+	triHits = hitmask & 0x00ffffffu;
+}
+
+struct TriHit {
+	float t, u, v;
+	uint32_t instanceIdx, triangleIdx, flat;
+};
+
+// Möller–Trumbore in the fixed operation order of the numeric contract; accepted iff tmin < t < tmax
+RT_DEV bool triTest(const SceneView& s, const TravRay& r, uint32_t triIndex, float tmax, TriHit& h) {
+	const float4* tp = reinterpret_cast<const float4*>(s.tris + triIndex);
+	const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+	const float3 v0 = f3(t0), e1 = f3(t1), e2 = f3(t2);
+	const float3 p = cross(r.d, e2);
+	const float det = dot(e1, p);
+	const float inv = 1.0f / det;
+	const float3 sv = r.o - v0;
+	const float u = dot(sv, p) * inv;
+	const float3 q = cross(sv, e1);
+	const float v = dot(r.d, q) * inv;
+	const float t = dot(e2, q) * inv;
+	h.t = t; h.u = u; h.v = v;
+	h.instanceIdx = __float_as_uint(t0.w); h.triangleIdx = __float_as_uint(t1.w); h.flat = __float_as_uint(t2.w);
+	return u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > r.tmin && t < tmax;
+}
+
+// Running result of one ray (closest hit with the order-independent tie rule, any hit, or candidate count)
+struct TravResult {
+	Hit best;
+	float bestT;
+	uint32_t bestFlat, count;
+	RT_DEV void init(float tmax) {
+		best.u = 0.0f; best.v = 0.0f; best.instanceIdx = InvalidHitIndex; best.triangleIdx = 0;
+		bestT = tmax; bestFlat = 0xffffffffu; count = 0;
+	}
+	// returns true when the traversal may stop (any-hit found)
+	template <int MODE>
+	RT_DEV bool accept(const TriHit& h) {
+		if (MODE == TraceAny) {
+			best.instanceIdx = h.instanceIdx; best.triangleIdx = h.triangleIdx;
+			return true;
+		}
+		if (MODE == TraceCount) { count++; return false; }
+		if (MODE == TraceClosestNoLights && h.instanceIdx == 0u) return false;
+		if (h.t < bestT || (h.t == bestT && h.flat < bestFlat)) {
+			bestT = h.t; bestFlat = h.flat;
+			best.u = h.u; best.v = h.v;
+			best.instanceIdx = h.instanceIdx; best.triangleIdx = h.triangleIdx;
+		}
+		return false;
+	}
+};
+
+// One ray per thread, run to completion (the per-pixel passes call this in line).
+template <int MODE>
+RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tmax, uint32_t* candidateCount = nullptr) {
+	TravResult res;
+	res.init(tmax);
+	uint32_t nodeVisits = 0, triTests = 0;
+	if (rayIsDegenerate(o, tmin, d, tmax)) {
+		if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+		if (MODE == TraceCount && candidateCount) *candidateCount = 0;
+		return res.best;
+	}
+	const TravRay r = makeTravRay(o, tmin, d);
+	const float tmaxOrig = tmax;
 	uint2 stack[TraversalStackSize];
 	int sp = 0;
 	uint2 ngroup = make_uint2(0u, 0x80000000u);
@@ -87,89 +201,18 @@ RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tm
 	for (;;) {
 		uint32_t triBase = 0, triHits = 0;
 		if (ngroup.y > 0x00ffffffu) {
-			const uint32_t hits = ngroup.y;
-			const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
-			ngroup.y &= ~(1u << bit);
-			if (ngroup.y > 0x00ffffffu && sp < TraversalStackSize) stack[sp++] = ngroup;
-			const uint32_t slot = (bit - 24u) ^ octinv;
-			const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
-			const float4* np = reinterpret_cast<const float4*>(s.nodes + (ngroup.x + rel));
-			const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			nodeStep(s, r, res.bestT, ngroup, stack, sp, triBase, triHits);
 			nodeVisits++;
-
-			const uint32_t ebits = __float_as_uint(n0.w);
-			// 2^(e-127) per axis times 1/d, and (p - o)/d, padded by a bound on their rounding error so the
-			// slab interval can only grow
-			const float ex = __uint_as_float((ebits & 0xffu) << 23);
-			const float ey = __uint_as_float(((ebits >> 8) & 0xffu) << 23);
-			const float ez = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
-			const float sx = ex * idx, sy = ey * idy, sz = ez * idz;
-			const float hx = (n0.x - o.x) * idx, hy = (n0.y - o.y) * idy, hz = (n0.z - o.z) * idz;
-			const float padx = fma_(abs_(sx), 255.0f, abs_(hx)) * 1e-6f;
-			const float pady = fma_(abs_(sy), 255.0f, abs_(hy)) * 1e-6f;
-			const float padz = fma_(abs_(sz), 255.0f, abs_(hz)) * 1e-6f;
-			const float nx = hx - padx, ny = hy - pady, nz = hz - padz;
-			const float fx = hx + padx, fy = hy + pady, fz = hz + padz;
-
-			const uint32_t qlox0 = __float_as_uint(n2.x), qlox1 = __float_as_uint(n2.y);
-			const uint32_t qloy0 = __float_as_uint(n2.z), qloy1 = __float_as_uint(n2.w);
-			const uint32_t qloz0 = __float_as_uint(n3.x), qloz1 = __float_as_uint(n3.y);
-			const uint32_t qhix0 = __float_as_uint(n3.z), qhix1 = __float_as_uint(n3.w);
-			const uint32_t qhiy0 = __float_as_uint(n4.x), qhiy1 = __float_as_uint(n4.y);
-			const uint32_t qhiz0 = __float_as_uint(n4.z), qhiz1 = __float_as_uint(n4.w);
-
-			uint32_t hitmask = slabHits4(__float_as_uint(n1.z), octinv4,
-				negx ? qhix0 : qlox0, negy ? qhiy0 : qloy0, negz ? qhiz0 : qloz0,
-				negx ? qlox0 : qhix0, negy ? qloy0 : qhiy0, negz ? qloz0 : qhiz0,
-				sx, sy, sz, nx, ny, nz, fx, fy, fz, tmin, bestT);
-			hitmask |= slabHits4(__float_as_uint(n1.w), octinv4,
-				negx ? qhix1 : qlox1, negy ? qhiy1 : qloy1, negz ? qhiz1 : qloz1,
-				negx ? qlox1 : qhix1, negy ? qloy1 : qhiy1, negz ? qloz1 : qhiz1,
-				sx, sy, sz, nx, ny, nz, fx, fy, fz, tmin, bestT);
-
-			ngroup.x = __float_as_uint(n1.x);
-			ngroup.y = (hitmask & 0xff000000u) | (ebits >> 24);
-			triBase = __float_as_uint(n1.y);
-			triHits = hitmask & 0x00ffffffu;
 		}
-
 		while (triHits) {
 			const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
 			triHits &= triHits - 1u;
-			const float4* tp = reinterpret_cast<const float4*>(s.tris + (triBase + i));
-			const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
 			triTests++;
-			const float3 v0 = f3(t0), e1 = f3(t1), e2 = f3(t2);
-			const float3 p = cross(d, e2);
-			const float det = dot(e1, p);
-			const float inv = 1.0f / det;
-			const float3 sv = o - v0;
-			const float u = dot(sv, p) * inv;
-			const float3 q = cross(sv, e1);
-			const float v = dot(d, q) * inv;
-			const float t = dot(e2, q) * inv;
-			if (u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > tmin && t < tmax) {
-				const uint32_t inst = __float_as_uint(t0.w);
-				if (MODE == TraceAny) {
-					best.instanceIdx = inst;
-					best.triangleIdx = __float_as_uint(t1.w);
-					goto done;
-				}
-				if (MODE == TraceCount) {
-					count++;
-					continue;
-				}
-				if (MODE == TraceClosestNoLights && inst == 0u) continue;
-				const uint32_t flat = __float_as_uint(t2.w);
-				if (t < bestT || (t == bestT && flat < bestFlat)) {
-					bestT = t; bestFlat = flat;
-					best.u = u; best.v = v;
-					best.instanceIdx = inst;
-					best.triangleIdx = __float_as_uint(t1.w);
-				}
+			TriHit h;
+			if (triTest(s, r, triBase + i, tmaxOrig, h)) {
+				if (res.accept<MODE>(h)) goto done;
 			}
 		}
-
 		if (ngroup.y <= 0x00ffffffu) {
 			if (sp == 0) break;
 			ngroup = stack[--sp];
@@ -181,8 +224,8 @@ done:
 		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
 		atomicAdd(&s.counters[3], (unsigned long long)triTests);
 	}
-	if (MODE == TraceCount && candidateCount) *candidateCount = count;
-	return best;
+	if (MODE == TraceCount && candidateCount) *candidateCount = res.count;
+	return res.best;
 }
 
 // wrappers with the reference's names (ray_query.glsl:6-70)

@@ -51,6 +51,7 @@ struct RptFrame {
 	uint32_t halo = 0;
 	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
 	uint32_t* work = nullptr;                  // WorkCounterCount queue heads of the persistent kernels
+	WavefrontView wf{};                        // wavefront path-tracing queues (owned rows only)
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
@@ -317,6 +318,17 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	e = cudaMalloc(&f->work, WorkCounterCount * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(f->work, 0, WorkCounterCount * sizeof(uint32_t));
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc work counters"); }
+	{
+		const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
+		void** wfSlots[] = { (void**)&f->wf.state, (void**)&f->wf.vertex, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1], (void**)&f->wf.pix[0],
+		                     (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays, (void**)&f->wf.occluded, (void**)&f->wf.counters };
+		const size_t wfBytes[] = { f->pixels() * PathStateWords * 16, px * VertexWords * 16, px * 32, px * 32, px * 4, px * 4, px * 16, px * 32, px,
+		                           size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) };
+		for (int i = 0; i < 10; i++) {
+			e = cudaMalloc(wfSlots[i], wfBytes[i]);
+			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }
+		}
+	}
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
 	CU(ctx, cudaStreamSynchronize(f->stream));
@@ -334,6 +346,8 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
+	for (void* p : { (void*)f->wf.state, (void*)f->wf.vertex, (void*)f->wf.rays[0], (void*)f->wf.rays[1], (void*)f->wf.pix[0], (void*)f->wf.pix[1],
+	                 (void*)f->wf.hits, (void*)f->wf.shadowRays, (void*)f->wf.occluded, (void*)f->wf.counters }) if (p) cudaFree(p);
 	drainTiming(f);
 	for (cudaEvent_t e : f->eventPool) cudaEventDestroy(e);
 	if (f->stream) cudaStreamDestroy(f->stream);
@@ -375,6 +389,7 @@ static FrameView makeView(RptFrame* f) {
 	v.camera = f->camera; v.prevCamera = f->prevCamera;
 	v.halo = f->halo;
 	v.work = f->work;
+	v.wf = f->wf;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
 	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;
@@ -617,6 +632,44 @@ static int traceCommon(RptCtx* ctx, const RptScene* s, const float* rays, uint32
 	cudaFree(dRays); if (dOut) cudaFree(dOut); if (dOcc) cudaFree(dOcc);
 	return RPT_OK;
 }
+// Traversal microbenchmark: the same rays through either traversal kernel, timed with CUDA events on the context's
+// stream.  kernel 0 = one ray per thread run to completion (what the per-pixel passes do in line), 1 = the persistent
+// queue kernel with dynamic fetch (what the wavefront passes use).  Results of the last iteration are returned.
+RPT_API int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, int anyHit, int kernel, int iterations,
+                            float* msPerIteration, RptIntersection* out, uint8_t* occ) {
+	if (!ctx || !s || !rays || n == 0 || iterations < 1 || !msPerIteration) return fail(ctx, RPT_ERR_INVALID, "rpt_trace_bench: bad argument");
+	CU(ctx, cudaSetDevice(ctx->device));
+	float4* dRays = nullptr; RptIntersection* dOut = nullptr; uint8_t* dOcc = nullptr; uint32_t* dHead = nullptr;
+	CU(ctx, cudaMalloc(&dRays, size_t(n) * 32));
+	CU(ctx, cudaMalloc(&dOut, size_t(n) * sizeof(RptIntersection)));
+	CU(ctx, cudaMalloc(&dOcc, n));
+	CU(ctx, cudaMalloc(&dHead, sizeof(uint32_t)));
+	CU(ctx, cudaMemcpyAsync(dRays, rays, size_t(n) * 32, cudaMemcpyHostToDevice, ctx->stream));
+	cudaEvent_t e0, e1;
+	CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
+	const SceneView sv = sceneView(s);
+	for (int it = -2; it < iterations; it++) {   // two warm-up iterations
+		if (it == 0) CU(ctx, cudaEventRecord(e0, ctx->stream));
+		if (kernel == 0) launchTraceRays(sv, dRays, n, anyHit ? nullptr : dOut, anyHit ? dOcc : nullptr, ctx->stream);
+		else {
+			CU(ctx, cudaMemsetAsync(dHead, 0, sizeof(uint32_t), ctx->stream));
+			if (anyHit) launchTraceQueueAny(sv, dRays, nullptr, n, dHead, dOcc, ctx->stream);
+			else launchTraceQueueClosest(sv, dRays, nullptr, n, dHead, dOut, ctx->stream);
+		}
+	}
+	CU(ctx, cudaEventRecord(e1, ctx->stream));
+	CU(ctx, cudaGetLastError());
+	if (out && !anyHit) CU(ctx, cudaMemcpyAsync(out, dOut, size_t(n) * sizeof(RptIntersection), cudaMemcpyDeviceToHost, ctx->stream));
+	if (occ && anyHit) CU(ctx, cudaMemcpyAsync(occ, dOcc, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(ctx, cudaStreamSynchronize(ctx->stream));
+	float ms = 0.f;
+	CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+	*msPerIteration = ms / float(iterations);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaFree(dRays); cudaFree(dOut); cudaFree(dOcc); cudaFree(dHead);
+	return RPT_OK;
+}
+
 RPT_API int rpt_trace_closest(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out) { return traceCommon(ctx, s, rays, n, out, nullptr); }
 RPT_API int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, uint8_t* occ) { return traceCommon(ctx, s, rays, n, nullptr, occ); }
 

@@ -19,6 +19,14 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
 void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
 
+// wavefront traversal (trace_queue.cu): rays[2i] = {o, tmin}, rays[2i+1] = {d, tmax}; the ray count is read from
+// countPtr on the device when it is not NULL (queues filled by a previous kernel), else countHost; head is the
+// queue's fetch counter and must be zero at launch
+void launchTraceQueueClosest(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
+                             RptIntersection* hits, cudaStream_t st);
+void launchTraceQueueAny(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
+                         uint8_t* occluded, cudaStream_t st);
+
 // pixel of this thread for a pass over rows [row0, row1); false when outside the film
 constexpr int PassBlockX = 8, PassBlockY = 8;
 inline dim3 passGrid(uint32_t width, uint32_t rows) {

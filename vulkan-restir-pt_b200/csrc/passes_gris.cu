@@ -5,6 +5,7 @@
 //   host sequence: GRISReSTIR::render (src/GRISReSTIR.cpp:9-53)
 #include "passes.h"
 #include "shading.cuh"
+#include "persist.cuh"
 
 namespace rt {
 
@@ -71,15 +72,6 @@ RT_DEV void grisCap(GRISResv& resv, float cap) {   // :131-136
 		resv.sampleCount() = cap;
 	}
 }
-
-struct GrisStream {   // gris_path_trace.glsl:10-33
-	GRISResv sample;
-	float weight, sumWeight;
-	RT_DEV void add(const GRISResv& ps, float w, float r) {
-		sumWeight += w;
-		if (r * sumWeight < w) { weight = w; sample.copySample(ps); }
-	}
-};
 
 RT_DEV uint32_t nextRcVertexSampleState(uint32_t state, bool connectible) {   // :35-43
 	if (state == 2) return 2;
@@ -219,163 +211,366 @@ RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRI
 
 } // namespace
 
-// gris_path_trace.comp -> tracePath
-__global__ void __launch_bounds__(PassBlockX* PassBlockY) grisPathTraceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
-	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
-	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
+// ---- gris_path_trace.comp -> tracePath, as a wavefront ---------------------------------------------------------
+//
+// The shader runs one invocation per pixel through a loop of up to 15 bounces with two ray queries per bounce
+// (gris_path_trace.glsl:85-257).  Here the loop is cut at its ray queries: per bounce
+//     [extend]   trace_queue.cu, closest hit of every queued extension ray
+//     [vertex]   grisVertexKernel: surface fetch, state machine, emitter hit, reconnection-vertex choice, random
+//                draws, light sample -> shadow-ray queue                                     (:90-175)
+//     [shadow]   trace_queue.cu, any hit of every queued shadow ray
+//     [scatter]  grisScatterKernel: the three NEE candidate kinds, Russian roulette, BSDF sample, throughput
+//                update -> extension-ray queue of the next bounce                             (:176-257)
+// and the state of a path lives in global memory between the kernels (PathState below, 160 B per pixel).  A path
+// that ends (miss, emitter, roulette, failed BSDF sample, bounce limit) writes its reservoir at once (:259-278).
+// The winner of the path's streaming RIS (StreamSampler, :10-33) is kept directly in the pixel's output reservoir
+// slot: it is only ever overwritten until the path ends.
+// Per-pixel arithmetic, its order and the RNG stream are exactly those of the shader's loop.
+
+struct PathState {
+	float3 dir;              // direction that arrived at the current vertex (wo = -dir)
+	uint32_t rng;
+	float3 throughput, rcThroughput, lastPos;
+	float bsPdf;
+	uint32_t bsType;
+	uint32_t sampleState, lastSampleState;
+	bool isLastVertexConnectible, isThisVertexConnectible, streamWritten;
+	int bounce;
+	float streamWeight, streamSumWeight;
+	GRISResv ps;             // q0..q4 = the GRISPathSample under construction
+};
+
+RT_DEV void storePathState(float4* __restrict__ base, size_t pix, const PathState& st) {
+	float4* w = base + pix * PathStateWords;
+	const uint32_t flags = uint32_t(st.bounce) | (st.sampleState << 4) | (st.lastSampleState << 6) | (st.isLastVertexConnectible ? 1u << 8 : 0u)
+		| (st.isThisVertexConnectible ? 1u << 9 : 0u) | (st.streamWritten ? 1u << 10 : 0u) | (st.bsType << 16);
+	w[0] = make_float4(st.dir.x, st.dir.y, st.dir.z, __uint_as_float(st.rng));
+	w[1] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.bsPdf);
+	w[2] = make_float4(st.rcThroughput.x, st.rcThroughput.y, st.rcThroughput.z, st.streamWeight);
+	w[3] = make_float4(st.lastPos.x, st.lastPos.y, st.lastPos.z, st.streamSumWeight);
+	w[4] = make_float4(__uint_as_float(flags), 0.f, 0.f, 0.f);
+	w[5] = st.ps.q0; w[6] = st.ps.q1; w[7] = st.ps.q2; w[8] = st.ps.q3; w[9] = st.ps.q4;
+}
+RT_DEV void loadPathState(const float4* __restrict__ base, size_t pix, PathState& st) {
+	const float4* w = base + pix * PathStateWords;
+	const float4 a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+	st.dir = f3(a); st.rng = __float_as_uint(a.w);
+	st.throughput = f3(b); st.bsPdf = b.w;
+	st.rcThroughput = f3(c); st.streamWeight = c.w;
+	st.lastPos = f3(d); st.streamSumWeight = d.w;
+	const uint32_t flags = __float_as_uint(e.x);
+	st.bounce = int(flags & 15u);
+	st.sampleState = (flags >> 4) & 3u; st.lastSampleState = (flags >> 6) & 3u;
+	st.isLastVertexConnectible = (flags >> 8) & 1u; st.isThisVertexConnectible = (flags >> 9) & 1u; st.streamWritten = (flags >> 10) & 1u;
+	st.bsType = flags >> 16;
+	st.ps.q0 = w[5]; st.ps.q1 = w[6]; st.ps.q2 = w[7]; st.ps.q3 = w[8]; st.ps.q4 = w[9];
+	st.ps.q5 = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// StreamSampler::add (gris_path_trace.glsl:21-32); the selected sample goes straight to the pixel's reservoir slot
+RT_DEV void streamAdd(PathState& st, RptGRISReservoir* __restrict__ slot, float w, float r) {
+	st.streamSumWeight += w;
+	if (r * st.streamSumWeight < w) {
+		st.streamWeight = w;
+		st.streamWritten = true;
+		float4* q = reinterpret_cast<float4*>(slot);
+		q[0] = st.ps.q0; q[1] = st.ps.q1; q[2] = st.ps.q2; q[3] = st.ps.q3; q[4] = st.ps.q4;
+	}
+}
+
+// end of tracePath (gris_path_trace.glsl:259-278)
+RT_DEV void finishPath(PathState& st, RptGRISReservoir* __restrict__ slot) {
+	if (st.sampleState == 2 && st.lastSampleState == 2) {
+		streamAdd(st, slot, luminance(st.ps.F()), sample1f(st.rng));
+	}
+	float4* q = reinterpret_cast<float4*>(slot);
+	const bool scaled = st.streamSumWeight > 0 && st.streamWeight > 0;
+	if (st.streamWritten) {
+		float4 q0 = q[0], q1 = q[1], q4 = q[4];
+		float resampleWeight = 0.0f;
+		if (scaled) {
+			const float k = st.streamSumWeight / st.streamWeight;
+			const float3 F = f3(q4) * k, rcLi = f3(q1) * k;
+			q4.x = F.x; q4.y = F.y; q4.z = F.z;
+			q1.x = rcLi.x; q1.y = rcLi.y; q1.z = rcLi.z;
+			resampleWeight = luminance(F);
+			q[1] = q1;
+		}
+		else {
+			q0.z = __uint_as_float(InvalidHitIndex);
+			q4.x = 0.f; q4.y = 0.f; q4.z = 0.f;
+			q[0] = q0;
+		}
+		q[4] = q4;
+		q[5] = make_float4(1.0f, resampleWeight, 0.f, 0.f);
+	}
+	else {   // nothing was ever selected: the zero sample, marked invalid
+		const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+		q[0] = make_float4(0.f, 0.f, __uint_as_float(InvalidHitIndex), 0.f);
+		q[1] = z; q[2] = z; q[3] = z; q[4] = z;
+		q[5] = make_float4(1.0f, 0.f, 0.f, 0.f);
+	}
+}
+
+struct VertexOut {
+	float4 lightRandSample;
+	float resvRandSample;
+};
+
+// [vertex] gris_path_trace.glsl:101-174.  isecWord = the hit that led here.  Returns false when the path ended here.
+RT_DEV bool vertexStage(PathState& st, const RptGRISSettings& set, const Surface& surf, const Mat& mat, float4 isecWord, float sumPower,
+                        RptGRISReservoir* __restrict__ slot, VertexOut& out) {
+	GRISResv& ps = st.ps;
+	const int bounce = st.bounce;
+	ps.setFlags(withPathLength(ps.flags(), uint32_t(bounce + 1)));
+	const float cosPrevWi = dot(st.dir, surf.norm);
+	const float distToPrev = distance(st.lastPos, surf.pos);
+	const float geometryJacobian = abs_(cosPrevWi) / square(distToPrev);
+	st.isThisVertexConnectible = surf.isLight || isBSDFConnectible(mat);
+	st.lastSampleState = st.sampleState;
+	st.sampleState = nextRcVertexSampleState(st.sampleState, st.isThisVertexConnectible);
+	if (set.shiftType == ShiftReconnection && bounce == 1 && !surf.isLight) {
+		st.sampleState = 2;
+		st.lastSampleState = 1;
+	}
+	out.resvRandSample = sample1f(st.rng);
+
+	if (surf.isLight) {
+		if (bounce > 1 && cosPrevWi < 0) {
+			float weight = 1.0f;
+			const float lightPdf = luminance(surf.albedo) / sumPower / geometryJacobian;
+			if (!isSampleTypeDelta(st.bsType)) weight = MISWeight(st.bsPdf, lightPdf);
+			const float3 weightedLi = surf.albedo * weight;
+			if (st.sampleState == 2 && st.lastSampleState == 2) {
+				ps.setRcLi(ps.rcLi() + weightedLi * st.rcThroughput);
+				ps.setF(ps.F() + weightedLi * st.throughput);
+			}
+			else if ((st.sampleState == 2 && st.lastSampleState == 1) && st.isLastVertexConnectible && distToPrev > GRISDistanceThreshold) {
+				ps.q0 = isecWord;
+				ps.q1.w = __uint_as_float(st.rng);
+				ps.rcPrevSamplePdf() = st.bsPdf;
+				ps.rcJacobian() = geometryJacobian;
+				ps.setRcLi(weightedLi);
+				ps.setRcWi(f3(0.0f));
+				ps.setF(weightedLi * st.throughput);
+				ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcLightScattered));
+				streamAdd(st, slot, luminance(ps.F()), out.resvRandSample);
+			}
+		}
+		return false;
+	}
+	const bool connectible = st.isThisVertexConnectible && st.isLastVertexConnectible && distToPrev > GRISDistanceThreshold;
+	if ((st.sampleState == 2 && st.lastSampleState == 1) && (connectible || set.shiftType == ShiftReconnection)) {
+		ps.q0 = isecWord;
+		ps.q1.w = __uint_as_float(st.rng);
+		ps.rcPrevSamplePdf() = st.bsPdf;
+		ps.rcJacobian() = geometryJacobian;
+		ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcSurface));
+		st.rcThroughput = f3(1.0f);
+	}
+	out.lightRandSample = sample4f(st.rng);
+	out.resvRandSample = sample1f(st.rng);
+	return true;
+}
+
+// NEE contributions (gris_path_trace.glsl:186-223) of an unoccluded light sample
+RT_DEV void neeStage(PathState& st, const Surface& surf, const Mat& mat, const LightSample& ls, float resvRandSample, RptGRISReservoir* __restrict__ slot) {
+	GRISResv& ps = st.ps;
+	const float3 wo = -st.dir;
+	const float bsdfPdf = absDot(surf.norm, ls.wi) * RT_PI_INV;
+	const float weight = MISWeight(ls.pdf, bsdfPdf);
+	const float3 scatterTerm = evalBSDF(mat, surf.albedo, surf.norm, wo, ls.wi) * satDot(surf.norm, ls.wi);
+	const float3 weightedLi = ls.radiance / ls.pdf * weight;
+	if (st.sampleState == 2 && st.lastSampleState == 2) {
+		ps.setRcLi(ps.rcLi() + weightedLi * scatterTerm * st.rcThroughput);
+		ps.setF(ps.F() + weightedLi * scatterTerm * st.throughput);
+	}
+	else if (st.sampleState == 2 && st.lastSampleState == 1) {
+		ps.setRcLi(weightedLi);
+		ps.setRcWi(ls.wi);
+		ps.setF(weightedLi * scatterTerm * st.throughput);
+		streamAdd(st, slot, luminance(ps.F()), resvRandSample);
+	}
+	else if (st.sampleState == 1 && st.isThisVertexConnectible && ls.dist > GRISDistanceThreshold) {
+		ps.q0 = make_float4(ls.bary.x, ls.bary.y, __uint_as_float(0u), __uint_as_float(ls.id));
+		ps.q1.w = __uint_as_float(st.rng);
+		ps.rcPrevSamplePdf() = ls.pdf;
+		ps.rcJacobian() = ls.jacobian;
+		ps.setRcLi(ls.radiance * weight);
+		ps.setRcWi(f3(0.0f));
+		ps.setF(weightedLi * scatterTerm * st.throughput);
+		ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(st.bounce + 1)), RcLightSampled));
+		streamAdd(st, slot, luminance(ps.F()), resvRandSample);
+	}
+}
+
+// [scatter] gris_path_trace.glsl:226-257.  Returns false when the path ended; else rayOri/st.dir hold the next ray.
+RT_DEV bool scatterStage(PathState& st, const RptGRISSettings& set, const Surface& surf, const Mat& mat, float3& rayOri) {
+	GRISResv& ps = st.ps;
+	const float3 wo = -st.dir;
+	if (st.bounce > 4) {
+		const float pdfTerminate = max_(1.0f - luminance(st.throughput) * set.rrScale, 0.0f);
+		if (sample1f(st.rng) < pdfTerminate) return false;
+		st.throughput /= (1.0f - pdfTerminate);
+		st.rcThroughput /= (1.0f - pdfTerminate);
+	}
+	const float3 r3 = sample3f(st.rng);
+	BSDFSample bs = emptyBSDFSample();
+	bs.pdf = st.bsPdf; bs.type = st.bsType;
+	const bool ok = sampleBSDF(mat, surf.albedo, surf.norm, wo, r3, bs);
+	if (!ok || bs.pdf < 1e-6f) return false;
+	st.bsPdf = bs.pdf; st.bsType = bs.type;
+	const float cosTheta = isSampleTypeDelta(bs.type) ? 1.0f : absDot(surf.norm, bs.wi);
+	const float3 scatterTerm = bs.bsdf * cosTheta / bs.pdf;
+	st.throughput *= scatterTerm;
+	if (st.sampleState == 2 && st.lastSampleState == 2) {
+		st.rcThroughput *= scatterTerm;
+	}
+	else if (st.sampleState == 2 && st.lastSampleState == 1) {
+		ps.setRcLi(f3(0.0f));
+		ps.setRcWi(bs.wi);
+		ps.setF(f3(0.0f));
+		st.rcThroughput /= bs.pdf;
+	}
+	st.lastPos = surf.pos;
+	st.dir = bs.wi;
+	rayOri = surf.pos + st.dir * 1e-4f;
+	st.isLastVertexConnectible = st.isThisVertexConnectible;
+	st.bounce++;
+	return st.bounce < 15;
+}
+
+constexpr uint32_t SlotEnded = 0xfffffffeu, SlotNoShadow = 0xffffffffu;
+constexpr int ShadeBlock = 128;
+
+// appends one entry per requesting lane to a device queue: one atomic per warp
+RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count, bool want) {
+	const unsigned mask = __ballot_sync(__activemask(), want);
+	if (!want) return 0u;
+	const uint32_t lane = threadIdx.x & 31u;
+	const int leader = __ffs(int(mask)) - 1;
+	uint32_t base = 0;
+	if (int(lane) == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
+	base = __shfl_sync(mask, base, leader);
+	return base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
+}
+
+RT_DEV void pushExtensionRay(const FrameView& f, int nextBounce, uint32_t pix, float3 ori, float3 dir) {
+	uint32_t* cnt = f.wf.counters + 4 * nextBounce;
+	const uint32_t slot = queueAppend(cnt, true);
+	float4* rq = f.wf.rays[nextBounce & 1] + 2 * size_t(slot);
+	rq[0] = make_float4(ori.x, ori.y, ori.z, MinRayDistance);
+	rq[1] = make_float4(dir.x, dir.y, dir.z, MaxRayDistance);
+	f.wf.pix[nextBounce & 1][slot] = pix;
+}
+
+// bounce 0: the primary hit comes from the G-buffer, there is no NEE (gris_path_trace.glsl:176), so vertex and scatter
+// stages run back to back.  One thread per pixel in 8x4-tile order.
+__global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set) {
+	const uint32_t tilesX = (f.width + 7u) / 8u;
+	const uint32_t id = blockIdx.x * ShadeBlock + threadIdx.x;
+	const uint32_t tile = id >> 5, within = id & 31u;
+	const uint32_t x = (tile % tilesX) * 8u + (within & 7u), y = f.rowBegin + (tile / tilesX) * 4u + (within >> 3);
 	if (x >= f.width || y >= f.rowEnd) return;
 	const Primary p = loadPrimary(f, x, y);
-	if (!p.valid) return;
-	Ray ray = p.ray;
-	uint32_t rng = makeSeed(f.camera.seed, x, y);
-	float3 throughput = f3(1.0f), rcThroughput = f3(0.0f), lastPos = f3(0.0f);
-	float3 wo = -ray.dir;
-	bool isLastVertexConnectible = false;
-	uint32_t sampleState = 0, lastSampleState = 0;
-	Surface surf = primarySurface(p);
-	Mat mat = loadMaterial(s, uint32_t(p.matId));
-	BSDFSample bs = emptyBSDFSample();
-	Hit isec;
-	isec.u = 0.f; isec.v = 0.f; isec.instanceIdx = 0; isec.triangleIdx = 0;
+	if (!p.valid) return;   // background pixels keep their old reservoir (gris_path_trace.glsl:54-56)
+	const uint32_t pix = uint32_t(f.index(x, y));
+	RptGRISReservoir* slot = f.grisThis + pix;
+
+	PathState st;
+	st.dir = p.ray.dir;
+	st.rng = makeSeed(f.camera.seed, x, y);
+	st.throughput = f3(1.0f); st.rcThroughput = f3(0.0f); st.lastPos = f3(0.0f);
+	st.bsPdf = 0.0f; st.bsType = 0;
+	st.sampleState = 0; st.lastSampleState = 0;
+	st.isLastVertexConnectible = false; st.isThisVertexConnectible = false; st.streamWritten = false;
+	st.bounce = 0;
+	st.streamWeight = 0.0f; st.streamSumWeight = 0.0f;
+	st.ps = zeroGRIS();   // GRISPathSampleReset, gris_reservoir.glsl:61-69
+	st.ps.q0.z = __uint_as_float(InvalidHitIndex);
+	st.ps.q4.w = __uint_as_float(st.rng);   // primaryRng
+
+	const Surface surf = primarySurface(p);
+	const Mat mat = loadMaterial(s, uint32_t(p.matId));
+	VertexOut vo;
+	float3 rayOri;
+	const float4 isecWord = make_float4(0.f, 0.f, __uint_as_float(0u), __uint_as_float(0u));
+	bool go = vertexStage(st, set, surf, mat, isecWord, s.lightTable[0].prob, slot, vo);
+	if (go) go = scatterStage(st, set, surf, mat, rayOri);
+	if (!go) { finishPath(st, slot); return; }
+	storePathState(f.wf.state, pix, st);
+	pushExtensionRay(f, 1, pix, rayOri, st.dir);
+}
+
+// [vertex] of bounce >= 1: one thread per slot of the bounce's extension queue
+__global__ void __launch_bounds__(ShadeBlock) grisVertexKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
+	const uint32_t n = f.wf.counters[4 * bounce];
 	const float sumPower = s.lightTable[0].prob;
-
-	GRISResv ps = zeroGRIS();   // GRISPathSampleReset, gris_reservoir.glsl:61-69
-	ps.q0.z = __uint_as_float(InvalidHitIndex);
-	ps.q4.w = __uint_as_float(rng);   // primaryRng
-	GrisStream stream;
-	stream.sample = zeroGRIS(); stream.weight = 0.0f; stream.sumWeight = 0.0f;
-
-	for (int bounce = 0; bounce < 15; bounce++) {
-		if (bounce > 0) {
-			isec = traceClosestHit(s, ray.ori, MinRayDistance, ray.dir, MaxRayDistance);
-			if (isec.instanceIdx == InvalidHitIndex) break;
-			loadSurfaceInfo(s, isec, surf);
-			mat = loadMaterial(s, surf.matIndex);
+	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
+		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
+		const RptIntersection hit = f.wf.hits[slotIdx];
+		RptGRISReservoir* slot = f.grisThis + pix;
+		float4* vtx = f.wf.vertex + size_t(slotIdx) * VertexWords;
+		PathState st;
+		loadPathState(f.wf.state, pix, st);
+		if (hit.instanceIdx == InvalidHitIndex) {   // the ray left the scene (gris_path_trace.glsl:92-94)
+			finishPath(st, slot);
+			vtx[2].w = __uint_as_float(SlotEnded);
+			continue;
 		}
-		ps.setFlags(withPathLength(ps.flags(), uint32_t(bounce + 1)));
-		const float cosPrevWi = dot(ray.dir, surf.norm);
-		const float distToPrev = distance(lastPos, surf.pos);
-		const float geometryJacobian = abs_(cosPrevWi) / square(distToPrev);
-		const bool isThisVertexConnectible = surf.isLight || isBSDFConnectible(mat);
-		lastSampleState = sampleState;
-		sampleState = nextRcVertexSampleState(sampleState, isThisVertexConnectible);
-		if (st.shiftType == ShiftReconnection && bounce == 1 && !surf.isLight) {
-			sampleState = 2;
-			lastSampleState = 1;
+		Surface surf;
+		loadSurfaceInfo(s, hit, surf);
+		const Mat mat = loadMaterial(s, surf.matIndex);
+		VertexOut vo;
+		vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
+		const float4 isecWord = make_float4(hit.bary[0], hit.bary[1], __uint_as_float(hit.instanceIdx), __uint_as_float(hit.triangleIdx));
+		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) {
+			finishPath(st, slot);
+			vtx[2].w = __uint_as_float(SlotEnded);
+			continue;
 		}
-		float resvRandSample = sample1f(rng);
-		const float4 isecWord = make_float4(isec.u, isec.v, __uint_as_float(isec.instanceIdx), __uint_as_float(isec.triangleIdx));
-
-		if (surf.isLight) {
-			if (bounce > 1 && cosPrevWi < 0) {
-				float weight = 1.0f;
-				const float lightPdf = luminance(surf.albedo) / sumPower / geometryJacobian;
-				if (!isSampleTypeDelta(bs.type)) weight = MISWeight(bs.pdf, lightPdf);
-				const float3 weightedLi = surf.albedo * weight;
-				if (sampleState == 2 && lastSampleState == 2) {
-					ps.setRcLi(ps.rcLi() + weightedLi * rcThroughput);
-					ps.setF(ps.F() + weightedLi * throughput);
-				}
-				else if ((sampleState == 2 && lastSampleState == 1) && isLastVertexConnectible && distToPrev > GRISDistanceThreshold) {
-					ps.q0 = isecWord;
-					ps.q1.w = __uint_as_float(rng);
-					ps.rcPrevSamplePdf() = bs.pdf;
-					ps.rcJacobian() = geometryJacobian;
-					ps.setRcLi(weightedLi);
-					ps.setRcWi(f3(0.0f));
-					ps.setF(weightedLi * throughput);
-					ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcLightScattered));
-					stream.add(ps, luminance(ps.F()), resvRandSample);
-				}
-			}
-			break;
+		uint32_t shadowIdx = SlotNoShadow;
+		const bool nee = !isBSDFDelta(mat);
+		if (nee) {
+			const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
+			shadowIdx = queueAppend(f.wf.counters + 4 * bounce + 1, true);
+			float4* rq = f.wf.shadowRays + 2 * size_t(shadowIdx);
+			rq[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
+			rq[1] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
 		}
-		const bool connectible = isThisVertexConnectible && isLastVertexConnectible && distToPrev > GRISDistanceThreshold;
-		if ((sampleState == 2 && lastSampleState == 1) && (connectible || st.shiftType == ShiftReconnection)) {
-			ps.q0 = isecWord;
-			ps.q1.w = __uint_as_float(rng);
-			ps.rcPrevSamplePdf() = bs.pdf;
-			ps.rcJacobian() = geometryJacobian;
-			ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcSurface));
-			rcThroughput = f3(1.0f);
-		}
-		const float4 lightRandSample = sample4f(rng);
-		resvRandSample = sample1f(rng);
-
-		if (bounce > 0 && !isBSDFDelta(mat)) {
-			const LightSample ls = sampleLight(s, surf.pos, lightRandSample);
-			const bool shadowed = traceShadow(s, surf.pos, MinRayDistance, ls.wi, ls.dist - MinRayDistance);
-			if (!shadowed && ls.pdf > 1e-6f) {
-				const float bsdfPdf = absDot(surf.norm, ls.wi) * RT_PI_INV;
-				const float weight = MISWeight(ls.pdf, bsdfPdf);
-				const float3 scatterTerm = evalBSDF(mat, surf.albedo, surf.norm, wo, ls.wi) * satDot(surf.norm, ls.wi);
-				const float3 weightedLi = ls.radiance / ls.pdf * weight;
-				if (sampleState == 2 && lastSampleState == 2) {
-					ps.setRcLi(ps.rcLi() + weightedLi * scatterTerm * rcThroughput);
-					ps.setF(ps.F() + weightedLi * scatterTerm * throughput);
-				}
-				else if (sampleState == 2 && lastSampleState == 1) {
-					ps.setRcLi(weightedLi);
-					ps.setRcWi(ls.wi);
-					ps.setF(weightedLi * scatterTerm * throughput);
-					stream.add(ps, luminance(ps.F()), resvRandSample);
-				}
-				else if (sampleState == 1 && isThisVertexConnectible && ls.dist > GRISDistanceThreshold) {
-					ps.q0 = make_float4(ls.bary.x, ls.bary.y, __uint_as_float(0u), __uint_as_float(ls.id));
-					ps.q1.w = __uint_as_float(rng);
-					ps.rcPrevSamplePdf() = ls.pdf;
-					ps.rcJacobian() = ls.jacobian;
-					ps.setRcLi(ls.radiance * weight);
-					ps.setRcWi(f3(0.0f));
-					ps.setF(weightedLi * scatterTerm * throughput);
-					ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce + 1)), RcLightSampled));
-					stream.add(ps, luminance(ps.F()), resvRandSample);
-				}
-			}
-		}
-		if (bounce > 4) {
-			const float pdfTerminate = max_(1.0f - luminance(throughput) * st.rrScale, 0.0f);
-			if (sample1f(rng) < pdfTerminate) break;
-			throughput /= (1.0f - pdfTerminate);
-			rcThroughput /= (1.0f - pdfTerminate);
-		}
-		const float3 r3 = sample3f(rng);
-		if (!sampleBSDF(mat, surf.albedo, surf.norm, wo, r3, bs) || bs.pdf < 1e-6f) break;
-		const float cosTheta = isSampleTypeDelta(bs.type) ? 1.0f : absDot(surf.norm, bs.wi);
-		const float3 scatterTerm = bs.bsdf * cosTheta / bs.pdf;
-		throughput *= scatterTerm;
-		if (sampleState == 2 && lastSampleState == 2) {
-			rcThroughput *= scatterTerm;
-		}
-		else if (sampleState == 2 && lastSampleState == 1) {
-			ps.setRcLi(f3(0.0f));
-			ps.setRcWi(bs.wi);
-			ps.setF(f3(0.0f));
-			rcThroughput /= bs.pdf;
-		}
-		lastPos = surf.pos;
-		wo = -bs.wi;
-		ray.dir = bs.wi;
-		ray.ori = surf.pos + ray.dir * 1e-4f;
-		isLastVertexConnectible = isThisVertexConnectible;
+		storePathState(f.wf.state, pix, st);
+		vtx[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, __uint_as_float(surf.matIndex));
+		vtx[1] = make_float4(surf.norm.x, surf.norm.y, surf.norm.z, vo.resvRandSample);
+		vtx[2] = make_float4(surf.albedo.x, surf.albedo.y, surf.albedo.z, __uint_as_float(shadowIdx));
+		vtx[3] = vo.lightRandSample;
 	}
-	if (sampleState == 2 && lastSampleState == 2) {
-		stream.add(ps, luminance(ps.F()), sample1f(rng));
+}
+
+// [scatter] of bounce >= 1: one thread per slot of the same queue
+__global__ void __launch_bounds__(ShadeBlock) grisScatterKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
+	const uint32_t n = f.wf.counters[4 * bounce];
+	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
+		const float4* vtx = f.wf.vertex + size_t(slotIdx) * VertexWords;
+		const float4 v2 = vtx[2];
+		const uint32_t shadowIdx = __float_as_uint(v2.w);
+		if (shadowIdx == SlotEnded) continue;
+		const float4 v0 = vtx[0], v1 = vtx[1];
+		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
+		RptGRISReservoir* slot = f.grisThis + pix;
+		PathState st;
+		loadPathState(f.wf.state, pix, st);
+		Surface surf;
+		surf.pos = f3(v0); surf.norm = f3(v1); surf.albedo = f3(v2); surf.matIndex = __float_as_uint(v0.w); surf.isLight = false;
+		const Mat mat = loadMaterial(s, surf.matIndex);
+		if (shadowIdx != SlotNoShadow && f.wf.occluded[shadowIdx] == 0) {
+			const LightSample ls = sampleLight(s, surf.pos, vtx[3]);
+			if (ls.pdf > 1e-6f) neeStage(st, surf, mat, ls, v1.w, slot);
+		}
+		float3 rayOri;
+		if (!scatterStage(st, set, surf, mat, rayOri)) { finishPath(st, slot); continue; }
+		storePathState(f.wf.state, pix, st);
+		pushExtensionRay(f, bounce + 1, pix, rayOri, st.dir);
 	}
-	GRISResv resv = zeroGRIS();
-	resv.copySample(stream.sample);
-	if (stream.sumWeight > 0 && stream.weight > 0) {
-		const float k = stream.sumWeight / stream.weight;
-		resv.setF(resv.F() * k);
-		resv.setRcLi(resv.rcLi() * k);
-		resv.resampleWeight() = luminance(resv.F());
-	}
-	else {
-		resv.q0.z = __uint_as_float(InvalidHitIndex);
-		resv.setF(f3(0.0f));
-	}
-	resv.sampleCount() = 1;
-	storeGRIS(f.grisThis + f.index(x, y), resv);
 }
 
 // gris_resample_temporal.comp -> temporalReuse
@@ -455,7 +650,19 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(cons
 }
 
 void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
-	grisPathTraceKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p);
+	static const int vertexBlocks = persistentBlocks(reinterpret_cast<const void*>(grisVertexKernel), ShadeBlock);
+	static const int scatterBlocks = persistentBlocks(reinterpret_cast<const void*>(grisScatterKernel), ShadeBlock);
+	const uint32_t rows = f.rowEnd - f.rowBegin;
+	const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
+	cudaMemsetAsync(f.wf.counters, 0, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), st);
+	grisBeginKernel<<<(slots + ShadeBlock - 1) / ShadeBlock, ShadeBlock, 0, st>>>(f, s, p);
+	for (int bounce = 1; bounce < 15; bounce++) {
+		uint32_t* c = f.wf.counters + 4 * bounce;
+		launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		grisVertexKernel<<<vertexBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
+		launchTraceQueueAny(s, f.wf.shadowRays, c + 1, 0, c + 3, f.wf.occluded, st);
+		grisScatterKernel<<<scatterBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
+	}
 }
 void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
 	grisTemporalKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p);

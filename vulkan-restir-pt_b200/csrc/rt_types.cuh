@@ -55,6 +55,22 @@ struct SceneView {
 	unsigned long long* counters; // RptCounters layout, or nullptr when counting is off
 };
 
+// Wavefront path-tracing buffers of one frame (passes_gris.cu, trace_queue.cu).  All indexed by queue slot except
+// `state`, which is indexed by the pixel's storage index.
+constexpr int PathStateWords = 10;    // float4 words per pixel
+constexpr int VertexWords = 4;        // float4 words handed from the vertex stage to the scatter stage, per slot
+constexpr int WavefrontMaxBounces = 16;
+struct WavefrontView {
+	float4* state;
+	float4* vertex;
+	float4* rays[2];                  // extension-ray queues (ping-pong over bounces): {o, tmin}, {d, tmax}
+	uint32_t* pix[2];                 // pixel storage index of each slot
+	RptIntersection* hits;            // closest hit of each slot of the current queue
+	float4* shadowRays;
+	uint8_t* occluded;
+	uint32_t* counters;               // [bounce][4]: extension count, shadow count, extension head, shadow head
+};
+
 struct FrameView {
 	uint32_t width, height;       // full film
 	uint32_t rowBegin, rowEnd;    // rows this frame owns
@@ -79,6 +95,7 @@ struct FrameView {
 	RptDIReservoir* peerDiUp;      RptDIReservoir* peerDiDown;
 	bool striped;                 // true when this frame is one strip of a larger film
 	uint32_t* work;               // work-queue heads of the persistent kernels (WorkCounterCount words)
+	WavefrontView wf;
 
 	__device__ __forceinline__ size_t index(uint32_t x, uint32_t y) const { return size_t(y - storeBegin) * width + x; }
 };

@@ -1,0 +1,135 @@
+// Wavefront ray traversal: a persistent kernel that pulls rays from a queue in global memory.
+//
+// Replaces the ray-query calls of the reference (src/shader/ray_query.glsl:6-70, executed by the driver's RT cores)
+// for the wavefront passes.  The RT cores hide the fact that the rays of one SIMD group need very different numbers
+// of BVH steps; on B200 that shows up as idle lanes (profiles/: 7-9 of 32 lanes active when each thread keeps its
+// ray until the slowest ray of the warp is done).  Here rays are decoupled from threads: every lane runs the
+// while-while traversal loop on its current ray, and as soon as enough lanes of the warp have finished theirs the
+// idle lanes fetch the next rays of the queue (one atomic per warp) — "persistent threads with dynamic fetch"
+// (Aila & Laine 2009), over the compressed 8-wide BVH.
+//
+// Queue entry i: rays[2i] = {origin, tmin}, rays[2i+1] = {direction, tmax}.  Results land at index i: a 16-byte
+// RptIntersection (closest hit) or one byte (occluded).  Per-ray results are identical to traceRay<> (same box and
+// triangle arithmetic, order-independent closest-hit rule).
+#include "passes.h"
+#include "persist.cuh"
+#include "bvh_traverse.cuh"
+
+namespace rt {
+
+namespace {
+
+constexpr int TraceBlock = 128;
+constexpr uint32_t NoRay = 0xffffffffu;
+constexpr int FetchThreshold = 8;   // idle lanes per warp that trigger a fetch
+
+template <int MODE>
+__global__ void __launch_bounds__(TraceBlock) traceQueueKernel(const __grid_constant__ SceneView s, const float4* __restrict__ rays,
+                                                                const uint32_t* __restrict__ countPtr, uint32_t countHost, uint32_t* __restrict__ head,
+                                                                RptIntersection* __restrict__ hits, uint8_t* __restrict__ occluded) {
+	const uint32_t n = countPtr ? *countPtr : countHost;
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t rayIdx = NoRay;
+	bool dry = false;
+	TravRay r = makeTravRay(f3(0.0f), 0.0f, f3(1.0f));
+	TravResult res;
+	res.init(0.0f);
+	float tmaxOrig = 0.0f;
+	uint2 stack[TraversalStackSize];
+	int sp = 0;
+	uint2 ngroup = make_uint2(0u, 0u);
+	uint32_t nodeVisits = 0, triTests = 0;
+
+	for (;;) {
+		// ---- dynamic fetch ----------------------------------------------------------------------------------
+		const unsigned idleMask = __ballot_sync(FullWarp, rayIdx == NoRay);
+		if (!dry && __popc(idleMask) >= FetchThreshold) {
+			const int leader = __ffs(int(idleMask)) - 1;
+			const uint32_t want = uint32_t(__popc(idleMask));
+			uint32_t base = 0;
+			if (int(lane) == leader) base = atomicAdd(head, want);
+			base = __shfl_sync(FullWarp, base, leader);
+			if (base + want >= n) dry = true;
+			if (rayIdx == NoRay) {
+				const uint32_t idx = base + uint32_t(__popc(idleMask & ((1u << lane) - 1u)));
+				if (idx < n) {
+					if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+					const float4 a = __ldcs(rays + 2 * size_t(idx)), b = __ldcs(rays + 2 * size_t(idx) + 1);
+					if (rayIsDegenerate(f3(a), a.w, f3(b), b.w)) {
+						if (MODE == TraceAny) occluded[idx] = 0;
+						else { RptIntersection o; o.bary[0] = 0.f; o.bary[1] = 0.f; o.instanceIdx = InvalidHitIndex; o.triangleIdx = 0; hits[idx] = o; }
+					}
+					else {
+						rayIdx = idx;
+						r = makeTravRay(f3(a), a.w, f3(b));
+						tmaxOrig = b.w;
+						res.init(b.w);
+						sp = 0;
+						ngroup = make_uint2(0u, 0x80000000u);
+					}
+				}
+			}
+		}
+		if (__all_sync(FullWarp, rayIdx == NoRay)) {
+			if (dry) break;
+			continue;
+		}
+
+		// ---- one traversal step of every lane that holds a ray -----------------------------------------------
+		if (rayIdx != NoRay) {
+			bool finished = false;
+			uint32_t triBase = 0, triHits = 0;
+			if (ngroup.y > 0x00ffffffu) {
+				nodeStep(s, r, res.bestT, ngroup, stack, sp, triBase, triHits);
+				nodeVisits++;
+			}
+			while (triHits) {
+				const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
+				triHits &= triHits - 1u;
+				triTests++;
+				TriHit h;
+				if (triTest(s, r, triBase + i, tmaxOrig, h)) {
+					if (res.accept<MODE>(h)) { finished = true; break; }
+				}
+			}
+			if (!finished && ngroup.y <= 0x00ffffffu) {
+				if (sp == 0) finished = true;
+				else ngroup = stack[--sp];
+			}
+			if (finished) {
+				if (MODE == TraceAny) occluded[rayIdx] = res.best.instanceIdx != InvalidHitIndex ? 1 : 0;
+				else {
+					RptIntersection o;
+					o.bary[0] = res.best.u; o.bary[1] = res.best.v; o.instanceIdx = res.best.instanceIdx; o.triangleIdx = res.best.triangleIdx;
+					hits[rayIdx] = o;
+				}
+				rayIdx = NoRay;
+			}
+		}
+	}
+	if (s.counters != nullptr) {
+		// per-thread totals (a thread serves many rays); the rays themselves were counted at fetch time
+		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
+		atomicAdd(&s.counters[3], (unsigned long long)triTests);
+	}
+}
+
+template <int MODE>
+void launchQueue(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
+                 RptIntersection* hits, uint8_t* occluded, cudaStream_t st) {
+	static const int blocks = persistentBlocks(reinterpret_cast<const void*>(traceQueueKernel<MODE>), TraceBlock);
+	traceQueueKernel<MODE><<<blocks, TraceBlock, 0, st>>>(s, rays, countPtr, countHost, head, hits, occluded);
+}
+
+} // namespace
+
+void launchTraceQueueClosest(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
+                             RptIntersection* hits, cudaStream_t st) {
+	launchQueue<TraceClosest>(s, rays, countPtr, countHost, head, hits, nullptr, st);
+}
+void launchTraceQueueAny(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
+                         uint8_t* occluded, cudaStream_t st) {
+	launchQueue<TraceAny>(s, rays, countPtr, countHost, head, nullptr, occluded, st);
+}
+
+} // namespace rt
