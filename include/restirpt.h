@@ -311,6 +311,10 @@ int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t
 int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, int anyHit, int kernel, int iterations,
                     float* msPerIteration, RptIntersection* out, uint8_t* occludedOut);
 
+/* queue sizes of the last wavefront path-tracing pass (new; diagnostics): out64[4*b + 0] = extension rays traced
+ * for bounce b, out64[4*b + 1] = shadow rays of bounce b; implicit sync */
+int rpt_wavefront_counters(RptFrame* f, uint32_t* out64);
+
 int rpt_counters_enable(RptCtx* ctx, int on);
 int rpt_counters_reset(RptCtx* ctx);
 int rpt_counters_read(RptCtx* ctx, RptCounters* out);

@@ -1,0 +1,83 @@
+"""Full-size (BASELINE.json configs 3 / 4 shape) checks through size-independent properties — the oracle is far too slow at
+1920x1080 — on the bench scene (VeachAjar when the asset is prepared, else the synthetic 380 k-triangle room):
+  * the two traversal kernels (one ray per thread, persistent queue with dynamic fetch) agree bit for bit on 2 M rays;
+  * a 1920x1080 ReSTIR PT film cut into 2 strips (halo exchange through peer pointers) equals the uncut film bit for bit;
+  * reservoir invariants: finite non-negative weights, M <= cap, valid samples carry a reconnection vertex id >= 1."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import prepare_assets
+import restirpt
+from restirpt import GRISSettings, P
+from restirpt.multigpu import partition
+from common import Backend, FrameDriver, bitwise_mismatch, camera_rays
+from test_gpu_strips import _run, HALO
+
+pytestmark = pytest.mark.gpu
+W, H = 1920, 1080
+
+
+@pytest.fixture(scope="module")
+def bench_scene(built):
+    xml = prepare_assets.ajar_xml()
+    return restirpt.HostScene.xml(xml) if xml else restirpt.HostScene.room(380000, 1)
+
+
+def test_traversal_kernels_agree_on_two_million_rays(bench_scene):
+    dev = restirpt.Device(0)
+    scene_h = dev.scene(bench_scene.desc)
+    cam = bench_scene.camera(W, H)
+    o, d = camera_rays(cam, W, H)
+    rng = np.random.default_rng(5)
+    rays = np.zeros((W * H, 8), dtype=np.float32)
+    rays[:, 0:3] = o
+    rays[:, 3] = 1e-4
+    dirs = d.reshape(-1, 3) + rng.normal(scale=0.3, size=(W * H, 3))    # perturbed primary rays: incoherent within a warp
+    rays[:, 4:7] = dirs / np.linalg.norm(dirs, axis=1, keepdims=True)
+    rays[:, 7] = 1e7
+    res = {}
+    for any_hit in (0, 1):
+        if any_hit:
+            rays[:, 7] = rng.uniform(0.5, 6.0, size=W * H)
+        for kernel in (0, 1):
+            ms = C.c_float()
+            out = np.zeros(W * H, dtype=restirpt.ISEC_DTYPE)
+            occ = np.zeros(W * H, dtype=np.uint8)
+            restirpt.check(dev.ctx, dev.lib.rpt_trace_bench(dev.ctx, scene_h, rays.ctypes.data_as(P), W * H, any_hit, kernel, 1, C.byref(ms),
+                                                            out.ctypes.data_as(P), occ.ctypes.data_as(P)), "rpt_trace_bench")
+            res[(any_hit, kernel)] = (out, occ)
+    a, b = res[(0, 0)][0], res[(0, 1)][0]
+    assert np.array_equal(a["instanceIdx"], b["instanceIdx"]) and np.array_equal(a["triangleIdx"], b["triangleIdx"])
+    assert np.array_equal(a["bary"].view(np.uint32), b["bary"].view(np.uint32))
+    assert (a["instanceIdx"] != 0xffffffff).mean() > 0.5
+    assert np.array_equal(res[(1, 0)][1], res[(1, 1)][1])
+    assert 0.02 < res[(1, 0)][1].mean() < 0.98
+    dev.lib.rpt_scene_destroy(scene_h)
+
+
+def test_full_hd_film_strips_and_reservoir_invariants(bench_scene):
+    dev = restirpt.Device(0)
+    scene_h = dev.scene(bench_scene.desc)
+    cam = bench_scene.camera(W, H)
+    full = _run(dev, scene_h, [(0, H, 0)], W, H, cam, 2, "gris")[0]
+    parts = _run(dev, scene_h, [(r0, r1, HALO) for r0, r1 in partition(H, 2)], W, H, cam, 2, "gris")
+    img = np.concatenate([p[0] for p in parts], axis=0)
+    res = np.concatenate([p[1] for p in parts], axis=0)
+    assert bitwise_mismatch(img, full[0]) == 0
+    assert bitwise_mismatch(res, full[1]) == 0
+    img, res = full
+    assert np.isfinite(img).all() and (img[..., :3] >= 0).all() and (img[..., :3] <= 1e4).all() and img[..., :3].mean() > 0
+    w, m = res["resampleWeight"], res["sampleCount"]
+    assert np.isfinite(w).all() and (w >= 0).all()
+    assert (m <= 20.0).all() and (m >= 0).all()
+    valid = res["rcIsec"]["instanceIdx"] != 0xffffffff
+    lit = valid & (w > 0)
+    assert lit.mean() > 0.2
+    assert ((res["flags"][lit] & 0xff) >= 1).all()          # rcVertexId
+    assert (((res["flags"][lit] >> 8) & 0xff) <= 15).all()   # pathLength
+    dev.lib.rpt_scene_destroy(scene_h)

@@ -51,6 +51,30 @@ def test_closest_hit_ids_random_rays(pair):
     assert np.array_equal(a["bary"][hit].view(np.uint32), b["bary"][hit].view(np.uint32))
 
 
+def test_queue_traversal_kernel_matches_oracle(pair):
+    """the persistent dynamic-fetch traversal kernel of the wavefront passes (trace_queue.cu), closest and any hit"""
+    import ctypes as C
+    from restirpt import P
+    name, sc, gpu, cpu = pair
+    rng = np.random.default_rng(4321)
+    rays = random_rays(rng, 30011, -3.0, 3.0)     # not a multiple of the warp size
+    rays[::97, 4:7] = np.nan                      # degenerate rays are misses
+    want = cpu.trace_closest(rays)
+    ms = C.c_float()
+    got = np.zeros(rays.shape[0], dtype=restirpt.ISEC_DTYPE)
+    restirpt.check(gpu.dev.ctx, gpu.lib.rpt_trace_bench(gpu.dev.ctx, gpu.scene, rays.ctypes.data_as(P), rays.shape[0], 0, 1, 1, C.byref(ms),
+                                                        got.ctypes.data_as(P), None), "rpt_trace_bench")
+    assert np.array_equal(got["instanceIdx"], want["instanceIdx"]) and np.array_equal(got["triangleIdx"], want["triangleIdx"])
+    hit = want["instanceIdx"] != 0xffffffff
+    assert np.array_equal(got["bary"][hit].view(np.uint32), want["bary"][hit].view(np.uint32))
+    rays[:, 7] = 1.5
+    want_occ = cpu.trace_shadow(rays)
+    occ = np.zeros(rays.shape[0], dtype=np.uint8)
+    restirpt.check(gpu.dev.ctx, gpu.lib.rpt_trace_bench(gpu.dev.ctx, gpu.scene, rays.ctypes.data_as(P), rays.shape[0], 1, 1, 1, C.byref(ms),
+                                                        None, occ.ctypes.data_as(P)), "rpt_trace_bench")
+    assert np.array_equal(occ, want_occ)
+
+
 def test_shadow_rays(pair):
     name, sc, gpu, cpu = pair
     rng = np.random.default_rng(99)

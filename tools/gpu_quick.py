@@ -73,6 +73,9 @@ def main():
     rays = c.closestRays + c.shadowRays
     print(f"rays/frame {rays/1e6:.2f} M (closest {c.closestRays/1e6:.2f} shadow {c.shadowRays/1e6:.2f}) rays/px {rays/(w*h):.2f} "
           f"nodes/ray {c.nodeVisits/max(rays,1):.1f} tris/ray {c.triTests/max(rays,1):.1f} hits {c.shadedHits/1e6:.2f} M")
+    wc = (C.c_uint32 * 64)()
+    dev.lib.rpt_wavefront_counters(b.frame, wc)
+    print("wavefront rays per bounce (extension/shadow):", " ".join(f"{b_}:{wc[4*b_]}/{wc[4*b_+1]}" for b_ in range(1, 15)))
     print(f"Mrays/s {rays/1e6/(total/frames/1000):.1f}")
     img = b.postprocess(PostSettings(1, 1, 1, 0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

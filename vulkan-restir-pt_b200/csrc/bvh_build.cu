@@ -7,6 +7,7 @@
 //   3. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) binary BVH;
 //   4. greedy surface-area collapse to 8-wide nodes, octant-ordered child slots, 80-byte compressed nodes
 //      (Ylitie, Karras, Laine 2017), triangles re-emitted in leaf order.
+#include <cstdlib>
 #include <cub/cub.cuh>
 #include <cfloat>
 #include "bvh_build.h"
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
                                                       uint32_t numLeaves, const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi,
                                                       const uint32_t* __restrict__ nodeCount, const TriRecord* __restrict__ trisFlat,
                                                       WideNode* __restrict__ wide, TriRecord* __restrict__ trisOut,
-                                                      CollapseCounters* __restrict__ counters) {
+                                                      CollapseCounters* __restrict__ counters, uint32_t leafMax) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= numTasks) return;
 	const uint2 task = tasks[t];
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
 		const uint32_t c = slotChild[sl];
 		if (c == 0xffffffffu) continue;
 		const uint32_t n = nodeCount[c];
-		if (n <= 3) { triOffset[sl] = numTri; triCount[sl] = n; numTri += n; }
+		if (n <= leafMax) { triOffset[sl] = numTri; triCount[sl] = n; numTri += n; }
 		else { imask |= 1u << sl; numInner++; }
 	}
 	const uint32_t childBase = numInner ? atomicAdd(&counters->numNodes, numInner) : 0u;
@@ -429,9 +430,10 @@ cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* o
 	CK(cudaMemcpyAsync(cc, &cc0, sizeof(cc0), cudaMemcpyHostToDevice, stream));
 	const uint2 rootTask = make_uint2(root, 0u);
 	CK(cudaMemcpyAsync(qA, &rootTask, sizeof(rootTask), cudaMemcpyHostToDevice, stream));
+	const uint32_t leafMax = getenv("RPT_LEAF_MAX") ? uint32_t(atoi(getenv("RPT_LEAF_MAX"))) : 3u;
 	uint32_t numTasks = 1;
 	while (numTasks) {
-		collapseKernel<<<(numTasks + 63) / 64, 64, 0, stream>>>(numTasks, qA, qB, N, nodeLo, nodeHi, nodeCount, trisFlat, wide, trisOut, cc);
+		collapseKernel<<<(numTasks + 63) / 64, 64, 0, stream>>>(numTasks, qA, qB, N, nodeLo, nodeHi, nodeCount, trisFlat, wide, trisOut, cc, leafMax);
 		CollapseCounters h;
 		CK(cudaMemcpyAsync(&h, cc, sizeof(h), cudaMemcpyDeviceToHost, stream));
 		CK(cudaStreamSynchronize(stream));

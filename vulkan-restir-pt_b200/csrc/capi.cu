@@ -673,6 +673,15 @@ RPT_API int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, u
 RPT_API int rpt_trace_closest(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, RptIntersection* out) { return traceCommon(ctx, s, rays, n, out, nullptr); }
 RPT_API int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t n, uint8_t* occ) { return traceCommon(ctx, s, rays, n, nullptr, occ); }
 
+// queue sizes of the last wavefront path-tracing pass: out[4*b + {0,1}] = extension / shadow rays of bounce b
+RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
+	if (!f || !out64) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_wavefront_counters: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	CU(f->ctx, cudaMemcpy(out64, f->wf.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return RPT_OK;
+}
+
 // ---- counters ---------------------------------------------------------------------------------------------------
 RPT_API int rpt_counters_enable(RptCtx* ctx, int on) {
 	if (!ctx) return fail(nullptr, RPT_ERR_INVALID, "rpt_counters_enable: NULL ctx");

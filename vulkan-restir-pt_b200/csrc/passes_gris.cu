@@ -3,6 +3,7 @@
 //   reference src/shader/gris_path_trace.glsl:45-305, gris_retrace.glsl:42-236, gris_reservoir.glsl:37-136,
 //   gris_resample_temporal.glsl:11-83, gris_resample_spatial.glsl:11-134 (+ the three .comp entry points)
 //   host sequence: GRISReSTIR::render (src/GRISReSTIR.cpp:9-53)
+#include <cstdlib>
 #include "passes.h"
 #include "shading.cuh"
 #include "persist.cuh"
@@ -573,8 +574,38 @@ __global__ void __launch_bounds__(ShadeBlock) grisScatterKernel(const __grid_con
 	}
 }
 
+// experiment: vertex + in-line shadow ray + scatter in one kernel (one state round trip per bounce)
+__global__ void __launch_bounds__(ShadeBlock) grisShadeFusedKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
+	const uint32_t n = f.wf.counters[4 * bounce];
+	const float sumPower = s.lightTable[0].prob;
+	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
+		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
+		const RptIntersection hit = f.wf.hits[slotIdx];
+		RptGRISReservoir* slot = f.grisThis + pix;
+		PathState st;
+		loadPathState(f.wf.state, pix, st);
+		if (hit.instanceIdx == InvalidHitIndex) { finishPath(st, slot); continue; }
+		Surface surf;
+		loadSurfaceInfo(s, hit, surf);
+		const Mat mat = loadMaterial(s, surf.matIndex);
+		VertexOut vo;
+		vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
+		const float4 isecWord = make_float4(hit.bary[0], hit.bary[1], __uint_as_float(hit.instanceIdx), __uint_as_float(hit.triangleIdx));
+		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) { finishPath(st, slot); continue; }
+		if (!isBSDFDelta(mat)) {
+			const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
+			const bool shadowed = traceShadow(s, surf.pos, MinRayDistance, ls.wi, ls.dist - MinRayDistance);
+			if (!shadowed && ls.pdf > 1e-6f) neeStage(st, surf, mat, ls, vo.resvRandSample, slot);
+		}
+		float3 rayOri;
+		if (!scatterStage(st, set, surf, mat, rayOri)) { finishPath(st, slot); continue; }
+		storePathState(f.wf.state, pix, st);
+		pushExtensionRay(f, bounce + 1, pix, rayOri, st.dir);
+	}
+}
+
 // gris_resample_temporal.comp -> temporalReuse
-__global__ void __launch_bounds__(PassBlockX* PassBlockY) grisTemporalKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
 	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
 	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
 	if (x >= f.width || y >= f.rowEnd) return;
@@ -656,9 +687,12 @@ void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSe
 	const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
 	cudaMemsetAsync(f.wf.counters, 0, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), st);
 	grisBeginKernel<<<(slots + ShadeBlock - 1) / ShadeBlock, ShadeBlock, 0, st>>>(f, s, p);
+	static const int fusedMode = getenv("RPT_FUSED_SHADE") ? atoi(getenv("RPT_FUSED_SHADE")) : 0;
+	static const int fusedBlocks = persistentBlocks(reinterpret_cast<const void*>(grisShadeFusedKernel), ShadeBlock);
 	for (int bounce = 1; bounce < 15; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
 		launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		if (fusedMode) { grisShadeFusedKernel<<<fusedBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce); continue; }
 		grisVertexKernel<<<vertexBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 		launchTraceQueueAny(s, f.wf.shadowRays, c + 1, 0, c + 3, f.wf.occluded, st);
 		grisScatterKernel<<<scatterBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);

@@ -196,6 +196,7 @@ DEVICE_API = {
     "rpt_trace_closest": (C.c_int, [P, P, P, C.c_uint32, P]),
     "rpt_trace_shadow": (C.c_int, [P, P, P, C.c_uint32, P]),
     "rpt_trace_bench": (C.c_int, [P, P, P, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), P, P]),
+    "rpt_wavefront_counters": (C.c_int, [P, C.POINTER(C.c_uint32)]),
     "rpt_counters_enable": (C.c_int, [P, C.c_int]),
     "rpt_counters_reset": (C.c_int, [P]),
     "rpt_counters_read": (C.c_int, [P, C.POINTER(Counters)]),
