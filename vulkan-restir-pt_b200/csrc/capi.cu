@@ -276,6 +276,11 @@ static std::vector<void**> frameSlots(RptFrame* f) {
 	         (void**)&f->diTemp, (void**)&f->gi[0], (void**)&f->gi[1], (void**)&f->gris[0], (void**)&f->gris[1], (void**)&f->grisTemp,
 	         (void**)&f->primaryIsec, (void**)&f->rgba8 };
 }
+static std::vector<void**> wavefrontSlots(RptFrame* f) {
+	return { (void**)&f->wf.state[0], (void**)&f->wf.state[1], (void**)&f->wf.cold, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1],
+	         (void**)&f->wf.pix[0], (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays[0], (void**)&f->wf.shadowRays[1],
+	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters };
+}
 static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
 // the two depthNormal images carry two extra rows (film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
 static size_t slotBytes(const RptFrame* f, size_t i) {
@@ -320,14 +325,14 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc work counters"); }
 	{
 		const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
-		void** wfSlots[] = { (void**)&f->wf.state, (void**)&f->wf.vertex, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1], (void**)&f->wf.pix[0],
-		                     (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays, (void**)&f->wf.occluded, (void**)&f->wf.counters };
-		const size_t wfBytes[] = { f->pixels() * PathStateWords * 16, px * VertexWords * 16, px * 32, px * 32, px * 4, px * 4, px * 16, px * 32, px,
-		                           size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) };
-		for (int i = 0; i < 10; i++) {
-			e = cudaMalloc(wfSlots[i], wfBytes[i]);
+		auto wfs = wavefrontSlots(f);
+		const size_t wfBytes[] = { px * PathStateWords * 16, px * PathStateWords * 16, f->pixels() * 32, px * 32, px * 32, px * 4, px * 4, px * 16,
+		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) };
+		for (size_t i = 0; i < wfs.size(); i++) {
+			e = cudaMalloc(wfs[i], wfBytes[i]);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }
 		}
+		f->wf.capacity = uint32_t(px);
 	}
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
@@ -346,8 +351,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
-	for (void* p : { (void*)f->wf.state, (void*)f->wf.vertex, (void*)f->wf.rays[0], (void*)f->wf.rays[1], (void*)f->wf.pix[0], (void*)f->wf.pix[1],
-	                 (void*)f->wf.hits, (void*)f->wf.shadowRays, (void*)f->wf.occluded, (void*)f->wf.counters }) if (p) cudaFree(p);
+	for (void** p : wavefrontSlots(f)) if (*p) cudaFree(*p);
 	drainTiming(f);
 	for (cudaEvent_t e : f->eventPool) cudaEventDestroy(e);
 	if (f->stream) cudaStreamDestroy(f->stream);

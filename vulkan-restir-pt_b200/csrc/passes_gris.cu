@@ -215,18 +215,30 @@ RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRI
 // ---- gris_path_trace.comp -> tracePath, as a wavefront ---------------------------------------------------------
 //
 // The shader runs one invocation per pixel through a loop of up to 15 bounces with two ray queries per bounce
-// (gris_path_trace.glsl:85-257).  Here the loop is cut at its ray queries: per bounce
-//     [extend]   trace_queue.cu, closest hit of every queued extension ray
-//     [vertex]   grisVertexKernel: surface fetch, state machine, emitter hit, reconnection-vertex choice, random
-//                draws, light sample -> shadow-ray queue                                     (:90-175)
-//     [shadow]   trace_queue.cu, any hit of every queued shadow ray
-//     [scatter]  grisScatterKernel: the three NEE candidate kinds, Russian roulette, BSDF sample, throughput
-//                update -> extension-ray queue of the next bounce                             (:176-257)
-// and the state of a path lives in global memory between the kernels (PathState below, 160 B per pixel).  A path
-// that ends (miss, emitter, roulette, failed BSDF sample, bounce limit) writes its reservoir at once (:259-278).
-// The winner of the path's streaming RIS (StreamSampler, :10-33) is kept directly in the pixel's output reservoir
-// slot: it is only ever overwritten until the path ends.
-// Per-pixel arithmetic, its order and the RNG stream are exactly those of the shader's loop.
+// (gris_path_trace.glsl:85-257).  Here the loop is cut at its ray queries and every bounce is ONE shading kernel
+// between two traversal launches (trace_queue.cu):
+//
+//     [extend b]   closest hit of every extension ray queued for bounce b
+//     [bounce b]   grisBounceKernel: (1) fold in the light sample of vertex b-1 now that its shadow ray is known,
+//                  (2) surface fetch + vertex logic of vertex b (:90-175), (3) light sample of vertex b -> shadow
+//                  queue, (4) Russian roulette + BSDF sample (:226-257) -> extension queue of bounce b+1
+//     [shadow b]   any hit of every queued shadow ray (overlaps nothing else of this path: consumed at bounce b+1)
+//
+// Deferring the light sample's contribution by one kernel is exact, not approximate: its VALUE (the three candidate
+// kinds of :186-223) is computed at vertex b from the state of that moment and only its application — the
+// stream-reservoir insertion / the additions into rcLi and F — waits for the visibility bit; nothing that happens in
+// between (roulette, BSDF sampling, throughput update) reads what the application writes, and the next reader (the
+// vertex logic of b+1, or the end of the path) runs after it, so every floating-point operation sees the same
+// operands in the same order as in the shader.  A path that ends while its light sample is pending is queued once
+// more without a ray ("zombie") and finishes at the next kernel.
+//
+// Path state lives in HBM between kernels as structure-of-arrays planes indexed by QUEUE SLOT (ping-pong over
+// bounces), so every warp reads and writes full 512-byte runs; only the two rarely touched words of the path sample
+// (rcIsec, rcPrevSamplePdf/rcJacobian) are indexed by pixel.  The winner of the path's streaming RIS (StreamSampler,
+// :10-33) is kept directly in the pixel's output reservoir slot: it is only ever overwritten until the path ends.
+
+constexpr int ShadeBlock = 128;
+constexpr uint32_t NeeNone = 0, NeeAccumulate = 1, NeeRcVertex = 2, NeeLightSampled = 3;
 
 struct PathState {
 	float3 dir;              // direction that arrived at the current vertex (wo = -dir)
@@ -235,54 +247,82 @@ struct PathState {
 	float bsPdf;
 	uint32_t bsType;
 	uint32_t sampleState, lastSampleState;
-	bool isLastVertexConnectible, isThisVertexConnectible, streamWritten;
+	bool isLastVertexConnectible, isThisVertexConnectible, streamWritten, zombie;
 	int bounce;
 	float streamWeight, streamSumWeight;
-	GRISResv ps;             // q0..q4 = the GRISPathSample under construction
+	// light sample of the last vertex, waiting for its shadow ray
+	uint32_t neeKind, shadowIdx;
+	float neeResvRand;
+	float4 nee0, nee1, nee2;
+	// the GRISPathSample under construction; q0 / q3 are loaded from the per-pixel cold array on demand
+	GRISResv ps;
+	bool coldValid, coldDirty;
 };
 
-RT_DEV void storePathState(float4* __restrict__ base, size_t pix, const PathState& st) {
-	float4* w = base + pix * PathStateWords;
+struct PathBuffers {
+	float4* hot;             // PathStateWords planes of `capacity` float4 each
+	float4* cold;            // 2 float4 per pixel
+	uint32_t capacity;
+};
+
+RT_DEV void storePathState(const PathBuffers& b, uint32_t slot, uint32_t pix, const PathState& st) {
 	const uint32_t flags = uint32_t(st.bounce) | (st.sampleState << 4) | (st.lastSampleState << 6) | (st.isLastVertexConnectible ? 1u << 8 : 0u)
-		| (st.isThisVertexConnectible ? 1u << 9 : 0u) | (st.streamWritten ? 1u << 10 : 0u) | (st.bsType << 16);
-	w[0] = make_float4(st.dir.x, st.dir.y, st.dir.z, __uint_as_float(st.rng));
-	w[1] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.bsPdf);
-	w[2] = make_float4(st.rcThroughput.x, st.rcThroughput.y, st.rcThroughput.z, st.streamWeight);
-	w[3] = make_float4(st.lastPos.x, st.lastPos.y, st.lastPos.z, st.streamSumWeight);
-	w[4] = make_float4(__uint_as_float(flags), 0.f, 0.f, 0.f);
-	w[5] = st.ps.q0; w[6] = st.ps.q1; w[7] = st.ps.q2; w[8] = st.ps.q3; w[9] = st.ps.q4;
+		| (st.isThisVertexConnectible ? 1u << 9 : 0u) | (st.streamWritten ? 1u << 10 : 0u) | (st.zombie ? 1u << 11 : 0u) | (st.neeKind << 12) | (st.bsType << 16);
+	float4* w = b.hot + slot;
+	const size_t n = b.capacity;
+	w[0 * n] = make_float4(st.dir.x, st.dir.y, st.dir.z, __uint_as_float(st.rng));
+	w[1 * n] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.bsPdf);
+	w[2 * n] = make_float4(st.rcThroughput.x, st.rcThroughput.y, st.rcThroughput.z, st.streamWeight);
+	w[3 * n] = make_float4(st.lastPos.x, st.lastPos.y, st.lastPos.z, st.streamSumWeight);
+	w[4 * n] = make_float4(__uint_as_float(flags), __uint_as_float(st.shadowIdx), st.neeResvRand, 0.f);
+	w[5 * n] = st.ps.q1; w[6 * n] = st.ps.q2; w[7 * n] = st.ps.q4;
+	if (st.neeKind != NeeNone) { w[8 * n] = st.nee0; w[9 * n] = st.nee1; w[10 * n] = st.nee2; }
+	if (st.coldDirty) { b.cold[2 * size_t(pix)] = st.ps.q0; b.cold[2 * size_t(pix) + 1] = st.ps.q3; }
 }
-RT_DEV void loadPathState(const float4* __restrict__ base, size_t pix, PathState& st) {
-	const float4* w = base + pix * PathStateWords;
-	const float4 a = w[0], b = w[1], c = w[2], d = w[3], e = w[4];
+RT_DEV void loadPathState(const PathBuffers& b, uint32_t slot, PathState& st) {
+	const float4* w = b.hot + slot;
+	const size_t n = b.capacity;
+	const float4 a = w[0 * n], bb = w[1 * n], c = w[2 * n], d = w[3 * n], e = w[4 * n];
 	st.dir = f3(a); st.rng = __float_as_uint(a.w);
-	st.throughput = f3(b); st.bsPdf = b.w;
+	st.throughput = f3(bb); st.bsPdf = bb.w;
 	st.rcThroughput = f3(c); st.streamWeight = c.w;
 	st.lastPos = f3(d); st.streamSumWeight = d.w;
 	const uint32_t flags = __float_as_uint(e.x);
 	st.bounce = int(flags & 15u);
 	st.sampleState = (flags >> 4) & 3u; st.lastSampleState = (flags >> 6) & 3u;
-	st.isLastVertexConnectible = (flags >> 8) & 1u; st.isThisVertexConnectible = (flags >> 9) & 1u; st.streamWritten = (flags >> 10) & 1u;
+	st.isLastVertexConnectible = (flags >> 8) & 1u; st.isThisVertexConnectible = (flags >> 9) & 1u;
+	st.streamWritten = (flags >> 10) & 1u; st.zombie = (flags >> 11) & 1u;
+	st.neeKind = (flags >> 12) & 3u;
 	st.bsType = flags >> 16;
-	st.ps.q0 = w[5]; st.ps.q1 = w[6]; st.ps.q2 = w[7]; st.ps.q3 = w[8]; st.ps.q4 = w[9];
+	st.shadowIdx = __float_as_uint(e.y); st.neeResvRand = e.z;
+	st.ps.q1 = w[5 * n]; st.ps.q2 = w[6 * n]; st.ps.q4 = w[7 * n];
+	if (st.neeKind != NeeNone) { st.nee0 = w[8 * n]; st.nee1 = w[9 * n]; st.nee2 = w[10 * n]; }
 	st.ps.q5 = make_float4(0.f, 0.f, 0.f, 0.f);
+	st.coldValid = false; st.coldDirty = false;
+}
+RT_DEV void needCold(const PathBuffers& b, uint32_t pix, PathState& st) {
+	if (!st.coldValid) {
+		st.ps.q0 = b.cold[2 * size_t(pix)]; st.ps.q3 = b.cold[2 * size_t(pix) + 1];
+		st.coldValid = true;
+	}
 }
 
 // StreamSampler::add (gris_path_trace.glsl:21-32); the selected sample goes straight to the pixel's reservoir slot
-RT_DEV void streamAdd(PathState& st, RptGRISReservoir* __restrict__ slot, float w, float r) {
+RT_DEV void streamAdd(PathState& st, const GRISResv& sample, RptGRISReservoir* __restrict__ slot, float w, float r) {
 	st.streamSumWeight += w;
 	if (r * st.streamSumWeight < w) {
 		st.streamWeight = w;
 		st.streamWritten = true;
 		float4* q = reinterpret_cast<float4*>(slot);
-		q[0] = st.ps.q0; q[1] = st.ps.q1; q[2] = st.ps.q2; q[3] = st.ps.q3; q[4] = st.ps.q4;
+		q[0] = sample.q0; q[1] = sample.q1; q[2] = sample.q2; q[3] = sample.q3; q[4] = sample.q4;
 	}
 }
 
 // end of tracePath (gris_path_trace.glsl:259-278)
-RT_DEV void finishPath(PathState& st, RptGRISReservoir* __restrict__ slot) {
+RT_DEV void finishPath(const PathBuffers& b, uint32_t pix, PathState& st, RptGRISReservoir* __restrict__ slot) {
 	if (st.sampleState == 2 && st.lastSampleState == 2) {
-		streamAdd(st, slot, luminance(st.ps.F()), sample1f(st.rng));
+		needCold(b, pix, st);
+		streamAdd(st, st.ps, slot, luminance(st.ps.F()), sample1f(st.rng));
 	}
 	float4* q = reinterpret_cast<float4*>(slot);
 	const bool scaled = st.streamSumWeight > 0 && st.streamWeight > 0;
@@ -311,6 +351,13 @@ RT_DEV void finishPath(PathState& st, RptGRISReservoir* __restrict__ slot) {
 		q[1] = z; q[2] = z; q[3] = z; q[4] = z;
 		q[5] = make_float4(1.0f, 0.f, 0.f, 0.f);
 	}
+}
+
+RT_DEV void setRcVertex(PathState& st, float4 isecWord, float prevSamplePdf, float jacobian) {
+	st.ps.q0 = isecWord;
+	st.ps.q1.w = __uint_as_float(st.rng);
+	st.ps.q3 = make_float4(0.f, 0.f, prevSamplePdf, jacobian);   // the two pad words are never written: always 0
+	st.coldValid = true; st.coldDirty = true;
 }
 
 struct VertexOut {
@@ -347,25 +394,19 @@ RT_DEV bool vertexStage(PathState& st, const RptGRISSettings& set, const Surface
 				ps.setF(ps.F() + weightedLi * st.throughput);
 			}
 			else if ((st.sampleState == 2 && st.lastSampleState == 1) && st.isLastVertexConnectible && distToPrev > GRISDistanceThreshold) {
-				ps.q0 = isecWord;
-				ps.q1.w = __uint_as_float(st.rng);
-				ps.rcPrevSamplePdf() = st.bsPdf;
-				ps.rcJacobian() = geometryJacobian;
+				setRcVertex(st, isecWord, st.bsPdf, geometryJacobian);
 				ps.setRcLi(weightedLi);
 				ps.setRcWi(f3(0.0f));
 				ps.setF(weightedLi * st.throughput);
 				ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcLightScattered));
-				streamAdd(st, slot, luminance(ps.F()), out.resvRandSample);
+				streamAdd(st, ps, slot, luminance(ps.F()), out.resvRandSample);
 			}
 		}
 		return false;
 	}
 	const bool connectible = st.isThisVertexConnectible && st.isLastVertexConnectible && distToPrev > GRISDistanceThreshold;
 	if ((st.sampleState == 2 && st.lastSampleState == 1) && (connectible || set.shiftType == ShiftReconnection)) {
-		ps.q0 = isecWord;
-		ps.q1.w = __uint_as_float(st.rng);
-		ps.rcPrevSamplePdf() = st.bsPdf;
-		ps.rcJacobian() = geometryJacobian;
+		setRcVertex(st, isecWord, st.bsPdf, geometryJacobian);
 		ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(bounce)), RcSurface));
 		st.rcThroughput = f3(1.0f);
 	}
@@ -374,34 +415,66 @@ RT_DEV bool vertexStage(PathState& st, const RptGRISSettings& set, const Surface
 	return true;
 }
 
-// NEE contributions (gris_path_trace.glsl:186-223) of an unoccluded light sample
-RT_DEV void neeStage(PathState& st, const Surface& surf, const Mat& mat, const LightSample& ls, float resvRandSample, RptGRISReservoir* __restrict__ slot) {
-	GRISResv& ps = st.ps;
+// NEE of the current vertex (gris_path_trace.glsl:176-223): evaluates the light sample and records what it WILL
+// contribute if its shadow ray finds nothing; returns false when nothing could be contributed (no ray needed)
+RT_DEV bool neePrepare(PathState& st, const Surface& surf, const Mat& mat, const LightSample& ls, float resvRandSample) {
+	st.neeKind = NeeNone;
+	if (!(ls.pdf > 1e-6f)) return false;
 	const float3 wo = -st.dir;
 	const float bsdfPdf = absDot(surf.norm, ls.wi) * RT_PI_INV;
 	const float weight = MISWeight(ls.pdf, bsdfPdf);
 	const float3 scatterTerm = evalBSDF(mat, surf.albedo, surf.norm, wo, ls.wi) * satDot(surf.norm, ls.wi);
 	const float3 weightedLi = ls.radiance / ls.pdf * weight;
+	st.neeResvRand = resvRandSample;
 	if (st.sampleState == 2 && st.lastSampleState == 2) {
-		ps.setRcLi(ps.rcLi() + weightedLi * scatterTerm * st.rcThroughput);
-		ps.setF(ps.F() + weightedLi * scatterTerm * st.throughput);
+		const float3 dRc = weightedLi * scatterTerm * st.rcThroughput, dF = weightedLi * scatterTerm * st.throughput;
+		st.neeKind = NeeAccumulate;
+		st.nee0 = make_float4(dRc.x, dRc.y, dRc.z, 0.f);
+		st.nee1 = make_float4(dF.x, dF.y, dF.z, 0.f);
+		st.nee2 = make_float4(0.f, 0.f, 0.f, 0.f);
 	}
 	else if (st.sampleState == 2 && st.lastSampleState == 1) {
-		ps.setRcLi(weightedLi);
-		ps.setRcWi(ls.wi);
-		ps.setF(weightedLi * scatterTerm * st.throughput);
-		streamAdd(st, slot, luminance(ps.F()), resvRandSample);
+		const float3 F = weightedLi * scatterTerm * st.throughput;
+		st.neeKind = NeeRcVertex;
+		st.nee0 = make_float4(weightedLi.x, weightedLi.y, weightedLi.z, 0.f);
+		st.nee1 = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, 0.f);
+		st.nee2 = make_float4(F.x, F.y, F.z, 0.f);
 	}
 	else if (st.sampleState == 1 && st.isThisVertexConnectible && ls.dist > GRISDistanceThreshold) {
-		ps.q0 = make_float4(ls.bary.x, ls.bary.y, __uint_as_float(0u), __uint_as_float(ls.id));
-		ps.q1.w = __uint_as_float(st.rng);
-		ps.rcPrevSamplePdf() = ls.pdf;
-		ps.rcJacobian() = ls.jacobian;
-		ps.setRcLi(ls.radiance * weight);
+		const float3 rcLi = ls.radiance * weight, F = weightedLi * scatterTerm * st.throughput;
+		st.neeKind = NeeLightSampled;
+		st.nee0 = make_float4(ls.bary.x, ls.bary.y, __uint_as_float(ls.id), ls.pdf);
+		st.nee1 = make_float4(rcLi.x, rcLi.y, rcLi.z, ls.jacobian);
+		st.nee2 = make_float4(F.x, F.y, F.z, __uint_as_float(st.rng));
+	}
+	return st.neeKind != NeeNone;
+}
+
+// ... and its application once the shadow ray is known to be unoccluded.  neeBounce = bounce index of that vertex.
+RT_DEV void neeApply(const PathBuffers& b, uint32_t pix, PathState& st, int neeBounce, RptGRISReservoir* __restrict__ slot) {
+	GRISResv& ps = st.ps;
+	if (st.neeKind == NeeAccumulate) {
+		ps.setRcLi(ps.rcLi() + f3(st.nee0));
+		ps.setF(ps.F() + f3(st.nee1));
+	}
+	else if (st.neeKind == NeeRcVertex) {
+		// the shader sets rcLi / rcWi / F, inserts the sample, and the BSDF-sampling step right after overwrites the
+		// three fields again (:246-250); only the inserted copy ever sees them
+		needCold(b, pix, st);
+		GRISResv tmp = ps;
+		tmp.setRcLi(f3(st.nee0)); tmp.setRcWi(f3(st.nee1)); tmp.setF(f3(st.nee2));
+		streamAdd(st, tmp, slot, luminance(tmp.F()), st.neeResvRand);
+	}
+	else if (st.neeKind == NeeLightSampled) {
+		ps.q0 = make_float4(st.nee0.x, st.nee0.y, __uint_as_float(0u), st.nee0.z);
+		ps.q1.w = st.nee2.w;
+		ps.q3 = make_float4(0.f, 0.f, st.nee0.w, st.nee1.w);
+		st.coldValid = true; st.coldDirty = true;
+		ps.setRcLi(f3(st.nee1));
 		ps.setRcWi(f3(0.0f));
-		ps.setF(weightedLi * scatterTerm * st.throughput);
-		ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(st.bounce + 1)), RcLightSampled));
-		streamAdd(st, slot, luminance(ps.F()), resvRandSample);
+		ps.setF(f3(st.nee2));
+		ps.setFlags(withRcVertexType(withRcVertexId(ps.flags(), uint32_t(neeBounce + 1)), RcLightSampled));
+		streamAdd(st, ps, slot, luminance(ps.F()), st.neeResvRand);
 	}
 }
 
@@ -441,13 +514,9 @@ RT_DEV bool scatterStage(PathState& st, const RptGRISSettings& set, const Surfac
 	return st.bounce < 15;
 }
 
-constexpr uint32_t SlotEnded = 0xfffffffeu, SlotNoShadow = 0xffffffffu;
-constexpr int ShadeBlock = 128;
-
-// appends one entry per requesting lane to a device queue: one atomic per warp
-RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count, bool want) {
-	const unsigned mask = __ballot_sync(__activemask(), want);
-	if (!want) return 0u;
+// appends one entry per calling lane to a device queue: one atomic per converged group of lanes
+RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count) {
+	const unsigned mask = __activemask();
 	const uint32_t lane = threadIdx.x & 31u;
 	const int leader = __ffs(int(mask)) - 1;
 	uint32_t base = 0;
@@ -456,17 +525,51 @@ RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count, bool want) {
 	return base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
 }
 
-RT_DEV void pushExtensionRay(const FrameView& f, int nextBounce, uint32_t pix, float3 ori, float3 dir) {
-	uint32_t* cnt = f.wf.counters + 4 * nextBounce;
-	const uint32_t slot = queueAppend(cnt, true);
-	float4* rq = f.wf.rays[nextBounce & 1] + 2 * size_t(slot);
-	rq[0] = make_float4(ori.x, ori.y, ori.z, MinRayDistance);
-	rq[1] = make_float4(dir.x, dir.y, dir.z, MaxRayDistance);
-	f.wf.pix[nextBounce & 1][slot] = pix;
+RT_DEV PathBuffers pathBuffers(const FrameView& f, int bounce) {
+	PathBuffers b;
+	b.hot = f.wf.state[bounce & 1]; b.cold = f.wf.cold; b.capacity = f.wf.capacity;
+	return b;
 }
 
-// bounce 0: the primary hit comes from the G-buffer, there is no NEE (gris_path_trace.glsl:176), so vertex and scatter
-// stages run back to back.  One thread per pixel in 8x4-tile order.
+// light sample + scatter of the current vertex, then hand the path to the next bounce (or end it)
+RT_DEV void shadeAndContinue(const FrameView& f, const SceneView& s, const RptGRISSettings& set, PathState& st, const Surface& surf, const Mat& mat,
+                             const VertexOut& vo, uint32_t pix, RptGRISReservoir* __restrict__ slot) {
+	const int bounce = st.bounce;
+	st.neeKind = NeeNone;
+	if (bounce > 0 && !isBSDFDelta(mat)) {
+		const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
+		if (neePrepare(st, surf, mat, ls, vo.resvRandSample)) {
+			st.shadowIdx = queueAppend(f.wf.counters + 4 * bounce + 1);
+			float4* rq = f.wf.shadowRays[bounce & 1] + 2 * size_t(st.shadowIdx);
+			rq[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
+			rq[1] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
+		}
+	}
+	float3 rayOri = f3(0.0f);
+	const bool go = scatterStage(st, set, surf, mat, rayOri);
+	if (!go) st.bounce = bounce;   // a path that ends keeps the index of its last vertex (its light sample may still be pending)
+	const PathBuffers next = pathBuffers(f, bounce + 1);
+	if (!go && st.neeKind == NeeNone) {   // nothing pending: the path ends here
+		finishPath(next, pix, st, slot);   // (cold words are per pixel: either PathBuffers view works)
+		return;
+	}
+	st.zombie = !go;
+	const uint32_t nslot = queueAppend(f.wf.counters + 4 * (bounce + 1));
+	float4* rq = f.wf.rays[(bounce + 1) & 1] + 2 * size_t(nslot);
+	if (go) {
+		rq[0] = make_float4(rayOri.x, rayOri.y, rayOri.z, MinRayDistance);
+		rq[1] = make_float4(st.dir.x, st.dir.y, st.dir.z, MaxRayDistance);
+	}
+	else {   // zombie: an empty interval, the traversal kernel reports a miss without touching the BVH
+		rq[0] = make_float4(0.f, 0.f, 0.f, 1.0f);
+		rq[1] = make_float4(0.f, 0.f, 1.f, 0.0f);
+	}
+	f.wf.pix[(bounce + 1) & 1][nslot] = pix;
+	storePathState(next, nslot, pix, st);
+}
+
+// bounce 0: the primary hit comes from the G-buffer and there is no light sample (gris_path_trace.glsl:176).
+// One thread per pixel in 8x4-tile order.
 __global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set) {
 	const uint32_t tilesX = (f.width + 7u) / 8u;
 	const uint32_t id = blockIdx.x * ShadeBlock + threadIdx.x;
@@ -484,123 +587,56 @@ __global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_const
 	st.throughput = f3(1.0f); st.rcThroughput = f3(0.0f); st.lastPos = f3(0.0f);
 	st.bsPdf = 0.0f; st.bsType = 0;
 	st.sampleState = 0; st.lastSampleState = 0;
-	st.isLastVertexConnectible = false; st.isThisVertexConnectible = false; st.streamWritten = false;
+	st.isLastVertexConnectible = false; st.isThisVertexConnectible = false; st.streamWritten = false; st.zombie = false;
 	st.bounce = 0;
 	st.streamWeight = 0.0f; st.streamSumWeight = 0.0f;
+	st.neeKind = NeeNone; st.shadowIdx = 0; st.neeResvRand = 0.0f;
+	st.nee0 = st.nee1 = st.nee2 = make_float4(0.f, 0.f, 0.f, 0.f);
 	st.ps = zeroGRIS();   // GRISPathSampleReset, gris_reservoir.glsl:61-69
 	st.ps.q0.z = __uint_as_float(InvalidHitIndex);
 	st.ps.q4.w = __uint_as_float(st.rng);   // primaryRng
+	st.coldValid = true; st.coldDirty = true;
 
 	const Surface surf = primarySurface(p);
 	const Mat mat = loadMaterial(s, uint32_t(p.matId));
 	VertexOut vo;
-	float3 rayOri;
+	vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
 	const float4 isecWord = make_float4(0.f, 0.f, __uint_as_float(0u), __uint_as_float(0u));
-	bool go = vertexStage(st, set, surf, mat, isecWord, s.lightTable[0].prob, slot, vo);
-	if (go) go = scatterStage(st, set, surf, mat, rayOri);
-	if (!go) { finishPath(st, slot); return; }
-	storePathState(f.wf.state, pix, st);
-	pushExtensionRay(f, 1, pix, rayOri, st.dir);
+	if (!vertexStage(st, set, surf, mat, isecWord, s.lightTable[0].prob, slot, vo)) {
+		finishPath(pathBuffers(f, 1), pix, st, slot);
+		return;
+	}
+	shadeAndContinue(f, s, set, st, surf, mat, vo, pix, slot);
 }
 
-// [vertex] of bounce >= 1: one thread per slot of the bounce's extension queue
-__global__ void __launch_bounds__(ShadeBlock) grisVertexKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
+// bounce >= 1: one thread per slot of the bounce's extension queue
+__global__ void __launch_bounds__(ShadeBlock) grisBounceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
 	const uint32_t n = f.wf.counters[4 * bounce];
 	const float sumPower = s.lightTable[0].prob;
+	const PathBuffers cur = pathBuffers(f, bounce);
 	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
 		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
-		const RptIntersection hit = f.wf.hits[slotIdx];
 		RptGRISReservoir* slot = f.grisThis + pix;
-		float4* vtx = f.wf.vertex + size_t(slotIdx) * VertexWords;
 		PathState st;
-		loadPathState(f.wf.state, pix, st);
-		if (hit.instanceIdx == InvalidHitIndex) {   // the ray left the scene (gris_path_trace.glsl:92-94)
-			finishPath(st, slot);
-			vtx[2].w = __uint_as_float(SlotEnded);
-			continue;
+		loadPathState(cur, slotIdx, st);
+		// (1) the light sample of the previous vertex
+		if (st.neeKind != NeeNone) {
+			if (f.wf.occluded[(bounce - 1) & 1][st.shadowIdx] == 0) neeApply(cur, pix, st, st.zombie ? st.bounce : st.bounce - 1, slot);   // index of the vertex that drew the sample
+			st.neeKind = NeeNone;
 		}
+		if (st.zombie) { finishPath(cur, pix, st, slot); continue; }
+		// (2) the vertex the extension ray found
+		const RptIntersection hit = f.wf.hits[slotIdx];
+		if (hit.instanceIdx == InvalidHitIndex) { finishPath(cur, pix, st, slot); continue; }   // left the scene (:92-94)
 		Surface surf;
 		loadSurfaceInfo(s, hit, surf);
 		const Mat mat = loadMaterial(s, surf.matIndex);
 		VertexOut vo;
 		vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
 		const float4 isecWord = make_float4(hit.bary[0], hit.bary[1], __uint_as_float(hit.instanceIdx), __uint_as_float(hit.triangleIdx));
-		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) {
-			finishPath(st, slot);
-			vtx[2].w = __uint_as_float(SlotEnded);
-			continue;
-		}
-		uint32_t shadowIdx = SlotNoShadow;
-		const bool nee = !isBSDFDelta(mat);
-		if (nee) {
-			const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
-			shadowIdx = queueAppend(f.wf.counters + 4 * bounce + 1, true);
-			float4* rq = f.wf.shadowRays + 2 * size_t(shadowIdx);
-			rq[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
-			rq[1] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
-		}
-		storePathState(f.wf.state, pix, st);
-		vtx[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, __uint_as_float(surf.matIndex));
-		vtx[1] = make_float4(surf.norm.x, surf.norm.y, surf.norm.z, vo.resvRandSample);
-		vtx[2] = make_float4(surf.albedo.x, surf.albedo.y, surf.albedo.z, __uint_as_float(shadowIdx));
-		vtx[3] = vo.lightRandSample;
-	}
-}
-
-// [scatter] of bounce >= 1: one thread per slot of the same queue
-__global__ void __launch_bounds__(ShadeBlock) grisScatterKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
-	const uint32_t n = f.wf.counters[4 * bounce];
-	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
-		const float4* vtx = f.wf.vertex + size_t(slotIdx) * VertexWords;
-		const float4 v2 = vtx[2];
-		const uint32_t shadowIdx = __float_as_uint(v2.w);
-		if (shadowIdx == SlotEnded) continue;
-		const float4 v0 = vtx[0], v1 = vtx[1];
-		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
-		RptGRISReservoir* slot = f.grisThis + pix;
-		PathState st;
-		loadPathState(f.wf.state, pix, st);
-		Surface surf;
-		surf.pos = f3(v0); surf.norm = f3(v1); surf.albedo = f3(v2); surf.matIndex = __float_as_uint(v0.w); surf.isLight = false;
-		const Mat mat = loadMaterial(s, surf.matIndex);
-		if (shadowIdx != SlotNoShadow && f.wf.occluded[shadowIdx] == 0) {
-			const LightSample ls = sampleLight(s, surf.pos, vtx[3]);
-			if (ls.pdf > 1e-6f) neeStage(st, surf, mat, ls, v1.w, slot);
-		}
-		float3 rayOri;
-		if (!scatterStage(st, set, surf, mat, rayOri)) { finishPath(st, slot); continue; }
-		storePathState(f.wf.state, pix, st);
-		pushExtensionRay(f, bounce + 1, pix, rayOri, st.dir);
-	}
-}
-
-// experiment: vertex + in-line shadow ray + scatter in one kernel (one state round trip per bounce)
-__global__ void __launch_bounds__(ShadeBlock) grisShadeFusedKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
-	const uint32_t n = f.wf.counters[4 * bounce];
-	const float sumPower = s.lightTable[0].prob;
-	for (uint32_t slotIdx = blockIdx.x * ShadeBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * ShadeBlock) {
-		const uint32_t pix = f.wf.pix[bounce & 1][slotIdx];
-		const RptIntersection hit = f.wf.hits[slotIdx];
-		RptGRISReservoir* slot = f.grisThis + pix;
-		PathState st;
-		loadPathState(f.wf.state, pix, st);
-		if (hit.instanceIdx == InvalidHitIndex) { finishPath(st, slot); continue; }
-		Surface surf;
-		loadSurfaceInfo(s, hit, surf);
-		const Mat mat = loadMaterial(s, surf.matIndex);
-		VertexOut vo;
-		vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
-		const float4 isecWord = make_float4(hit.bary[0], hit.bary[1], __uint_as_float(hit.instanceIdx), __uint_as_float(hit.triangleIdx));
-		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) { finishPath(st, slot); continue; }
-		if (!isBSDFDelta(mat)) {
-			const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
-			const bool shadowed = traceShadow(s, surf.pos, MinRayDistance, ls.wi, ls.dist - MinRayDistance);
-			if (!shadowed && ls.pdf > 1e-6f) neeStage(st, surf, mat, ls, vo.resvRandSample, slot);
-		}
-		float3 rayOri;
-		if (!scatterStage(st, set, surf, mat, rayOri)) { finishPath(st, slot); continue; }
-		storePathState(f.wf.state, pix, st);
-		pushExtensionRay(f, bounce + 1, pix, rayOri, st.dir);
+		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) { finishPath(cur, pix, st, slot); continue; }
+		// (3) + (4)
+		shadeAndContinue(f, s, set, st, surf, mat, vo, pix, slot);
 	}
 }
 
@@ -681,21 +717,17 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(cons
 }
 
 void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
-	static const int vertexBlocks = persistentBlocks(reinterpret_cast<const void*>(grisVertexKernel), ShadeBlock);
-	static const int scatterBlocks = persistentBlocks(reinterpret_cast<const void*>(grisScatterKernel), ShadeBlock);
+	static const int bounceBlocks = persistentBlocks(reinterpret_cast<const void*>(grisBounceKernel), ShadeBlock);
 	const uint32_t rows = f.rowEnd - f.rowBegin;
 	const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
 	cudaMemsetAsync(f.wf.counters, 0, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), st);
 	grisBeginKernel<<<(slots + ShadeBlock - 1) / ShadeBlock, ShadeBlock, 0, st>>>(f, s, p);
-	static const int fusedMode = getenv("RPT_FUSED_SHADE") ? atoi(getenv("RPT_FUSED_SHADE")) : 0;
-	static const int fusedBlocks = persistentBlocks(reinterpret_cast<const void*>(grisShadeFusedKernel), ShadeBlock);
-	for (int bounce = 1; bounce < 15; bounce++) {
+	// bounce 15 only drains the paths whose last light sample is still pending
+	for (int bounce = 1; bounce <= 15; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
-		launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
-		if (fusedMode) { grisShadeFusedKernel<<<fusedBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce); continue; }
-		grisVertexKernel<<<vertexBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
-		launchTraceQueueAny(s, f.wf.shadowRays, c + 1, 0, c + 3, f.wf.occluded, st);
-		grisScatterKernel<<<scatterBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
+		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c - 4 + 1, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);
+		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		grisBounceKernel<<<bounceBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 	}
 }
 void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {

@@ -55,20 +55,19 @@ struct SceneView {
 	unsigned long long* counters; // RptCounters layout, or nullptr when counting is off
 };
 
-// Wavefront path-tracing buffers of one frame (passes_gris.cu, trace_queue.cu).  All indexed by queue slot except
-// `state`, which is indexed by the pixel's storage index.
-constexpr int PathStateWords = 10;    // float4 words per pixel
-constexpr int VertexWords = 4;        // float4 words handed from the vertex stage to the scatter stage, per slot
+// Wavefront path-tracing buffers of one frame (passes_gris.cu, trace_queue.cu); layout described there.
+constexpr int PathStateWords = 11;    // float4 planes of the per-slot path state
 constexpr int WavefrontMaxBounces = 16;
 struct WavefrontView {
-	float4* state;
-	float4* vertex;
-	float4* rays[2];                  // extension-ray queues (ping-pong over bounces): {o, tmin}, {d, tmax}
+	float4* state[2];                 // [bounce & 1]: PathStateWords planes of `capacity` float4, indexed by queue slot
+	float4* cold;                     // 2 float4 per pixel (storage index): rarely touched words of the path sample
+	float4* rays[2];                  // extension-ray queues: {o, tmin}, {d, tmax} per slot
 	uint32_t* pix[2];                 // pixel storage index of each slot
 	RptIntersection* hits;            // closest hit of each slot of the current queue
-	float4* shadowRays;
-	uint8_t* occluded;
+	float4* shadowRays[2];            // shadow-ray queues
+	uint8_t* occluded[2];
 	uint32_t* counters;               // [bounce][4]: extension count, shadow count, extension head, shadow head
+	uint32_t capacity;                // slots per queue = pixels of the owned rows
 };
 
 struct FrameView {
