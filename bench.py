@@ -182,7 +182,7 @@ def run_reference(args):
 def run_cuda(args):
     import torch
     import restirpt
-    from restirpt import GRISSettings, PassStats, Counters, PASS_NAMES, P
+    from restirpt import GRISSettings, PassStats, Counters, PASS_NAMES, KERNEL_NAMES, P
     from restirpt import multigpu
 
     rank = int(os.environ.get("RANK", "0"))
@@ -287,18 +287,54 @@ def run_cuda(args):
 
     if rank == 0:
         px = fw * rows
+        steps = args.steps
         per_pass_ms = {PASS_NAMES[i]: stats.ms[i] / max(stats.launches[i], 1) for i in range(12) if stats.launches[i]}
-        launches = int(sum(stats.launches))
-        dom = max(per_pass_ms, key=per_pass_ms.get)
-        c = counters[dom]
-        rays = c.closestRays + c.shadowRays
-        # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record
-        # in/out, 272 B per shaded hit, plus the pass's per-pixel stream traffic
-        stream_bytes = {"gbuffer": 28 + 16, "gris_pathtrace": 24 + 96, "gris_temporal": 24 + 4 + 24 + 96 + 96 + 96,
-                        "gris_spatial": 24 + 96 + 3 * (24 + 96) + 96 + 32}[dom]
-        alg_bytes = 80 * c.nodeVisits + 48 * c.triTests + 48 * rays + 272 * c.shadedHits + px * stream_bytes
+        # kernels: single-kernel passes as they are; the wavefront path-tracing pass split into its kernels (events between
+        # the launches on the frame's stream; its tail, which runs concurrently on a second stream, is not in these figures)
+        kernels = {}
+        for name in ("gbuffer", "gris_temporal", "gris_spatial", "postprocess"):
+            i = PASS_NAMES.index(name)
+            if stats.launches[i]:
+                kernels[name] = {"ms_per_frame": stats.ms[i] / steps, "launches_per_frame": stats.launches[i] / steps}
+        for k, name in enumerate(KERNEL_NAMES):
+            if stats.kernelLaunches[k]:
+                kernels[name] = {"ms_per_frame": stats.kernelMs[k] / steps, "launches_per_frame": stats.kernelLaunches[k] / steps}
+        launches = int(sum(v["launches_per_frame"] for v in kernels.values()) * steps)
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_frame"])
+        # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record in/out,
+        # 272 B per shaded hit, plus the kernel's per-pixel stream traffic; counts from the instrumented frame below
+        cp, cs, ct, cg = (counters[k] for k in ("gris_pathtrace", "gris_spatial", "gris_temporal", "gbuffer"))
+
+        def ray_bytes(c, kind):
+            if kind == "closest":
+                return 80 * (c.nodeVisits - c.shadowNodeVisits) + 48 * (c.triTests - c.shadowTriTests) + 48 * c.closestRays
+            if kind == "any":
+                return 80 * c.shadowNodeVisits + 48 * c.shadowTriTests + 33 * c.shadowRays
+            return 80 * c.nodeVisits + 48 * c.triTests + 48 * (c.closestRays + c.shadowRays)
+
+        state_bytes = 11 * 16 * 2 + 16 + 8 + 1 + 64   # path state planes in + out, hit, pixel ids, visibility byte, two ray records
+        alg = {
+            "gbuffer": ray_bytes(cg, "all") + 272 * cg.shadedHits + px * (28 + 16),
+            "gris_temporal": ray_bytes(ct, "all") + 272 * ct.shadedHits + px * (24 + 4 + 24 + 96 + 96 + 96),
+            "gris_spatial": ray_bytes(cs, "all") + 272 * cs.shadedHits + px * (24 + 96 + 3 * (24 + 96) + 96 + 32),
+            "postprocess": px * 36,
+            "trace_closest": ray_bytes(cp, "closest"),
+            "trace_any": ray_bytes(cp, "any"),
+            "gris_begin": px * (24 + state_bytes // 2 + 36),
+            "gris_bounce": 272 * cp.shadedHits + cp.closestRays * state_bytes + px * 96,
+        }
+        nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "gris_temporal": ct.closestRays + ct.shadowRays,
+                 "gris_spatial": cs.closestRays + cs.shadowRays, "trace_closest": cp.closestRays, "trace_any": cp.shadowRays}
+        for name, v in kernels.items():
+            v["algorithmic_gb_per_frame"] = alg[name] / 1e9
+            v["achieved_gbs"] = alg[name] / (v["ms_per_frame"] * 1e-3) / 1e9
+            if name in nrays:
+                v["mrays_per_s"] = nrays[name] / 1e6 / (v["ms_per_frame"] * 1e-3)
         peak, peak_src = measured_peak_gbs()
-        achieved = alg_bytes / (per_pass_ms[dom] * 1e-3) / 1e9
+        c = {"gris_spatial": cs, "gris_temporal": ct, "gbuffer": cg}.get(dom, cp)
+        rays = c.closestRays + c.shadowRays
+        lpf = kernels[dom]["launches_per_frame"]
+        achieved = kernels[dom]["achieved_gbs"]
         total_rays = sum(v.closestRays + v.shadowRays for v in counters.values())
         fps = 1000.0 * args.steps / dev_ms
         line = {
@@ -309,20 +345,21 @@ def run_cuda(args):
                                    "ResampledPT {Hybrid, rrScale 1, temporal 1, spatial 1, cap 20}, seed hash2(frame+1), static camera",
                        "film_frames_per_s": fps, "halo_rows": halo,
                        "halo_exchange": (link.describe() if link else "none (single GPU)"),
-                       "l2_policy": "inputs larger than L2: per-frame working set (G-buffer + 3 reservoir buffers + outputs "
-                                    "~1.0 GB at 1080p) exceeds the 126 MB L2; every frame uses a new seed",
+                       "l2_policy": "inputs larger than L2: per-frame working set (G-buffer + 3 reservoir buffers + path state + outputs "
+                                    "~1.8 GB at 1080p) exceeds the 126 MB L2; every frame uses a new seed",
                        "mrays_per_s_per_gpu": total_rays / 1e6 * fps,
                        "rays_per_pixel": total_rays / px,
-                       "pass_ms": per_pass_ms},
+                       "pass_ms": per_pass_ms, "kernels": kernels},
             "e2e": {"value": 1000.0 * args.steps / e2e_ms * world, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 352, "d2h_bytes_per_step": strip_bytes},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": per_pass_ms[dom],
+                         "algorithmic_bytes_per_launch": alg[dom] / lpf, "kernel_ms": kernels[dom]["ms_per_frame"] / lpf,
+                         "launches_per_frame": lpf,
                          "nodes_per_ray": c.nodeVisits / max(rays, 1), "tris_per_ray": c.triTests / max(rays, 1),
-                         "note": "VeachAjar's BVH + triangles (23 MB) are L2-resident: the kernel is latency/divergence-bound, "
-                                 "not HBM-bound; the fraction is reported against the HBM copy peak as the contract asks"},
+                         "note": "VeachAjar's BVH + triangles (23 MB) are L2-resident: the traversal kernels are instruction-issue / "
+                                 "latency-bound, not HBM-bound (profiles/); the fraction is reported against the HBM copy peak as the contract asks"},
             "clocks": clock_info,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -196,6 +196,8 @@ typedef struct RptCounters {
 	uint64_t nodeVisits;     /* CWBVH nodes fetched (80 B each)  */
 	uint64_t triTests;       /* triangles fetched (48 B each)    */
 	uint64_t shadedHits;     /* loadSurfaceInfo gathers (272 B)  */
+	uint64_t shadowNodeVisits;   /* the share of nodeVisits / triTests spent on occlusion rays */
+	uint64_t shadowTriTests;
 } RptCounters;
 
 typedef struct RptBvhStats {
@@ -215,9 +217,18 @@ typedef enum RptPassId {
 	RPT_PASS_COUNT = 12
 } RptPassId;
 
+/* kernels inside the multi-kernel wavefront passes, timed individually (events between the launches on the frame's
+ * stream; the path-tracing tail that runs on the second stream is not included) */
+typedef enum RptKernelId {
+	RPT_KERNEL_TRACE_CLOSEST = 0, RPT_KERNEL_TRACE_ANY = 1, RPT_KERNEL_GRIS_BEGIN = 2, RPT_KERNEL_GRIS_BOUNCE = 3,
+	RPT_KERNEL_COUNT = 8
+} RptKernelId;
+
 typedef struct RptPassStats {
 	double ms[RPT_PASS_COUNT];         /* accumulated device time per pass since rpt_frame_timing(frame, 1) */
 	uint64_t launches[RPT_PASS_COUNT]; /* kernel launches per pass */
+	double kernelMs[RPT_KERNEL_COUNT];         /* the same per kernel of the wavefront passes */
+	uint64_t kernelLaunches[RPT_KERNEL_COUNT];
 } RptPassStats;
 
 typedef struct RptCtx RptCtx;

@@ -222,6 +222,7 @@ done:
 	if (s.counters != nullptr) {
 		atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
 		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
+		if (MODE == TraceAny) { atomicAdd(&s.counters[5], (unsigned long long)nodeVisits); atomicAdd(&s.counters[6], (unsigned long long)triTests); }
 		atomicAdd(&s.counters[3], (unsigned long long)triTests);
 	}
 	if (MODE == TraceCount && candidateCount) *candidateCount = res.count;

@@ -52,6 +52,9 @@ struct RptFrame {
 	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
 	uint32_t* work = nullptr;                  // WorkCounterCount queue heads of the persistent kernels
 	WavefrontView wf{};                        // wavefront path-tracing queues (owned rows only)
+	cudaStream_t tailStream = nullptr;         // the long tail of the path-tracing pass runs here ...
+	cudaEvent_t tailFork = nullptr, tailDone = nullptr;
+	bool tailPending = false;                  // ... until the next pass joins it back into `stream`
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
@@ -60,12 +63,17 @@ struct RptFrame {
 	uint32_t grisEpoch = 0, diEpoch = 0;
 
 	// per-pass timing
-	struct Pending { int pass; cudaEvent_t a, b; };
+	struct Pending { int pass; cudaEvent_t a, b; bool poolB; };
 	bool timing = false;
 	std::vector<Pending> pending;
 	std::vector<cudaEvent_t> eventPool;
 	RptPassStats stats{};
 };
+
+// the tail of the last path-tracing pass (second stream) must be complete before anything else touches the frame
+static void joinTail(RptFrame* f) {
+	if (f->tailPending) { cudaStreamWaitEvent(f->stream, f->tailDone, 0); f->tailPending = false; }
+}
 
 static cudaEvent_t takeEvent(RptFrame* f) {
 	if (!f->eventPool.empty()) { cudaEvent_t e = f->eventPool.back(); f->eventPool.pop_back(); return e; }
@@ -76,8 +84,12 @@ static cudaEvent_t takeEvent(RptFrame* f) {
 static void drainTiming(RptFrame* f) {
 	for (auto& p : f->pending) {
 		float ms = 0.f;
-		if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { f->stats.ms[p.pass] += ms; f->stats.launches[p.pass] += 1; }
-		f->eventPool.push_back(p.a); f->eventPool.push_back(p.b);
+		if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+			if (p.pass < RPT_PASS_COUNT) { f->stats.ms[p.pass] += ms; f->stats.launches[p.pass] += 1; }
+			else { f->stats.kernelMs[p.pass - RPT_PASS_COUNT] += ms; f->stats.kernelLaunches[p.pass - RPT_PASS_COUNT] += 1; }
+		}
+		f->eventPool.push_back(p.a);
+		if (p.poolB) f->eventPool.push_back(p.b);   // kernel spans share their end event with the next span's start
 	}
 	f->pending.clear();
 }
@@ -89,10 +101,24 @@ struct PassTimer {
 	~PassTimer() {
 		if (f->timing) {
 			cudaEventRecord(b, f->stream);
-			f->pending.push_back({ pass, a, b });
+			f->pending.push_back({ pass, a, b, true });
 			if (f->pending.size() >= 4096) { cudaStreamSynchronize(f->stream); drainTiming(f); }
 		}
 	}
+};
+
+// per-kernel timing inside a multi-kernel pass: an event before every launch, the span up to the next event is
+// booked on that kernel (passes.h KernelClock)
+struct FrameKernelClock : KernelClock {
+	RptFrame* f; int last = -1; cudaEvent_t lastEv = nullptr;
+	explicit FrameKernelClock(RptFrame* f_) : f(f_) {}
+	void tick(int kernelId) override {
+		cudaEvent_t e = takeEvent(f);
+		cudaEventRecord(e, f->stream);
+		if (last >= 0) f->pending.push_back({ RPT_PASS_COUNT + last, lastEv, e, kernelId < 0 });   // the last span also returns its end event
+		last = kernelId; lastEv = e;
+	}
+	~FrameKernelClock() { if (last >= 0) tick(-1); }
 };
 
 static thread_local std::string gThreadError;
@@ -279,7 +305,7 @@ static std::vector<void**> frameSlots(RptFrame* f) {
 static std::vector<void**> wavefrontSlots(RptFrame* f) {
 	return { (void**)&f->wf.state[0], (void**)&f->wf.state[1], (void**)&f->wf.cold, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1],
 	         (void**)&f->wf.pix[0], (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays[0], (void**)&f->wf.shadowRays[1],
-	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters };
+	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters, (void**)&f->wf.tailMark, (void**)&f->wf.tailList };
 }
 static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
 // the two depthNormal images carry two extra rows (film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
@@ -291,6 +317,7 @@ static size_t slotBytes(const RptFrame* f, size_t i) {
 RPT_API int rpt_frame_clear(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_clear: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	auto slots = frameSlots(f);
 	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, slotBytes(f, i), f->stream));
 	f->cur = 0;
@@ -327,12 +354,21 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
 		auto wfs = wavefrontSlots(f);
 		const size_t wfBytes[] = { px * PathStateWords * 16, px * PathStateWords * 16, f->pixels() * 32, px * 32, px * 32, px * 4, px * 4, px * 16,
-		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) };
+		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), f->pixels() * 4, px * 4 };
 		for (size_t i = 0; i < wfs.size(); i++) {
 			e = cudaMalloc(wfs[i], wfBytes[i]);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }
 		}
 		f->wf.capacity = uint32_t(px);
+		e = cudaMemset(f->wf.tailMark, 0, f->pixels() * 4);
+		if (e == cudaSuccess) {   // highest priority: its small kernels must slip in between the blocks of the big pass on `stream`
+			int lo = 0, hi = 0;
+			cudaDeviceGetStreamPriorityRange(&lo, &hi);
+			e = cudaStreamCreateWithPriority(&f->tailStream, cudaStreamNonBlocking, hi);
+		}
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailFork, cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailDone, cudaEventDisableTiming);
+		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "tail stream"); }
 	}
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
@@ -344,7 +380,11 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device);
+	if (f->tailStream) cudaStreamSynchronize(f->tailStream);
 	if (f->stream) cudaStreamSynchronize(f->stream);
+	if (f->tailFork) cudaEventDestroy(f->tailFork);
+	if (f->tailDone) cudaEventDestroy(f->tailDone);
+	if (f->tailStream) cudaStreamDestroy(f->tailStream);
 	for (RptFrame::Peer* p : { &f->up, &f->down }) {
 		if (p->connected && p->ipc) { cudaIpcCloseMemHandle(p->grisTemp); cudaIpcCloseMemHandle(p->diTemp); cudaIpcCloseMemHandle(p->flags); }
 	}
@@ -413,7 +453,8 @@ static SceneView sceneView(const RptScene* s) {
 #define PASS_PROLOGUE(name) \
 	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, name ": NULL argument"); \
 	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, name ": frame and scene belong to different contexts"); \
-	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaSetDevice(f->ctx->device)); \
+	joinTail(f);
 #define PASS_EPILOGUE(name) \
 	CU(f->ctx, cudaGetLastError()); \
 	return RPT_OK;
@@ -481,13 +522,56 @@ static void peerAfter(RptFrame* f, PeerHook h) {
 SETTINGS_PASS(rpt_di_pathgen, RptDISettings, RPT_PASS_DI_PATHGEN, launchDIPathGen, HookNone)
 SETTINGS_PASS(rpt_di_temporal, RptDISettings, RPT_PASS_DI_TEMPORAL, launchDITemporal, HookDiTemporal)
 SETTINGS_PASS(rpt_di_spatial, RptDISettings, RPT_PASS_DI_SPATIAL, launchDISpatial, HookDiSpatial)
-SETTINGS_PASS(rpt_gris_pathtrace, RptGRISSettings, RPT_PASS_GRIS_PATHTRACE, launchGRISPathTrace, HookNone)
-SETTINGS_PASS(rpt_gris_temporal, RptGRISSettings, RPT_PASS_GRIS_TEMPORAL, launchGRISTemporal, HookGrisTemporal)
+
+// GRISReSTIR::render step 1.  Bounces 0..WavefrontTailStart-1 (all but a few percent of the rays) run on the frame's
+// stream; the long tail of the few paths that live on is enqueued on the tail stream and joined by the next pass.
+RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
+	PASS_PROLOGUE("rpt_gris_pathtrace")
+	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_pathtrace: NULL settings");
+	f->wf.epoch++;
+	const FrameView view = makeView(f);
+	const SceneView scene = sceneView(s);
+	{
+		PassTimer timer(f, RPT_PASS_GRIS_PATHTRACE);
+		FrameKernelClock clock(f);
+		launchGRISPathTraceBounces(view, scene, *st, 0, WavefrontTailStart - 1, f->stream, f->timing ? &clock : nullptr);
+	}
+	CU(f->ctx, cudaEventRecord(f->tailFork, f->stream));
+	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
+	launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);
+	CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
+	f->tailPending = true;
+	PASS_EPILOGUE("rpt_gris_pathtrace")
+}
+
+// GRISReSTIR::render step 2.  While the path-tracing tail is still running, every pixel outside it is processed
+// first; the tail's pixels follow once it is done.
+RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
+	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_gris_temporal: NULL argument");
+	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: frame and scene belong to different contexts");
+	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: NULL settings");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	peerBefore(f, HookGrisTemporal);
+	{
+		PassTimer timer(f, RPT_PASS_GRIS_TEMPORAL);
+		const FrameView view = makeView(f);
+		const SceneView scene = sceneView(s);
+		if (f->tailPending) {
+			launchGRISTemporal(view, scene, *st, f->stream, 1);
+			joinTail(f);
+			launchGRISTemporal(view, scene, *st, f->stream, 2);
+		}
+		else launchGRISTemporal(view, scene, *st, f->stream, 0);
+	}
+	peerAfter(f, HookGrisTemporal);
+	PASS_EPILOGUE("rpt_gris_temporal")
+}
 SETTINGS_PASS(rpt_gris_spatial, RptGRISSettings, RPT_PASS_GRIS_SPATIAL, launchGRISSpatial, HookGrisSpatial)
 
 RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
 	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	{ PassTimer timer(f, RPT_PASS_POSTPROCESS); launchPostProcess(makeView(f), *st, f->rgba8, f->stream); }
 	CU(f->ctx, cudaGetLastError());
 	if (rgba8Out) {
@@ -500,6 +584,7 @@ RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgb
 RPT_API int rpt_sync(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_sync: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	return RPT_OK;
 }
@@ -517,6 +602,7 @@ RPT_API int rpt_frame_timing(RptFrame* f, int enable) {
 RPT_API int rpt_frame_pass_stats(RptFrame* f, RptPassStats* out) {
 	if (!f || !out) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_pass_stats: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	drainTiming(f);
 	*out = f->stats;
@@ -534,6 +620,7 @@ RPT_API int rpt_read(RptFrame* f, RptBufferId id, void* dst, size_t bytes) {
 	void* p = framePtr(f, id);
 	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_read: bad buffer id or size");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	CU(f->ctx, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, f->stream));
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	return RPT_OK;
@@ -544,6 +631,7 @@ RPT_API int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes
 	void* p = framePtr(f, id);
 	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_write: bad buffer id or size");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	CU(f->ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, f->stream));
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	return RPT_OK;
@@ -681,6 +769,7 @@ RPT_API int rpt_trace_shadow(RptCtx* ctx, const RptScene* s, const float* rays, 
 RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
 	if (!f || !out64) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_wavefront_counters: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	CU(f->ctx, cudaMemcpy(out64, f->wf.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return RPT_OK;
@@ -706,5 +795,6 @@ RPT_API int rpt_counters_read(RptCtx* ctx, RptCounters* out) {
 	unsigned long long h[8];
 	CU(ctx, cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
 	out->closestRays = h[0]; out->shadowRays = h[1]; out->nodeVisits = h[2]; out->triTests = h[3]; out->shadedHits = h[4];
+	out->shadowNodeVisits = h[5]; out->shadowTriTests = h[6];
 	return RPT_OK;
 }

@@ -14,8 +14,13 @@ void launchDIPathGen(const FrameView& f, const SceneView& s, const RptDISettings
 void launchDITemporal(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
 void launchDISpatial(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
 void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st);
-void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
+// path tracing bounces [firstBounce, lastBounce] of the wavefront (bounce 0 = the G-buffer vertex); the C ABI layer
+// runs the long tail [WavefrontTailStart, 15] on a second stream
+struct KernelClock { virtual void tick(int rptKernelId) = 0; virtual ~KernelClock() = default; };   // called before every launch
+void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
+                                KernelClock* clock = nullptr);
+// tailMode 0: every pixel; 1: every pixel whose path is not in the tail; 2: only the pixels of the tail list
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0);
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
 void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
 

@@ -565,6 +565,7 @@ RT_DEV void shadeAndContinue(const FrameView& f, const SceneView& s, const RptGR
 		rq[1] = make_float4(0.f, 0.f, 1.f, 0.0f);
 	}
 	f.wf.pix[(bounce + 1) & 1][nslot] = pix;
+	if (bounce + 1 == WavefrontTailStart) { f.wf.tailList[nslot] = pix; f.wf.tailMark[pix] = f.wf.epoch; }
 	storePathState(next, nslot, pix, st);
 }
 
@@ -640,11 +641,8 @@ __global__ void __launch_bounds__(ShadeBlock) grisBounceKernel(const __grid_cons
 	}
 }
 
-// gris_resample_temporal.comp -> temporalReuse
-__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
-	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
-	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
-	if (x >= f.width || y >= f.rowEnd) return;
+// gris_resample_temporal.comp -> temporalReuse, one pixel
+RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t x, uint32_t y) {
 	const Primary p = loadPrimary(f, x, y);
 	if (!p.valid) return;
 	const size_t idx = f.index(x, y);
@@ -667,6 +665,23 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalKernel(
 	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
 	if (f.peerGrisUp != nullptr && y < f.rowBegin + f.halo) storeGRIS(f.peerGrisUp + (size_t(y - f.peerUpStoreBegin) * f.width + x), resv);
 	if (f.peerGrisDown != nullptr && y + f.halo >= f.rowEnd) storeGRIS(f.peerGrisDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
+}
+
+// every pixel of the owned rows; with skipTail, pixels whose path is still being traced on the tail stream are left
+// to grisTemporalTailKernel
+__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
+	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
+	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
+	if (x >= f.width || y >= f.rowEnd) return;
+	if (skipTail && f.wf.tailMark[f.index(x, y)] == f.wf.epoch) return;
+	grisTemporalPixel(f, s, st, x, y);
+}
+__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalTailKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = f.wf.counters[4 * WavefrontTailStart];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t pix = f.wf.tailList[i];
+		grisTemporalPixel(f, s, st, pix % f.width, f.storeBegin + pix / f.width);
+	}
 }
 
 // gris_resample_spatial.comp -> spatialReuse
@@ -716,22 +731,35 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(cons
 	accumulate(f.indirectOutput, f, x, y, radiance);
 }
 
-void launchGRISPathTrace(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
+void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
+                                KernelClock* clock) {
 	static const int bounceBlocks = persistentBlocks(reinterpret_cast<const void*>(grisBounceKernel), ShadeBlock);
-	const uint32_t rows = f.rowEnd - f.rowBegin;
-	const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
-	cudaMemsetAsync(f.wf.counters, 0, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), st);
-	grisBeginKernel<<<(slots + ShadeBlock - 1) / ShadeBlock, ShadeBlock, 0, st>>>(f, s, p);
+	if (firstBounce == 0) {
+		const uint32_t rows = f.rowEnd - f.rowBegin;
+		const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
+		cudaMemsetAsync(f.wf.counters, 0, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), st);
+		if (clock) clock->tick(RPT_KERNEL_GRIS_BEGIN);
+		grisBeginKernel<<<(slots + ShadeBlock - 1) / ShadeBlock, ShadeBlock, 0, st>>>(f, s, p);
+		firstBounce = 1;
+	}
 	// bounce 15 only drains the paths whose last light sample is still pending
-	for (int bounce = 1; bounce <= 15; bounce++) {
+	for (int bounce = firstBounce; bounce <= lastBounce; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
+		if (clock && bounce > 1) clock->tick(RPT_KERNEL_TRACE_ANY);
 		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c - 4 + 1, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);
+		if (clock && bounce < 15) clock->tick(RPT_KERNEL_TRACE_CLOSEST);
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		if (clock) clock->tick(RPT_KERNEL_GRIS_BOUNCE);
 		grisBounceKernel<<<bounceBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 	}
 }
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
-	grisTemporalKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p);
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode) {
+	if (tailMode == 2) {
+		static const int blocks = persistentBlocks(reinterpret_cast<const void*>(grisTemporalTailKernel), PassBlockX * PassBlockY);
+		grisTemporalTailKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
+		return;
+	}
+	grisTemporalKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p, tailMode);
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
 	grisSpatialKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p);

@@ -68,7 +68,13 @@ struct WavefrontView {
 	uint8_t* occluded[2];
 	uint32_t* counters;               // [bounce][4]: extension count, shadow count, extension head, shadow head
 	uint32_t capacity;                // slots per queue = pixels of the owned rows
+	// "tail": the few long paths still alive after bounce WavefrontTailStart - 1 finish on a second stream while the
+	// temporal pass already runs for every other pixel (passes_gris.cu)
+	uint32_t* tailMark;               // per pixel (storage index): == epoch when the pixel's path is in the tail
+	uint32_t* tailList;               // pixels of the tail, one per slot of the extension queue of bounce WavefrontTailStart
+	uint32_t epoch;                   // changes with every path-tracing pass
 };
+constexpr int WavefrontTailStart = 7;
 
 struct FrameView {
 	uint32_t width, height;       // full film

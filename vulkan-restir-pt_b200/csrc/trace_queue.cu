@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(TraceBlock) traceQueueKernel(const __grid_cons
 	if (s.counters != nullptr) {
 		// per-thread totals (a thread serves many rays); the rays themselves were counted at fetch time
 		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
+		if (MODE == TraceAny) { atomicAdd(&s.counters[5], (unsigned long long)nodeVisits); atomicAdd(&s.counters[6], (unsigned long long)triTests); }
 		atomicAdd(&s.counters[3], (unsigned long long)triTests);
 	}
 }

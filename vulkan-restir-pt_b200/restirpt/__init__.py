@@ -91,7 +91,8 @@ class SceneDesc(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("closestRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodeVisits", C.c_uint64),
-                ("triTests", C.c_uint64), ("shadedHits", C.c_uint64)]
+                ("triTests", C.c_uint64), ("shadedHits", C.c_uint64), ("shadowNodeVisits", C.c_uint64),
+                ("shadowTriTests", C.c_uint64)]
 
 
 class PeerInfo(C.Structure):
@@ -102,9 +103,11 @@ class PeerInfo(C.Structure):
 
 
 class PassStats(C.Structure):
-    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12)]
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12), ("kernelMs", C.c_double * 8),
+                ("kernelLaunches", C.c_uint64 * 8)]
 
 
+KERNEL_NAMES = ["trace_closest", "trace_any", "gris_begin", "gris_bounce"]
 PASS_NAMES = ["gbuffer", "di_naive", "gi_naive", "di_pathgen", "di_temporal", "di_spatial", "gi_restir",
               "gris_pathtrace", "gris_temporal", "gris_spatial", "visualize_as", "postprocess"]
 
