@@ -52,6 +52,7 @@ struct RptFrame {
 	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
 	uint32_t* work = nullptr;                  // WorkCounterCount queue heads of the persistent kernels
 	WavefrontView wf{};                        // wavefront path-tracing queues (owned rows only)
+	ReuseView ru{};                            // wavefront temporal / spatial reuse
 	cudaStream_t tailStream = nullptr;         // the long tail of the path-tracing pass runs here ...
 	cudaEvent_t tailFork = nullptr, tailDone = nullptr;
 	bool tailPending = false;                  // ... until the next pass joins it back into `stream`
@@ -305,7 +306,8 @@ static std::vector<void**> frameSlots(RptFrame* f) {
 static std::vector<void**> wavefrontSlots(RptFrame* f) {
 	return { (void**)&f->wf.state[0], (void**)&f->wf.state[1], (void**)&f->wf.cold, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1],
 	         (void**)&f->wf.pix[0], (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays[0], (void**)&f->wf.shadowRays[1],
-	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters, (void**)&f->wf.tailMark, (void**)&f->wf.tailList };
+	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters, (void**)&f->wf.tailMark, (void**)&f->wf.tailList,
+	         (void**)&f->ru.task, (void**)&f->ru.rays, (void**)&f->ru.occluded, (void**)&f->ru.shadeList, (void**)&f->ru.redoList, (void**)&f->ru.counters };
 }
 static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
 // the two depthNormal images carry two extra rows (film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
@@ -354,12 +356,14 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
 		auto wfs = wavefrontSlots(f);
 		const size_t wfBytes[] = { px * PathStateWords * 16, px * PathStateWords * 16, f->pixels() * 32, px * 32, px * 32, px * 4, px * 4, px * 16,
-		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), f->pixels() * 4, px * 4 };
+		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), f->pixels() * 4, px * 4,
+		                           px * 3 * ShiftTaskWords * 16, px * 3 * 32, px * 3, px * 4, px * 4, 16 * sizeof(uint32_t) };
 		for (size_t i = 0; i < wfs.size(); i++) {
 			e = cudaMalloc(wfs[i], wfBytes[i]);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }
 		}
 		f->wf.capacity = uint32_t(px);
+		f->ru.capacity = uint32_t(px);
 		e = cudaMemset(f->wf.tailMark, 0, f->pixels() * 4);
 		if (e == cudaSuccess) {   // highest priority: its small kernels must slip in between the blocks of the big pass on `stream`
 			int lo = 0, hi = 0;
@@ -434,6 +438,7 @@ static FrameView makeView(RptFrame* f) {
 	v.halo = f->halo;
 	v.work = f->work;
 	v.wf = f->wf;
+	v.ru = f->ru;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
 	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;

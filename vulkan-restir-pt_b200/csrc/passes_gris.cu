@@ -88,6 +88,8 @@ struct RcData {   // GRISReconnectionData (layouts.glsl:158-164), only ever a lo
 
 // gris_retrace.glsl:42-136: replay the BSDF chain from the destination's primary hit with the source path's
 // random numbers, consuming them in lock-step with tracePath, up to the vertex before the reconnection vertex
+// CanTrace = false: only the rcVertexId == 1 case (no ray needed) is compiled in
+template <bool CanTrace = true>
 RT_DEV void traceReplayPath(const SceneView& s, const RptGRISSettings& st, const Surface& primarySurf, float2 primaryUv, Ray ray,
                             uint32_t targetFlags, uint32_t rng, RcData& rc) {
 	float3 throughput = f3(1.0f);
@@ -105,6 +107,7 @@ RT_DEV void traceReplayPath(const SceneView& s, const RptGRISSettings& st, const
 		rc.rcPrevWo = wo; rc.rcPrevThroughput = throughput;
 		return;
 	}
+	if (!CanTrace) return;
 	for (int bounce = 0; bounce < 15; bounce++) {
 		if (bounce > 0) {
 			const Hit h = traceClosestHit(s, ray.ori, MinRayDistance, ray.dir, MaxRayDistance);
@@ -156,44 +159,67 @@ RT_DEV float3 reconnectionLi(const SceneView& s, const GRISResv& sample, const R
 	return Li;
 }
 
-// gris_retrace.glsl:138-236
-RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRISResv& dst, const Surface& dstPrimarySurf, float2 dstUv,
-                              const Ray& primaryRay, GRISResv src, uint32_t& rng) {
-	RcData rc;
-	Surface rcPrevSurf, rcSurf;
-	Mat rcPrevMat;
-	float3 wi = f3(0.0f), Li = f3(0.0f);
-	bool srcSampleValid = false;
-	float dstJacobian = 0, jacobian = 0, dstPHat = 0, dstSamplePdf = 0;
+// ---- the hybrid shift (GRISReservoirReuseAndMerge, gris_retrace.glsl:138-236), cut at its visibility ray -------------
+// shiftPrepare: replay + reconnection geometry + the validity tests up to the ray (:150-184)
+// shiftFinish:  shifted contribution, Jacobian, new target function, reweighting (:186-231)
+// The per-pixel passes call both around an in-line visibility ray (grisReuseAndMerge); the wavefront reuse passes
+// run them in two kernels with the ray traced from a queue in between.
+constexpr uint32_t TaskInvalid = 0, TaskRay = 1, TaskSkip = 3;
 
-	if (src.sampleValid()) {
-		traceReplayPath(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
-		if (rc.prevInstance != InvalidHitIndex) {
-			if (rc.prevInstance == SpecialHitIndex) rcPrevSurf = dstPrimarySurf;
-			else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, rcPrevSurf);
-			loadSurfaceInfo(s, src.rcInstance(), __float_as_uint(src.q0.w), make_float2(src.q0.x, src.q0.y), rcSurf);
-			rcPrevMat = loadMaterial(s, rcPrevSurf.matIndex);
-			const float dist = distance(rcPrevSurf.pos, rcSurf.pos);
-			wi = normalize(rcSurf.pos - rcPrevSurf.pos);
-			const float cosTheta = -dot(rcSurf.norm, wi);
-			dstJacobian = abs_(cosTheta) / square(dist);
-			jacobian = dstJacobian / src.rcJacobian();
-			if (dist > GRISDistanceThreshold && cosTheta > 0 && !isnan_(jacobian) && src.rcJacobian() > 0 && isBSDFConnectible(rcPrevMat)) {
-				if (traceVisibility(s, rcPrevSurf.pos, rcSurf.pos)) srcSampleValid = true;
-			}
-		}
-	}
+struct ShiftTask {
+	uint32_t status;                 // TaskInvalid: the source sample cannot be shifted here; TaskRay: visibility decides
+	Surface rcPrevSurf, rcSurf;      // the two ends of the reconnection segment (status == TaskRay)
+	float3 rcPrevWo, rcPrevThroughput;
+};
+
+RT_DEV void shiftPrepare(const SceneView& s, const RptGRISSettings& st, const Surface& dstPrimarySurf, float2 dstUv, const Ray& primaryRay,
+                         const GRISResv& src, ShiftTask& t) {
+	t.status = TaskInvalid;
+	if (!src.sampleValid()) return;
+	RcData rc;
+	traceReplayPath(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
+	if (rc.prevInstance == InvalidHitIndex) return;
+	if (rc.prevInstance == SpecialHitIndex) t.rcPrevSurf = dstPrimarySurf;
+	else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, t.rcPrevSurf);
+	loadSurfaceInfo(s, src.rcInstance(), __float_as_uint(src.q0.w), make_float2(src.q0.x, src.q0.y), t.rcSurf);
+	t.rcPrevWo = rc.rcPrevWo; t.rcPrevThroughput = rc.rcPrevThroughput;
+	const Mat rcPrevMat = loadMaterial(s, t.rcPrevSurf.matIndex);
+	const float dist = distance(t.rcPrevSurf.pos, t.rcSurf.pos);
+	const float3 wi = normalize(t.rcSurf.pos - t.rcPrevSurf.pos);
+	const float cosTheta = -dot(t.rcSurf.norm, wi);
+	const float dstJacobian = abs_(cosTheta) / square(dist);
+	const float jacobian = dstJacobian / src.q3.w;
+	if (dist > GRISDistanceThreshold && cosTheta > 0 && !isnan_(jacobian) && src.q3.w > 0 && isBSDFConnectible(rcPrevMat)) t.status = TaskRay;
+}
+
+// the visibility ray of traceVisibility(rcPrevSurf.pos, rcSurf.pos), ray_query.glsl:27-38
+RT_DEV void shiftVisibilityRay(const ShiftTask& t, float3& dir, float& tmax) {
+	dir = normalize(t.rcSurf.pos - t.rcPrevSurf.pos);
+	tmax = distance(t.rcSurf.pos, t.rcPrevSurf.pos) - MinRayDistance;
+}
+
+RT_DEV void shiftFinish(const SceneView& s, GRISResv& src, const ShiftTask& t, bool srcSampleValid) {
 	if (srcSampleValid) {
+		const Mat rcPrevMat = loadMaterial(s, t.rcPrevSurf.matIndex);
+		const float dist = distance(t.rcPrevSurf.pos, t.rcSurf.pos);
+		const float3 wi = normalize(t.rcSurf.pos - t.rcPrevSurf.pos);
+		const float cosTheta = -dot(t.rcSurf.norm, wi);
+		const float dstJacobian = abs_(cosTheta) / square(dist);
+		const float jacobian = dstJacobian / src.rcJacobian();
+		RcData rc;
+		rc.rcPrevWo = t.rcPrevWo; rc.rcPrevThroughput = t.rcPrevThroughput;
+		float3 Li = f3(0.0f);
+		float dstPHat = 0, dstSamplePdf = 0;
 		const uint32_t rcType = flagsRcVertexType(src.flags());
 		if (!isnan_(src.rcPrevSamplePdf()) && src.rcPrevSamplePdf() > 1e-6f) {
-			Li = reconnectionLi(s, src, rc, rcPrevSurf, rcSurf, rcPrevMat, wi, src.rcPrevSamplePdf());
+			Li = reconnectionLi(s, src, rc, t.rcPrevSurf, t.rcSurf, rcPrevMat, wi, src.rcPrevSamplePdf());
 			if (!isBlack(Li) && !hasNan(Li)) dstPHat = luminance(Li * jacobian);
 			if (rcType == RcLightSampled) {
 				const float sumPower = s.lightTable[0].prob;
-				dstSamplePdf = luminance(rcSurf.albedo) / sumPower / dstJacobian;
+				dstSamplePdf = luminance(t.rcSurf.albedo) / sumPower / dstJacobian;
 			}
 			else {
-				dstSamplePdf = evalPdf(rcPrevMat, rcPrevSurf.norm, rc.rcPrevWo, wi);
+				dstSamplePdf = evalPdf(rcPrevMat, t.rcPrevSurf.norm, rc.rcPrevWo, wi);
 			}
 		}
 		const float srcPHat = luminance(src.F());
@@ -206,6 +232,14 @@ RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRI
 	else {
 		src.resampleWeight() = 0;
 	}
+}
+
+RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRISResv& dst, const Surface& dstPrimarySurf, float2 dstUv,
+                              const Ray& primaryRay, GRISResv src, uint32_t& rng) {
+	ShiftTask t;
+	shiftPrepare(s, st, dstPrimarySurf, dstUv, primaryRay, src, t);
+	const bool srcSampleValid = t.status == TaskRay && traceVisibility(s, t.rcPrevSurf.pos, t.rcSurf.pos);
+	shiftFinish(s, src, t, srcSampleValid);
 	if (src.valid()) grisMerge(dst, src, sample1f(rng));
 	grisCap(dst, float(st.cap));
 }
@@ -641,25 +675,79 @@ __global__ void __launch_bounds__(ShadeBlock) grisBounceKernel(const __grid_cons
 	}
 }
 
-// gris_resample_temporal.comp -> temporalReuse, one pixel
-RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t x, uint32_t y) {
-	const Primary p = loadPrimary(f, x, y);
-	if (!p.valid) return;
-	const size_t idx = f.index(x, y);
-	const float2 motion = f.motion[idx];
-	const uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 1u;
-	uint32_t resvRng = ~rng;
-	GRISResv resv = loadGRIS(f.grisThis + idx);
+// ---- temporal and spatial reuse (gris_resample_temporal.comp, gris_resample_spatial.comp) ------------------------------
+//
+// Each pass is a wavefront of two kernels around one launch of the queue traversal kernel:
+//     [gen]    per pixel: pick the candidate reservoir(s) (reprojected pixel / 3 disk neighbours), replay the source
+//              path's prefix on this pixel, reconnection geometry and validity tests -> ShiftTask + visibility ray
+//     [trace]  any-hit traversal of all visibility rays (trace_queue.cu)
+//     [merge]  per pixel: shifted contribution + Jacobian + reweighting of every candidate, reservoir merges in the
+//              shader's order, and (spatial) the final shading of the selected sample
+// The shader's random-number stream interleaves "2 numbers to place neighbour i" with "1 number for merge i-1, drawn
+// only if the shifted reservoir is well-formed".  [gen] assumes the merge draw happens whenever a candidate exists —
+// which is decided before the shift — and [merge] verifies it: if a shifted reservoir turns out ill-formed (NaN weight:
+// only a zero-contribution sample with a valid reconnection vertex can do that) the pixel is put on the redo list and
+// recomputed by the sequential per-pixel code.  Likewise the rare final samples whose shading needs replay rays
+// (reconnection vertex beyond the first bounce) go to a list handled by a small kernel with in-line traversal, so the
+// merge kernel itself never traverses.
 
-	if (st.temporalReuse) {
-		if ((f.camera.frameIndex & 0x80000000u) == 0) {
-			const Neighbor nb = lookupSurface(f, true, make_float2(p.uv.x + motion.x, p.uv.y + motion.y));
-			if (nb.found && !(nb.matMeshId != p.matMeshId || dot(nb.norm, p.norm) < 0.95f || distance(p.pos, nb.pos) > 0.5f)) {
-				const GRISResv prev = loadGRIS(f.grisPrev + nb.pixel);
-				if (prev.valid()) grisReuseAndMerge(s, st, resv, primarySurface(p), p.uv, p.ray, prev, resvRng);
-			}
-		}
+constexpr int ReuseBlock = 128;
+
+RT_DEV void storeShiftTask(const ReuseView& ru, uint32_t cand, uint32_t o, const ShiftTask& t, uint32_t srcPixel) {
+	const size_t n = size_t(ru.capacity) * 3;
+	float4* w = ru.task + size_t(cand) * ru.capacity + o;
+	w[2 * n] = make_float4(t.rcPrevSurf.albedo.x, t.rcPrevSurf.albedo.y, t.rcPrevSurf.albedo.z, __uint_as_float(srcPixel | (t.status << 30)));
+	if (t.status != TaskRay) return;
+	w[0 * n] = make_float4(t.rcPrevSurf.pos.x, t.rcPrevSurf.pos.y, t.rcPrevSurf.pos.z, __uint_as_float(t.rcPrevSurf.matIndex));
+	w[1 * n] = make_float4(t.rcPrevSurf.norm.x, t.rcPrevSurf.norm.y, t.rcPrevSurf.norm.z, __uint_as_float(t.rcSurf.matIndex));
+	w[3 * n] = make_float4(t.rcSurf.pos.x, t.rcSurf.pos.y, t.rcSurf.pos.z, t.rcPrevWo.x);
+	w[4 * n] = make_float4(t.rcSurf.norm.x, t.rcSurf.norm.y, t.rcSurf.norm.z, t.rcPrevWo.y);
+	w[5 * n] = make_float4(t.rcSurf.albedo.x, t.rcSurf.albedo.y, t.rcSurf.albedo.z, t.rcPrevWo.z);
+	w[6 * n] = make_float4(t.rcPrevThroughput.x, t.rcPrevThroughput.y, t.rcPrevThroughput.z, 0.f);
+}
+RT_DEV void storeSkipTask(const ReuseView& ru, uint32_t cand, uint32_t o) {
+	ru.task[2 * size_t(ru.capacity) * 3 + size_t(cand) * ru.capacity + o] = make_float4(0.f, 0.f, 0.f, __uint_as_float(TaskSkip << 30));
+}
+RT_DEV uint32_t loadShiftTask(const ReuseView& ru, uint32_t cand, uint32_t o, ShiftTask& t) {   // returns the source pixel
+	const size_t n = size_t(ru.capacity) * 3;
+	const float4* w = ru.task + size_t(cand) * ru.capacity + o;
+	const float4 c = w[2 * n];
+	const uint32_t packed = __float_as_uint(c.w);
+	t.status = packed >> 30;
+	if (t.status == TaskRay) {
+		const float4 a = w[0 * n], b = w[1 * n], d = w[3 * n], e = w[4 * n], g = w[5 * n], h = w[6 * n];
+		t.rcPrevSurf.pos = f3(a); t.rcPrevSurf.matIndex = __float_as_uint(a.w);
+		t.rcPrevSurf.norm = f3(b); t.rcSurf.matIndex = __float_as_uint(b.w);
+		t.rcPrevSurf.albedo = f3(c); t.rcPrevSurf.isLight = false;
+		t.rcSurf.pos = f3(d); t.rcSurf.norm = f3(e); t.rcSurf.albedo = f3(g); t.rcSurf.isLight = false;
+		t.rcPrevWo = make_float3(d.w, e.w, g.w);
+		t.rcPrevThroughput = f3(h);
 	}
+	return packed & 0x3fffffffu;
+}
+RT_DEV void storeVisibilityRay(const ReuseView& ru, uint32_t cand, uint32_t o, const ShiftTask* t) {
+	float4* rq = ru.rays + 2 * (size_t(cand) * ru.capacity + o);
+	if (t != nullptr && t->status == TaskRay) {
+		float3 dir; float tmax;
+		shiftVisibilityRay(*t, dir, tmax);
+		rq[0] = make_float4(t->rcPrevSurf.pos.x, t->rcPrevSurf.pos.y, t->rcPrevSurf.pos.z, MinRayDistance);
+		rq[1] = make_float4(dir.x, dir.y, dir.z, tmax);
+	}
+	else {   // empty interval: reported unoccluded without touching the BVH
+		rq[0] = make_float4(0.f, 0.f, 0.f, 1.0f);
+		rq[1] = make_float4(0.f, 0.f, 1.f, 0.0f);
+	}
+}
+
+// -------- temporal ------------------------------------------------------------------------------------------------------
+RT_DEV bool temporalCandidate(const FrameView& f, const RptGRISSettings& st, const Primary& p, size_t idx, Neighbor& nb) {
+	if (!st.temporalReuse || (f.camera.frameIndex & 0x80000000u) != 0) return false;
+	const float2 motion = f.motion[idx];
+	nb = lookupSurface(f, true, make_float2(p.uv.x + motion.x, p.uv.y + motion.y));
+	return nb.found && !(nb.matMeshId != p.matMeshId || dot(nb.norm, p.norm) < 0.95f || distance(p.pos, nb.pos) > 0.5f);
+}
+
+RT_DEV void temporalStore(const FrameView& f, uint32_t x, uint32_t y, size_t idx, GRISResv& resv) {
 	if (!resv.valid()) resv.reset();
 	storeGRIS(f.grisTemp + idx, resv);
 	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
@@ -667,15 +755,68 @@ RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptG
 	if (f.peerGrisDown != nullptr && y + f.halo >= f.rowEnd) storeGRIS(f.peerGrisDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
 }
 
-// every pixel of the owned rows; with skipTail, pixels whose path is still being traced on the tail stream are left
-// to grisTemporalTailKernel
-__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
-	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
-	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
-	if (x >= f.width || y >= f.rowEnd) return;
-	if (skipTail && f.wf.tailMark[f.index(x, y)] == f.wf.epoch) return;
-	grisTemporalPixel(f, s, st, x, y);
+// the sequential per-pixel form (gris_resample_temporal.glsl:11-83), used for the pixels of the path-tracing tail
+RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t x, uint32_t y) {
+	const Primary p = loadPrimary(f, x, y);
+	if (!p.valid) return;
+	const size_t idx = f.index(x, y);
+	const uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 1u;
+	uint32_t resvRng = ~rng;
+	GRISResv resv = loadGRIS(f.grisThis + idx);
+	Neighbor nb;
+	if (temporalCandidate(f, st, p, idx, nb)) {
+		const GRISResv prev = loadGRIS(f.grisPrev + nb.pixel);
+		if (prev.valid()) grisReuseAndMerge(s, st, resv, primarySurface(p), p.uv, p.ray, prev, resvRng);
+	}
+	temporalStore(f, x, y, idx, resv);
 }
+
+__global__ void __launch_bounds__(ReuseBlock) grisTemporalGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
+	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
+	if (o >= f.ru.capacity) return;
+	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
+	const size_t idx = f.index(x, y);
+	const ShiftTask* rayTask = nullptr;
+	ShiftTask t;
+	bool stored = false;
+	if (!(skipTail && f.wf.tailMark[idx] == f.wf.epoch)) {
+		const Primary p = loadPrimary(f, x, y);
+		Neighbor nb;
+		if (p.valid && temporalCandidate(f, st, p, idx, nb)) {
+			const GRISResv prev = loadGRIS(f.grisPrev + nb.pixel);
+			if (prev.valid()) {
+				shiftPrepare(s, st, primarySurface(p), p.uv, p.ray, prev, t);
+				storeShiftTask(f.ru, 0, o, t, uint32_t(nb.pixel));
+				stored = true;
+				rayTask = &t;
+			}
+		}
+	}
+	if (!stored) storeSkipTask(f.ru, 0, o);
+	storeVisibilityRay(f.ru, 0, o, rayTask);
+}
+
+__global__ void __launch_bounds__(ReuseBlock) grisTemporalMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
+	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
+	if (o >= f.ru.capacity) return;
+	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
+	const size_t idx = f.index(x, y);
+	if (skipTail && f.wf.tailMark[idx] == f.wf.epoch) return;
+	if (f.depthNormal[idx].x == 0.0f) return;   // background: the shader returns before touching the reservoir
+	const uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 1u;
+	uint32_t resvRng = ~rng;
+	GRISResv resv = loadGRIS(f.grisThis + idx);
+	ShiftTask t;
+	const uint32_t srcPixel = loadShiftTask(f.ru, 0, o, t);
+	if (t.status != TaskSkip) {
+		GRISResv prev = loadGRIS(f.grisPrev + srcPixel);
+		shiftFinish(s, prev, t, t.status == TaskRay && f.ru.occluded[o] == 0);
+		if (prev.valid()) grisMerge(resv, prev, sample1f(resvRng));
+		grisCap(resv, float(st.cap));
+	}
+	temporalStore(f, x, y, idx, resv);
+}
+
 __global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalTailKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
 	const uint32_t n = f.wf.counters[4 * WavefrontTailStart];
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -684,11 +825,38 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalTailKer
 	}
 }
 
-// gris_resample_spatial.comp -> spatialReuse
-__global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
-	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
-	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
-	if (x >= f.width || y >= f.rowEnd) return;
+// -------- spatial -------------------------------------------------------------------------------------------------------
+RT_DEV bool spatialCandidate(const FrameView& f, const Primary& p, uint32_t& rng, Neighbor& nb) {   // gris_resample_spatial.glsl:62-84
+	const float texelX = 1.0f / float(f.width), texelY = 1.0f / float(f.height);
+	const float2 d = toConcentricDisk(sample2f(rng));
+	const float2 nuv = make_float2(p.uv.x + d.x * 20.0f * texelX, p.uv.y + d.y * 20.0f * texelY);
+	nb = lookupSurface(f, false, nuv);
+	return nb.found && !(dot(nb.norm, p.norm) < 0.9f || distance(p.pos, nb.pos) > 0.4f);
+}
+
+// final shading of the selected sample (gris_resample_spatial.glsl:88-131); replays the path prefix
+template <bool CanTrace = true>
+RT_DEV float3 spatialShade(const SceneView& s, const RptGRISSettings& st, const Primary& p, const Surface& dstPrimarySurf, GRISResv& resv) {
+	float3 radiance = f3(0.0f);
+	if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid()) {
+		RcData rc;
+		traceReplayPath<CanTrace>(s, st, dstPrimarySurf, p.uv, p.ray, resv.flags(), resv.primaryRng(), rc);
+		if (rc.prevInstance != InvalidHitIndex) {
+			Surface rcPrevSurf, rcSurf;
+			if (rc.prevInstance == SpecialHitIndex) rcPrevSurf = dstPrimarySurf;
+			else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, rcPrevSurf);
+			loadSurfaceInfo(s, resv.rcInstance(), __float_as_uint(resv.q0.w), make_float2(resv.q0.x, resv.q0.y), rcSurf);
+			const Mat rcPrevMat = loadMaterial(s, rcPrevSurf.matIndex);
+			const float3 wi = normalize(rcSurf.pos - rcPrevSurf.pos);
+			const float3 Li = reconnectionLi(s, resv, rc, rcPrevSurf, rcSurf, rcPrevMat, wi, resv.rcPrevSamplePdf());
+			if (!isBlack(Li) && !hasNan(Li)) radiance = Li / luminance(Li) * resv.resampleWeight() / resv.sampleCount();
+		}
+	}
+	return clampColor(radiance);
+}
+
+// the sequential per-pixel form (gris_resample_spatial.glsl:11-134), used for the redo list
+RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t x, uint32_t y) {
 	const Primary p = loadPrimary(f, x, y);
 	float3 radiance = f3(0.0f);
 	if (p.valid) {
@@ -696,14 +864,10 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(cons
 		uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 2u;
 		GRISResv resv = loadGRIS(f.grisTemp + idx);
 		const Surface dstPrimarySurf = primarySurface(p);
-		const float texelX = 1.0f / float(f.width), texelY = 1.0f / float(f.height);
-
 		if (st.spatialReuse) {
 			for (uint32_t i = 0; i < 3; i++) {
-				const float2 d = toConcentricDisk(sample2f(rng));
-				const float2 nuv = make_float2(p.uv.x + d.x * 20.0f * texelX, p.uv.y + d.y * 20.0f * texelY);
-				const Neighbor nb = lookupSurface(f, false, nuv);
-				if (nb.found && !(dot(nb.norm, p.norm) < 0.9f || distance(p.pos, nb.pos) > 0.4f)) {
+				Neighbor nb;
+				if (spatialCandidate(f, p, rng, nb)) {
 					const GRISResv nr = loadGRIS(f.grisTemp + nb.pixel);
 					if (nr.valid()) grisReuseAndMerge(s, st, resv, dstPrimarySurf, p.uv, p.ray, nr, rng);
 				}
@@ -711,24 +875,92 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialKernel(cons
 		}
 		if (!resv.valid()) resv.reset();
 		storeGRIS(f.grisThis + idx, resv);
-
-		if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid()) {
-			RcData rc;
-			traceReplayPath(s, st, dstPrimarySurf, p.uv, p.ray, resv.flags(), resv.primaryRng(), rc);
-			if (rc.prevInstance != InvalidHitIndex) {
-				Surface rcPrevSurf, rcSurf;
-				if (rc.prevInstance == SpecialHitIndex) rcPrevSurf = dstPrimarySurf;
-				else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, rcPrevSurf);
-				loadSurfaceInfo(s, resv.rcInstance(), __float_as_uint(resv.q0.w), make_float2(resv.q0.x, resv.q0.y), rcSurf);
-				const Mat rcPrevMat = loadMaterial(s, rcPrevSurf.matIndex);
-				const float3 wi = normalize(rcSurf.pos - rcPrevSurf.pos);
-				const float3 Li = reconnectionLi(s, resv, rc, rcPrevSurf, rcSurf, rcPrevMat, wi, resv.rcPrevSamplePdf());
-				if (!isBlack(Li) && !hasNan(Li)) radiance = Li / luminance(Li) * resv.resampleWeight() / resv.sampleCount();
-			}
-		}
-		radiance = clampColor(radiance);
+		radiance = spatialShade(s, st, p, dstPrimarySurf, resv);
 	}
 	accumulate(f.indirectOutput, f, x, y, radiance);
+}
+
+__global__ void __launch_bounds__(ReuseBlock) grisSpatialGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
+	if (o >= f.ru.capacity) return;
+	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
+	const Primary p = loadPrimary(f, x, y);
+	const bool active = p.valid && st.spatialReuse != 0;
+	uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 2u;
+	const Surface dstPrimarySurf = primarySurface(p);
+	for (uint32_t i = 0; i < 3; i++) {
+		const ShiftTask* rayTask = nullptr;
+		ShiftTask t;
+		bool stored = false;
+		Neighbor nb;
+		if (active && spatialCandidate(f, p, rng, nb)) {
+			const GRISResv nr = loadGRIS(f.grisTemp + nb.pixel);
+			if (nr.valid()) {
+				shiftPrepare(s, st, dstPrimarySurf, p.uv, p.ray, nr, t);
+				storeShiftTask(f.ru, i, o, t, uint32_t(nb.pixel));
+				stored = true;
+				rayTask = &t;
+				sample1f(rng);   // the merge's random number, assumed drawn (verified in the merge kernel)
+			}
+		}
+		if (!stored) storeSkipTask(f.ru, i, o);
+		storeVisibilityRay(f.ru, i, o, rayTask);
+	}
+}
+
+__global__ void __launch_bounds__(ReuseBlock) grisSpatialMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
+	if (o >= f.ru.capacity) return;
+	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
+	const Primary p = loadPrimary(f, x, y);
+	float3 radiance = f3(0.0f);
+	if (p.valid) {
+		const size_t idx = f.index(x, y);
+		uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 2u;
+		GRISResv resv = loadGRIS(f.grisTemp + idx);
+		if (st.spatialReuse) {
+			for (uint32_t i = 0; i < 3; i++) {
+				sample2f(rng);   // the two numbers that placed neighbour i
+				ShiftTask t;
+				const uint32_t srcPixel = loadShiftTask(f.ru, i, o, t);
+				if (t.status == TaskSkip) continue;
+				GRISResv nr = loadGRIS(f.grisTemp + srcPixel);
+				shiftFinish(s, nr, t, t.status == TaskRay && f.ru.occluded[size_t(i) * f.ru.capacity + o] == 0);
+				if (!nr.valid()) {   // no random number is drawn for an ill-formed reservoir: the assumed sequence is off from here
+					f.ru.redoList[atomicAdd(f.ru.counters + 1, 1u)] = o;
+					return;
+				}
+				grisMerge(resv, nr, sample1f(rng));
+				grisCap(resv, float(st.cap));
+			}
+		}
+		if (!resv.valid()) resv.reset();
+		storeGRIS(f.grisThis + idx, resv);
+		if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid() && flagsRcVertexId(resv.flags()) != 1u) {
+			f.ru.shadeList[atomicAdd(f.ru.counters + 0, 1u)] = o;   // shading needs replay rays: grisSpatialShadeListKernel
+			return;
+		}
+		radiance = spatialShade<false>(s, st, p, primarySurface(p), resv);   // rcVertexId == 1: the replay is the primary hit itself, no ray
+	}
+	accumulate(f.indirectOutput, f, x, y, radiance);
+}
+
+__global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialShadeListKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = f.ru.counters[0];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t o = f.ru.shadeList[i];
+		const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
+		const Primary p = loadPrimary(f, x, y);
+		GRISResv resv = loadGRIS(f.grisThis + f.index(x, y));
+		accumulate(f.indirectOutput, f, x, y, spatialShade(s, st, p, primarySurface(p), resv));
+	}
+}
+__global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialRedoKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = f.ru.counters[1];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t o = f.ru.redoList[i];
+		grisSpatialPixel(f, s, st, o % f.width, f.rowBegin + o / f.width);
+	}
 }
 
 void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
@@ -759,10 +991,21 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 		grisTemporalTailKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 		return;
 	}
-	grisTemporalKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p, tailMode);
+	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
+	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	grisTemporalGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	launchTraceQueueAny(s, f.ru.rays, nullptr, n, f.ru.counters + 2, f.ru.occluded, st);
+	grisTemporalMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
-	grisSpatialKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s, p);
+	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
+	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
+	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	grisSpatialGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
+	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
+	grisSpatialMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
+	grisSpatialShadeListKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
+	grisSpatialRedoKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 }
 
 } // namespace rt

@@ -76,6 +76,19 @@ struct WavefrontView {
 };
 constexpr int WavefrontTailStart = 7;
 
+// Buffers of the wavefront reuse passes (temporal: 1 candidate per pixel, spatial: 3), indexed by candidate * capacity +
+// owned-pixel index (row-major over the owned rows): no compaction, every access is a full coalesced run.
+constexpr int ShiftTaskWords = 7;
+struct ReuseView {
+	float4* task;                     // ShiftTaskWords planes of 3 * capacity float4
+	float4* rays;                     // visibility rays, 2 float4 per candidate
+	uint8_t* occluded;
+	uint32_t* shadeList;              // pixels whose final shading needs a replay ray (rare) ...
+	uint32_t* redoList;               // ... and pixels whose speculated random-number sequence did not hold (very rare)
+	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head
+	uint32_t capacity;                // owned pixels
+};
+
 struct FrameView {
 	uint32_t width, height;       // full film
 	uint32_t rowBegin, rowEnd;    // rows this frame owns
@@ -101,6 +114,7 @@ struct FrameView {
 	bool striped;                 // true when this frame is one strip of a larger film
 	uint32_t* work;               // work-queue heads of the persistent kernels (WorkCounterCount words)
 	WavefrontView wf;
+	ReuseView ru;
 
 	__device__ __forceinline__ size_t index(uint32_t x, uint32_t y) const { return size_t(y - storeBegin) * width + x; }
 };
