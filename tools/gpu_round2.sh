@@ -1,0 +1,17 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, smoke, bench (N=1) + reference arm, ncu launch list, one full ncu capture of the
+# traversal kernels (development aid; outputs under gpurun_out/)
+mkdir -p gpurun_out
+nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
+nproc > gpurun_out/nproc.txt
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/smoke.log
+timeout 600 python bench.py --steps 100 --warmup 30 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+timeout 600 python bench.py --impl reference --steps 6 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:gris|gbuffer|gBuffer|postProcess|traceQueue" -s 600 -c 200 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 6 --warmup 12 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:traceQueueKernel" -s 338 -c 2 -f -o gpurun_out/prof_tq \
+   python bench.py --steps 4 --warmup 10 --no-cpu-baseline > gpurun_out/prof_tq.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench_n1.json; cat gpurun_out/bench_ref.json

@@ -144,8 +144,10 @@ uint32_t Scene::addModelFromTriangles(const std::vector<RptMeshVertex>& verts, c
 	mesh.indexCount = uint32_t(localIdx.size());
 	mesh.materialIdx = int(materials.size());   // material 0 of this model, offset by the pool size
 	vertices[L].insert(vertices[L].end(), verts.begin(), verts.end());
-	indices[L].reserve(indices[L].size() + localIdx.size());
-	for (uint32_t i : localIdx) indices[L].push_back(i + mesh.vertexOffset);
+	// (no exact-size reserve here: it would defeat the vector's geometric growth and make adding n models O(n^2))
+	const size_t firstIndex = indices[L].size();
+	indices[L].insert(indices[L].end(), localIdx.begin(), localIdx.end());
+	for (size_t k = firstIndex; k < indices[L].size(); k++) indices[L][k] += mesh.vertexOffset;
 	if (!isLight) {
 		materialIndices.insert(materialIndices.end(), localIdx.size() / 3, mesh.materialIdx);
 	}
