@@ -3,14 +3,17 @@
 #   vulkan-restir-pt_b200/lib/librestirpt_host.so   C++ host (Scene / Camera / Renderer), include/restirpt_host.h
 #   oracle/liboracle.so                             CPU oracle — TEST INFRASTRUCTURE, never linked by the two above
 PKG := vulkan-restir-pt_b200
-LIBDIR := $(PKG)/lib
+LIBDIR ?= $(PKG)/lib
+# experiment builds: make cuda host LIBDIR=<dir> BUILD=<dir> EXTRA=-D<macro>; loaded with RPT_LIB_DIR=<dir>
+BUILD ?= build
+EXTRA ?=
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX ?= g++
 
 # Numeric contract: no implicit FMA contraction on either side, so the CUDA kernels and
 # the oracle produce bit-identical fp32 results; fused multiply-adds are spelled out in the sources.
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \
-             -ftz=false -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Iinclude -diag-suppress 20012
+             -ftz=false -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Iinclude -diag-suppress 20012 $(EXTRA)
 HOSTFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude
 ORCFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -mfma -Iinclude -pthread
 
@@ -27,10 +30,10 @@ cuda: $(LIBDIR)/librestirpt.so
 host: $(LIBDIR)/librestirpt_host.so
 oracle: oracle/liboracle.so
 
-CUDA_OBJS := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(CUDA_SRCS))
+CUDA_OBJS := $(patsubst $(PKG)/csrc/%.cu,$(BUILD)/%.o,$(CUDA_SRCS))
 
-build/%.o: $(PKG)/csrc/%.cu $(CUDA_HDRS)
-	@mkdir -p build
+$(BUILD)/%.o: $(PKG)/csrc/%.cu $(CUDA_HDRS)
+	@mkdir -p $(BUILD)
 	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
 
 $(LIBDIR)/librestirpt.so: $(CUDA_OBJS)

@@ -292,15 +292,18 @@ def run_cuda(args):
         # kernels: single-kernel passes as they are; the wavefront path-tracing pass split into its kernels (events between
         # the launches on the frame's stream; its tail, which runs concurrently on a second stream, is not in these figures)
         kernels = {}
-        for name in ("gbuffer", "gris_temporal", "gris_spatial", "postprocess"):
+        for name in ("gbuffer", "postprocess"):
             i = PASS_NAMES.index(name)
             if stats.launches[i]:
                 kernels[name] = {"ms_per_frame": stats.ms[i] / steps, "launches_per_frame": stats.launches[i] / steps}
         for k, name in enumerate(KERNEL_NAMES):
             if stats.kernelLaunches[k]:
                 kernels[name] = {"ms_per_frame": stats.kernelMs[k] / steps, "launches_per_frame": stats.kernelLaunches[k] / steps}
-        launches = int(sum(v["launches_per_frame"] for v in kernels.values()) * steps)
-        dom = max(kernels, key=lambda k: kernels[k]["ms_per_frame"])
+        tail_wait = kernels.pop("tail_wait", None)   # not a kernel: the frame's stream waiting for the path tracer's tail
+        # (the spatial pass's shade-list and redo-list kernels run inside the reuse_merge span: + 2 launches per frame)
+        launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 2) * steps)
+        timed = {k: v for k, v in kernels.items() if k != "gris_tail"}
+        dom = max(timed, key=lambda k: timed[k]["ms_per_frame"])
         # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record in/out,
         # 272 B per shaded hit, plus the kernel's per-pixel stream traffic; counts from the instrumented frame below
         cp, cs, ct, cg = (counters[k] for k in ("gris_pathtrace", "gris_spatial", "gris_temporal", "gbuffer"))
@@ -313,25 +316,36 @@ def run_cuda(args):
             return 80 * c.nodeVisits + 48 * c.triTests + 48 * (c.closestRays + c.shadowRays)
 
         state_bytes = 11 * 16 * 2 + 16 + 8 + 1 + 64   # path state planes in + out, hit, pixel ids, visibility byte, two ray records
+        def closest_bytes(c):
+            return ray_bytes(c, "closest") - 48 * c.closestRays   # in-line rays: no ray record in memory
+
         alg = {
             "gbuffer": ray_bytes(cg, "all") + 272 * cg.shadedHits + px * (28 + 16),
-            "gris_temporal": ray_bytes(ct, "all") + 272 * ct.shadedHits + px * (24 + 4 + 24 + 96 + 96 + 96),
-            "gris_spatial": ray_bytes(cs, "all") + 272 * cs.shadedHits + px * (24 + 96 + 3 * (24 + 96) + 96 + 32),
             "postprocess": px * 36,
             "trace_closest": ray_bytes(cp, "closest"),
-            "trace_any": ray_bytes(cp, "any"),
+            "trace_any": ray_bytes(cp, "any") + ray_bytes(ct, "any") + ray_bytes(cs, "any"),
             "gris_begin": px * (24 + state_bytes // 2 + 36),
             "gris_bounce": 272 * cp.shadedHits + cp.closestRays * state_bytes + px * 96,
+            # gen: G-buffer + candidate reservoirs in, shift task (7 x 16 B) + visibility ray (32 B) out per candidate, the
+            # in-line replay rays and their surface fetches; merge: tasks + reservoirs in, reservoir (+ radiance RMW) out
+            "reuse_gen": closest_bytes(ct) + closest_bytes(cs) + 272 * (ct.shadedHits + cs.shadedHits)
+                         + px * ((24 + 4 + 24 + 96 + 144) + (24 + 3 * (24 + 96) + 3 * 144)),
+            "reuse_merge": px * ((112 + 96 + 96 + 1 + 96) + (96 + 3 * (112 + 96 + 1) + 96 + 32)),
         }
-        nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "gris_temporal": ct.closestRays + ct.shadowRays,
-                 "gris_spatial": cs.closestRays + cs.shadowRays, "trace_closest": cp.closestRays, "trace_any": cp.shadowRays}
+        nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "trace_closest": cp.closestRays,
+                 "trace_any": cp.shadowRays + ct.shadowRays + cs.shadowRays}
+        # the path tracer's tail (paths alive after bounce 6, run in line by one kernel on a second stream concurrently with the
+        # temporal pass) is latency-bound and tiny: reported with its time only
+        tail = kernels.pop("gris_tail", None)
         for name, v in kernels.items():
             v["algorithmic_gb_per_frame"] = alg[name] / 1e9
             v["achieved_gbs"] = alg[name] / (v["ms_per_frame"] * 1e-3) / 1e9
             if name in nrays:
                 v["mrays_per_s"] = nrays[name] / 1e6 / (v["ms_per_frame"] * 1e-3)
+        if tail:
+            kernels["gris_tail (concurrent stream)"] = tail
         peak, peak_src = measured_peak_gbs()
-        c = {"gris_spatial": cs, "gris_temporal": ct, "gbuffer": cg}.get(dom, cp)
+        c = {"gbuffer": cg}.get(dom, cp)
         rays = c.closestRays + c.shadowRays
         lpf = kernels[dom]["launches_per_frame"]
         achieved = kernels[dom]["achieved_gbs"]
@@ -349,7 +363,8 @@ def run_cuda(args):
                                     "~1.8 GB at 1080p) exceeds the 126 MB L2; every frame uses a new seed",
                        "mrays_per_s_per_gpu": total_rays / 1e6 * fps,
                        "rays_per_pixel": total_rays / px,
-                       "pass_ms": per_pass_ms, "kernels": kernels},
+                       "pass_ms": per_pass_ms, "kernels": kernels,
+                       "tail_wait_ms_per_frame": (tail_wait["ms_per_frame"] if tail_wait else 0.0)},
             "e2e": {"value": 1000.0 * args.steps / e2e_ms * world, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 352, "d2h_bytes_per_step": strip_bytes},
             "gpu_launches": launches,

@@ -198,6 +198,7 @@ typedef struct RptCounters {
 	uint64_t shadedHits;     /* loadSurfaceInfo gathers (272 B)  */
 	uint64_t shadowNodeVisits;   /* the share of nodeVisits / triTests spent on occlusion rays */
 	uint64_t shadowTriTests;
+	uint64_t maxNodeVisits;  /* most nodes any single queued ray fetched (the length of a traversal kernel's tail) */
 } RptCounters;
 
 typedef struct RptBvhStats {
@@ -221,6 +222,10 @@ typedef enum RptPassId {
  * stream; the path-tracing tail that runs on the second stream is not included) */
 typedef enum RptKernelId {
 	RPT_KERNEL_TRACE_CLOSEST = 0, RPT_KERNEL_TRACE_ANY = 1, RPT_KERNEL_GRIS_BEGIN = 2, RPT_KERNEL_GRIS_BOUNCE = 3,
+	RPT_KERNEL_GRIS_TAIL = 4,   /* the in-line tail of the path tracer, timed on its own (concurrent) stream */
+	RPT_KERNEL_REUSE_GEN = 5,   /* temporal / spatial reuse: candidate + shift preparation kernels */
+	RPT_KERNEL_REUSE_MERGE = 6, /* temporal / spatial reuse: merge, shading and list kernels */
+	RPT_KERNEL_TAIL_WAIT = 7,   /* not a kernel: time the frame's stream waited for the path tracer's tail */
 	RPT_KERNEL_COUNT = 8
 } RptKernelId;
 

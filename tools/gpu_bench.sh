@@ -1,0 +1,9 @@
+#!/bin/bash
+# parity tests + smoke + bench N=1 (development aid)
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py --steps 100 --warmup 30 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+cat gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err

@@ -72,7 +72,7 @@ def main():
     dev.lib.rpt_counters_enable(dev.ctx, 0)
     rays = c.closestRays + c.shadowRays
     print(f"rays/frame {rays/1e6:.2f} M (closest {c.closestRays/1e6:.2f} shadow {c.shadowRays/1e6:.2f}) rays/px {rays/(w*h):.2f} "
-          f"nodes/ray {c.nodeVisits/max(rays,1):.1f} tris/ray {c.triTests/max(rays,1):.1f} hits {c.shadedHits/1e6:.2f} M")
+          f"nodes/ray {c.nodeVisits/max(rays,1):.1f} tris/ray {c.triTests/max(rays,1):.1f} hits {c.shadedHits/1e6:.2f} M  max nodes of one queued ray {c.maxNodeVisits}")
     wc = (C.c_uint32 * 64)()
     dev.lib.rpt_wavefront_counters(b.frame, wc)
     print("wavefront rays per bounce (extension/shadow):", " ".join(f"{b_}:{wc[4*b_]}/{wc[4*b_+1]}" for b_ in range(1, 15)))

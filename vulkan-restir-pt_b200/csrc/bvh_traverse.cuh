@@ -23,31 +23,45 @@ enum TraceMode { TraceClosest = 0, TraceAny = 1, TraceClosestNoLights = 2, Trace
 
 constexpr int TraversalStackSize = 48;
 
-// one 4-child half of a node: accumulate hit bits for children j = 0..3 of the half
+// Byte j of q dropped into mantissa bits 8..15 of the float `unit` (a power of two 2^k): 2^k (1 + b 2^-15), by one PRMT
+// on the ALU pipe instead of an I2F.U8 on the XU pipe (a quarter of the ALU rate; 48 of them per node made XU the
+// busiest pipe of the traversal kernels, profiles/r1_03_wavefront_tracequeue_details.txt)
+template <int J>
+RT_DEV float byteIntoMantissa(uint32_t q, uint32_t unit) {
+#ifdef RT_SLAB_I2F   // A/B experiment build (profiles/README.md): float(b) through I2F.U8, `unit` = bits of the slope s
+	return __uint2float_rn((q >> (8 * J)) & 0xffu);
+#else
+	return __uint_as_float(__byte_perm(q, unit, 0x7604u | (uint32_t(J) << 4)));
+#endif
+}
+
+// one 4-child half of a node: accumulate hit bits for children j = 0..3 of the half.
+// Plane distances t = b * (2^e / d) + n (b = quantised byte, 2^e = the node's grid step) are evaluated as
+// fma(2^(e+15) (1 + b 2^-15), 1/d, N) with N = n - 2^(e+15) / d; the rounding of N (<= 2^-9 of one grid step in t) is
+// covered by the slab padding in nodeStep.  ux/uy/uz = bits of 2^(e+15) per axis (0 for a flat axis).
 RT_DEV uint32_t slabHits4(uint32_t meta4, uint32_t octinv4,
                           uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy, uint32_t qfz,
-                          float sx, float sy, float sz, float nx, float ny, float nz, float fx, float fy, float fz,
-                          float tmin, float tmax) {
+                          uint32_t ux, uint32_t uy, uint32_t uz, float idx, float idy, float idz,
+                          float nx, float ny, float nz, float fx, float fy, float fz, float tmin, float tmax) {
 	uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
 	uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
 	uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
 	uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 	uint32_t hits = 0;
-#pragma unroll
-	for (int j = 0; j < 4; j++) {
-		const int sh = 8 * j;
-		float tnx = fma_(__uint2float_rn((qnx >> sh) & 0xffu), sx, nx);
-		float tny = fma_(__uint2float_rn((qny >> sh) & 0xffu), sy, ny);
-		float tnz = fma_(__uint2float_rn((qnz >> sh) & 0xffu), sz, nz);
-		float tfx = fma_(__uint2float_rn((qfx >> sh) & 0xffu), sx, fx);
-		float tfy = fma_(__uint2float_rn((qfy >> sh) & 0xffu), sy, fy);
-		float tfz = fma_(__uint2float_rn((qfz >> sh) & 0xffu), sz, fz);
-		float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-		float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-		if (tn <= tf) {
-			hits |= ((childBits4 >> sh) & 0xffu) << ((bitIndex4 >> sh) & 0xffu);
-		}
+#define RT_SLAB_CHILD(J) { \
+		const int sh = 8 * J; \
+		float tnx = fma_(byteIntoMantissa<J>(qnx, ux), idx, nx); \
+		float tny = fma_(byteIntoMantissa<J>(qny, uy), idy, ny); \
+		float tnz = fma_(byteIntoMantissa<J>(qnz, uz), idz, nz); \
+		float tfx = fma_(byteIntoMantissa<J>(qfx, ux), idx, fx); \
+		float tfy = fma_(byteIntoMantissa<J>(qfy, uy), idy, fy); \
+		float tfz = fma_(byteIntoMantissa<J>(qfz, uz), idz, fz); \
+		float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin)); \
+		float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax)); \
+		if (tn <= tf) hits |= ((childBits4 >> sh) & 0xffu) << ((bitIndex4 >> sh) & 0xffu); \
 	}
+	RT_SLAB_CHILD(0) RT_SLAB_CHILD(1) RT_SLAB_CHILD(2) RT_SLAB_CHILD(3)
+#undef RT_SLAB_CHILD
 	return hits;
 }
 
@@ -96,18 +110,27 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 
 	const uint32_t ebits = __float_as_uint(n0.w);
-	// 2^(e-127) per axis times 1/d, and (p - o)/d, padded by a bound on their rounding error so the
-	// slab interval can only grow
-	const float ex = __uint_as_float((ebits & 0xffu) << 23);
-	const float ey = __uint_as_float(((ebits >> 8) & 0xffu) << 23);
-	const float ez = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
-	const float sx = ex * r.idx, sy = ey * r.idy, sz = ez * r.idz;
+	// grid step 2^(e-127) per axis (e == 0: flat axis, step 0); s = step / d and h = (p - o) / d are the plane
+	// distances' slope and offset.  The slab interval is padded so that it can only grow:
+	//   1e-6 (255 |s| + |h|)  rounding of s, h and of the plane fma;   0.003 |s| >= 2^-9 |s|  rounding of N (slabHits4)
+	const uint32_t ebx = ebits & 0xffu, eby = (ebits >> 8) & 0xffu, ebz = (ebits >> 16) & 0xffu;
+	const float sx = __uint_as_float(ebx << 23) * r.idx, sy = __uint_as_float(eby << 23) * r.idy, sz = __uint_as_float(ebz << 23) * r.idz;
+	const uint32_t ux = ebx ? (ebx + 15u) << 23 : 0u, uy = eby ? (eby + 15u) << 23 : 0u, uz = ebz ? (ebz + 15u) << 23 : 0u;
 	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;
-	const float padx = fma_(abs_(sx), 255.0f, abs_(hx)) * 1e-6f;
-	const float pady = fma_(abs_(sy), 255.0f, abs_(hy)) * 1e-6f;
-	const float padz = fma_(abs_(sz), 255.0f, abs_(hz)) * 1e-6f;
+	const float padx = fma_(fma_(abs_(sx), 255.0f, abs_(hx)), 1e-6f, abs_(sx) * 0.003f);
+	const float pady = fma_(fma_(abs_(sy), 255.0f, abs_(hy)), 1e-6f, abs_(sy) * 0.003f);
+	const float padz = fma_(fma_(abs_(sz), 255.0f, abs_(hz)), 1e-6f, abs_(sz) * 0.003f);
+	const float Sx = __uint_as_float(ux) * r.idx, Sy = __uint_as_float(uy) * r.idy, Sz = __uint_as_float(uz) * r.idz;
+#ifdef RT_SLAB_I2F
 	const float nx = hx - padx, ny = hy - pady, nz = hz - padz;
 	const float fx = hx + padx, fy = hy + pady, fz = hz + padz;
+	(void)Sx; (void)Sy; (void)Sz;
+#define RT_SLAB_ARGS ux, uy, uz, sx, sy, sz
+#else
+	const float nx = (hx - padx) - Sx, ny = (hy - pady) - Sy, nz = (hz - padz) - Sz;
+	const float fx = (hx + padx) - Sx, fy = (hy + pady) - Sy, fz = (hz + padz) - Sz;
+#define RT_SLAB_ARGS ux, uy, uz, r.idx, r.idy, r.idz
+#endif
 
 	const uint32_t qlox0 = __float_as_uint(n2.x), qlox1 = __float_as_uint(n2.y);
 	const uint32_t qloy0 = __float_as_uint(n2.z), qloy1 = __float_as_uint(n2.w);
@@ -119,11 +142,11 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	uint32_t hitmask = slabHits4(__float_as_uint(n1.z), octinv4,
 		negx ? qhix0 : qlox0, negy ? qhiy0 : qloy0, negz ? qhiz0 : qloz0,
 		negx ? qlox0 : qhix0, negy ? qloy0 : qhiy0, negz ? qloz0 : qhiz0,
-		sx, sy, sz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+		RT_SLAB_ARGS, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
 	hitmask |= slabHits4(__float_as_uint(n1.w), octinv4,
 		negx ? qhix1 : qlox1, negy ? qhiy1 : qloy1, negz ? qhiz1 : qloz1,
 		negx ? qlox1 : qhix1, negy ? qloy1 : qhiy1, negz ? qloz1 : qhiz1,
-		sx, sy, sz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+		RT_SLAB_ARGS, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
 
 	ngroup.x = __float_as_uint(n1.x);
 	ngroup.y = (hitmask & 0xff000000u) | (ebits >> 24);

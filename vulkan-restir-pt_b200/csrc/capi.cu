@@ -543,7 +543,11 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	}
 	CU(f->ctx, cudaEventRecord(f->tailFork, f->stream));
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
-	launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	if (f->timing) { t0 = takeEvent(f); t1 = takeEvent(f); cudaEventRecord(t0, f->tailStream); }
+	if (getenv("RPT_WAVEFRONT_TAIL")) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
+	else launchGRISPathTraceTail(view, scene, *st, f->tailStream);
+	if (f->timing) { cudaEventRecord(t1, f->tailStream); f->pending.push_back({ RPT_PASS_COUNT + RPT_KERNEL_GRIS_TAIL, t0, t1, true }); }
 	CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
 	f->tailPending = true;
 	PASS_EPILOGUE("rpt_gris_pathtrace")
@@ -561,17 +565,31 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 		PassTimer timer(f, RPT_PASS_GRIS_TEMPORAL);
 		const FrameView view = makeView(f);
 		const SceneView scene = sceneView(s);
+		FrameKernelClock clock(f);
+		KernelClock* ck = f->timing ? &clock : nullptr;
 		if (f->tailPending) {
-			launchGRISTemporal(view, scene, *st, f->stream, 1);
+			launchGRISTemporal(view, scene, *st, f->stream, 1, ck);
+			if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
 			joinTail(f);
-			launchGRISTemporal(view, scene, *st, f->stream, 2);
+			launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
 		}
-		else launchGRISTemporal(view, scene, *st, f->stream, 0);
+		else launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
 	}
 	peerAfter(f, HookGrisTemporal);
 	PASS_EPILOGUE("rpt_gris_temporal")
 }
-SETTINGS_PASS(rpt_gris_spatial, RptGRISSettings, RPT_PASS_GRIS_SPATIAL, launchGRISSpatial, HookGrisSpatial)
+RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
+	PASS_PROLOGUE("rpt_gris_spatial")
+	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_spatial: NULL settings");
+	peerBefore(f, HookGrisSpatial);
+	{
+		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
+		FrameKernelClock clock(f);
+		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr);
+	}
+	peerAfter(f, HookGrisSpatial);
+	PASS_EPILOGUE("rpt_gris_spatial")
+}
 
 RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
 	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
@@ -800,6 +818,6 @@ RPT_API int rpt_counters_read(RptCtx* ctx, RptCounters* out) {
 	unsigned long long h[8];
 	CU(ctx, cudaMemcpy(h, ctx->counters, sizeof(h), cudaMemcpyDeviceToHost));
 	out->closestRays = h[0]; out->shadowRays = h[1]; out->nodeVisits = h[2]; out->triTests = h[3]; out->shadedHits = h[4];
-	out->shadowNodeVisits = h[5]; out->shadowTriTests = h[6];
+	out->shadowNodeVisits = h[5]; out->shadowTriTests = h[6]; out->maxNodeVisits = h[7];
 	return RPT_OK;
 }

@@ -19,9 +19,10 @@ void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st);
 struct KernelClock { virtual void tick(int rptKernelId) = 0; virtual ~KernelClock() = default; };   // called before every launch
 void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
                                 KernelClock* clock = nullptr);
+void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
 // tailMode 0: every pixel; 1: every pixel whose path is not in the tail; 2: only the pixels of the tail list
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0);
-void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0, KernelClock* clock = nullptr);
+void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock = nullptr);
 void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
 
 // wavefront traversal (trace_queue.cu): rays[2i] = {o, tmin}, rays[2i+1] = {d, tmax}; the ray count is read from

@@ -3,6 +3,7 @@
 //   reference src/shader/gris_path_trace.glsl:45-305, gris_retrace.glsl:42-236, gris_reservoir.glsl:37-136,
 //   gris_resample_temporal.glsl:11-83, gris_resample_spatial.glsl:11-134 (+ the three .comp entry points)
 //   host sequence: GRISReSTIR::render (src/GRISReSTIR.cpp:9-53)
+#include <algorithm>
 #include <cstdlib>
 #include "passes.h"
 #include "shading.cuh"
@@ -548,17 +549,6 @@ RT_DEV bool scatterStage(PathState& st, const RptGRISSettings& set, const Surfac
 	return st.bounce < 15;
 }
 
-// appends one entry per calling lane to a device queue: one atomic per converged group of lanes
-RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count) {
-	const unsigned mask = __activemask();
-	const uint32_t lane = threadIdx.x & 31u;
-	const int leader = __ffs(int(mask)) - 1;
-	uint32_t base = 0;
-	if (int(lane) == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
-	base = __shfl_sync(mask, base, leader);
-	return base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
-}
-
 RT_DEV PathBuffers pathBuffers(const FrameView& f, int bounce) {
 	PathBuffers b;
 	b.hot = f.wf.state[bounce & 1]; b.cold = f.wf.cold; b.capacity = f.wf.capacity;
@@ -672,6 +662,74 @@ __global__ void __launch_bounds__(ShadeBlock) grisBounceKernel(const __grid_cons
 		if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) { finishPath(cur, pix, st, slot); continue; }
 		// (3) + (4)
 		shadeAndContinue(f, s, set, st, surf, mat, vo, pix, slot);
+	}
+}
+
+// The tail: after bounce WavefrontTailStart - 1 only a few percent of the paths are alive (VeachAjar 1080p: 87 k of 2 M,
+// halving with every bounce), and a wavefront of them is nine rounds of three nearly empty launches whose duration is the
+// latency of their longest ray — 1.3 ms end to end, during which the temporal pass waits for the tail's pixels
+// (profiles/r1_03_wavefront_launches.csv).  This kernel instead runs each surviving path to its end in one thread with
+// in-line traversal: the same stage functions in the same order, so the same bits; SIMD efficiency is irrelevant at
+// this size, the kernel takes as long as its longest path.
+//
+// The kernel runs on a second stream next to the temporal pass, which must not be starved: a thread holds ~170
+// registers and mostly waits on memory, so the grid is kept to a few small blocks per SM (a sixth to a third of the
+// register file) and every thread pulls its next path from the list as soon as one ends.
+constexpr int TailBlock = 64;
+__global__ void __launch_bounds__(TailBlock) grisTailKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set) {
+	const int first = WavefrontTailStart;
+	const uint32_t n = f.wf.counters[4 * first];
+	uint32_t* head = f.wf.counters + 4 * first + 2;   // (the fetch counter of the wavefront traversal of this bounce: unused here, zero)
+	const float sumPower = s.lightTable[0].prob;
+	const PathBuffers buf = pathBuffers(f, first);
+	for (;;) {
+		const uint32_t slotIdx = atomicAdd(head, 1u);
+		if (slotIdx >= n) break;
+		const uint32_t pix = f.wf.pix[first & 1][slotIdx];
+		RptGRISReservoir* slot = f.grisThis + pix;
+		PathState st;
+		loadPathState(buf, slotIdx, st);
+		// the two rays queued by the last wavefront bounce: the light sample's shadow ray and the extension ray
+		float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+		if (st.neeKind != NeeNone) {
+			const float4* rq = f.wf.shadowRays[(first - 1) & 1] + 2 * size_t(st.shadowIdx);
+			sh0 = rq[0]; sh1 = rq[1];
+		}
+		float3 rayOri = f3(f.wf.rays[first & 1][2 * size_t(slotIdx)]);
+		for (;;) {
+			// (1) the light sample of the previous vertex
+			if (st.neeKind != NeeNone) {
+				if (!traceShadow(s, f3(sh0), sh0.w, f3(sh1), sh1.w)) neeApply(buf, pix, st, st.zombie ? st.bounce : st.bounce - 1, slot);
+				st.neeKind = NeeNone;
+			}
+			if (st.zombie) break;
+			// (2) the vertex the extension ray finds
+			const Hit h = traceClosestHit(s, rayOri, MinRayDistance, st.dir, MaxRayDistance);
+			if (h.instanceIdx == InvalidHitIndex) break;
+			Surface surf;
+			loadSurfaceInfo(s, h, surf);
+			const Mat mat = loadMaterial(s, surf.matIndex);
+			VertexOut vo;
+			vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
+			const float4 isecWord = make_float4(h.u, h.v, __uint_as_float(h.instanceIdx), __uint_as_float(h.triangleIdx));
+			if (!vertexStage(st, set, surf, mat, isecWord, sumPower, slot, vo)) break;
+			// (3) light sample, (4) roulette + BSDF sample: shadeAndContinue without the queues
+			const int bounce = st.bounce;
+			if (!isBSDFDelta(mat)) {
+				const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
+				if (neePrepare(st, surf, mat, ls, vo.resvRandSample)) {
+					sh0 = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
+					sh1 = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
+				}
+			}
+			const bool go = scatterStage(st, set, surf, mat, rayOri);
+			if (!go) {
+				st.bounce = bounce;
+				if (st.neeKind == NeeNone) break;
+				st.zombie = true;
+			}
+		}
+		finishPath(buf, pix, st, slot);
 	}
 }
 
@@ -985,24 +1043,42 @@ void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const Rp
 		grisBounceKernel<<<bounceBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 	}
 }
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode) {
+// every path still alive after bounce WavefrontTailStart - 1, to its end
+void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
+	static const int blocks = [] {
+		int dev = 0, sms = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		const char* e = getenv("RPT_TAIL_BLOCKS_PER_SM");   // experiments; default = measured optimum (profiles/README.md)
+		return (sms > 0 ? sms : 148) * (e ? std::max(1, atoi(e)) : 4);
+	}();
+	grisTailKernel<<<blocks, TailBlock, 0, st>>>(f, s, p);
+}
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode, KernelClock* clock) {
 	if (tailMode == 2) {
 		static const int blocks = persistentBlocks(reinterpret_cast<const void*>(grisTemporalTailKernel), PassBlockX * PassBlockY);
+		if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 		grisTemporalTailKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 		return;
 	}
 	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
 	grisTemporalGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, n, f.ru.counters + 2, f.ru.occluded, st);
+	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 	grisTemporalMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
 }
-void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st) {
+void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock) {
 	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
 	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
 	grisSpatialGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
+	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
+	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 	grisSpatialMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
 	grisSpatialShadeListKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 	grisSpatialRedoKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);

@@ -9,6 +9,7 @@
 // Pixels are handed out in 8x4-tile-major order, so the lanes refilled together touch neighbouring G-buffer texels.
 // Results do not depend on the schedule: a pixel's arithmetic and RNG stream are a function of (seed, x, y) only.
 #pragma once
+#include "rt_math.cuh"
 #include "rt_types.cuh"
 
 namespace rt {
@@ -47,5 +48,16 @@ struct PixelQueue {
 		return x < width && y < rowEnd;
 	}
 };
+
+// appends one entry per calling lane to a device queue: one atomic per converged group of lanes
+RT_DEV uint32_t queueAppend(uint32_t* __restrict__ count) {
+	const unsigned mask = __activemask();
+	const uint32_t lane = threadIdx.x & 31u;
+	const int leader = __ffs(int(mask)) - 1;
+	uint32_t base = 0;
+	if (int(lane) == leader) base = atomicAdd(count, uint32_t(__popc(mask)));
+	base = __shfl_sync(mask, base, leader);
+	return base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
+}
 
 } // namespace rt

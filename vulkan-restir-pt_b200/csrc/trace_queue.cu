@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(TraceBlock) traceQueueKernel(const __grid_cons
 	uint2 stack[TraversalStackSize];
 	int sp = 0;
 	uint2 ngroup = make_uint2(0u, 0u);
-	uint32_t nodeVisits = 0, triTests = 0;
+	uint32_t nodeVisits = 0, triTests = 0, visitsAtFetch = 0;
 
 	for (;;) {
 		// ---- dynamic fetch ----------------------------------------------------------------------------------
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(TraceBlock) traceQueueKernel(const __grid_cons
 						res.init(b.w);
 						sp = 0;
 						ngroup = make_uint2(0u, 0x80000000u);
+						visitsAtFetch = nodeVisits;
 					}
 				}
 			}
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(TraceBlock) traceQueueKernel(const __grid_cons
 				else ngroup = stack[--sp];
 			}
 			if (finished) {
+				if (s.counters != nullptr) atomicMax(&s.counters[7], (unsigned long long)(nodeVisits - visitsAtFetch));
 				if (MODE == TraceAny) occluded[rayIdx] = res.best.instanceIdx != InvalidHitIndex ? 1 : 0;
 				else {
 					RptIntersection o;

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(os.path.dirname(_HERE), "lib")
+# RPT_LIB_DIR: an experiment build of the same two libraries (Makefile: LIBDIR=...), for A/B measurements
+LIB_DIR = os.environ.get("RPT_LIB_DIR") or os.path.join(os.path.dirname(_HERE), "lib")
 REPO_ROOT = os.path.dirname(os.path.dirname(_HERE))
 
 
@@ -92,7 +93,7 @@ class SceneDesc(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("closestRays", C.c_uint64), ("shadowRays", C.c_uint64), ("nodeVisits", C.c_uint64),
                 ("triTests", C.c_uint64), ("shadedHits", C.c_uint64), ("shadowNodeVisits", C.c_uint64),
-                ("shadowTriTests", C.c_uint64)]
+                ("shadowTriTests", C.c_uint64), ("maxNodeVisits", C.c_uint64)]
 
 
 class PeerInfo(C.Structure):
@@ -107,7 +108,7 @@ class PassStats(C.Structure):
                 ("kernelLaunches", C.c_uint64 * 8)]
 
 
-KERNEL_NAMES = ["trace_closest", "trace_any", "gris_begin", "gris_bounce"]
+KERNEL_NAMES = ["trace_closest", "trace_any", "gris_begin", "gris_bounce", "gris_tail", "reuse_gen", "reuse_merge", "tail_wait"]
 PASS_NAMES = ["gbuffer", "di_naive", "gi_naive", "di_pathgen", "di_temporal", "di_spatial", "gi_restir",
               "gris_pathtrace", "gris_temporal", "gris_spatial", "visualize_as", "postprocess"]
 
