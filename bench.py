@@ -202,19 +202,51 @@ def run_cuda(args):
     host, dev_lib = restirpt.host_lib(), restirpt.device_lib()
     scene, scene_name = load_scene()
     fw, fh = film_for(world)
-    rows = fh // world
-    row0, row1 = rank * rows, (rank + 1) * rows
     halo = HALO if world > 1 else 0
-    r = host.rh_renderer_create(scene.handle, fw, fh, local_rank, row0, row1, halo)
-    if not r:
-        raise SystemExit("renderer creation failed: " + host.rh_last_error().decode())
     gs = GRISSettings(2, 1.0, 1, 1, 20)
-    host.rh_renderer_set_methods(r, 0, 3, 1, 1, 0)   # direct None, indirect ResampledPT, filmic, gamma, no accumulation
-    host.rh_renderer_set_gris(r, C.byref(gs))
-    frame = P(host.rh_renderer_frame(r))
+
+    def open_strip(row0, row1):
+        r = host.rh_renderer_create(scene.handle, fw, fh, local_rank, row0, row1, halo)
+        if not r:
+            raise SystemExit("renderer creation failed: " + host.rh_last_error().decode())
+        host.rh_renderer_set_methods(r, 0, 3, 1, 1, 0)   # direct None, indirect ResampledPT, filmic, gamma, no accumulation
+        host.rh_renderer_set_gris(r, C.byref(gs))
+        frame = P(host.rh_renderer_frame(r))
+        link = multigpu.connect_strips(r, frame, rank, world) if world > 1 else None
+        return r, frame, link
+
+    # N > 1: the strips start equal and are re-cut so that every GPU has the same amount of work (the pots and the door
+    # cost several times more per row than floor and ceiling).  Calibration = a few untimed frames per round with per-pass
+    # device timing (time spent waiting for a neighbour is outside the pass timers), costs all-gathered, boundaries moved
+    # to the equal-cost points (multigpu.balanced_partition), strips re-created.  Done before the warm-up, never timed.
+    bounds = multigpu.partition(fh, world)
+    balance_rounds = 0 if world == 1 or args.no_balance else 3
+    balance_log = []
+    for round_no in range(balance_rounds + 1):
+        r, frame, link = open_strip(*bounds[rank])
+        if round_no == balance_rounds:
+            break
+        import torch.distributed as dist
+        for i in range(6):
+            if i == 2:
+                dev_lib.rpt_sync(frame)
+                dev_lib.rpt_frame_timing(frame, 1)
+            if host.rh_renderer_draw_frame(r, restirpt.hash2(1000 + i), None) != 0:
+                raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
+        st = PassStats()
+        dev_lib.rpt_frame_pass_stats(frame, C.byref(st))
+        cost = sum(st.ms[i] for i in range(12))
+        costs = [None] * world
+        dist.all_gather_object(costs, cost)
+        balance_log.append({"rows": [b[1] - b[0] for b in bounds], "ms_per_frame": [round(c / 4, 3) for c in costs]})
+        bounds = multigpu.balanced_partition(bounds, costs, min_rows=max(2 * HALO, 64))
+        link.close()
+        host.rh_renderer_destroy(r)
+        dist.barrier()
+    row0, row1 = bounds[rank]
+    rows = row1 - row0
     ctx = P(host.rh_renderer_ctx(r))
     stream = torch.cuda.ExternalStream(dev_lib.rpt_frame_stream(frame), device=torch.device("cuda", local_rank))
-    link = multigpu.connect_strips(r, frame, rank, world) if world > 1 else None
 
     frame_no = [0]
 
@@ -355,9 +387,9 @@ def run_cuda(args):
             "metric": METRIC, "value": fps * world, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{scene_name}, film {fw}x{fh} ({world} strip(s) of {fw}x{rows}), direct None, indirect "
+            "config": {"workload": f"{scene_name}, film {fw}x{fh} ({world} strip(s){'' if world == 1 else ', cost-balanced heights ' + str([b[1] - b[0] for b in bounds])}), direct None, indirect "
                                    "ResampledPT {Hybrid, rrScale 1, temporal 1, spatial 1, cap 20}, seed hash2(frame+1), static camera",
-                       "film_frames_per_s": fps, "halo_rows": halo,
+                       "film_frames_per_s": fps, "halo_rows": halo, "strip_balance_rounds": balance_log,
                        "halo_exchange": (link.describe() if link else "none (single GPU)"),
                        "l2_policy": "inputs larger than L2: per-frame working set (G-buffer + 3 reservoir buffers + path state + outputs "
                                     "~1.8 GB at 1080p) exceeds the 126 MB L2; every frame uses a new seed",
@@ -403,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal strips (skip the cost calibration)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

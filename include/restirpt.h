@@ -314,6 +314,9 @@ typedef struct RptPeerInfo {
 int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out);
 /* up = the strip above (smaller rows), down = the strip below; NULL at the film edge */
 int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const RptPeerInfo* down);
+/* drop the mappings of the neighbours' buffers again (every rank calls this, then a barrier, before any strip is
+ * destroyed or re-partitioned); also done by rpt_frame_destroy */
+int rpt_frame_disconnect_peers(RptFrame* f);
 int rpt_frame_peer_error(RptFrame* f);   /* non-zero if a device-side hand-over wait timed out */
 
 /* ---- ray queries exposed directly (new; closest-hit primitive-ID parity, traversal microbench) -------- */

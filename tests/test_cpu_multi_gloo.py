@@ -46,3 +46,32 @@ def test_halo_exchange_gloo(world, height):
     for p in procs:
         p.join(timeout=60)
     assert all(results[r] for r in range(world)), results
+
+
+def test_balanced_partition_equalises_cost():
+    """multigpu.balanced_partition: piecewise-uniform cost model, quantised rows, minimum strip height"""
+    from restirpt import multigpu
+    bounds = multigpu.partition(4320, 8)
+    assert bounds[0] == (0, 540) and bounds[-1] == (3780, 4320)
+    # uniform cost: nothing moves
+    assert multigpu.balanced_partition(bounds, [5.0] * 8, min_rows=64) == bounds
+    # the two middle strips cost three times as much: they must shrink, the outer ones grow, and the modelled cost
+    # of the new strips must be (nearly) equal
+    costs = [2.0, 2.0, 2.0, 6.0, 6.0, 2.0, 2.0, 2.0]
+    new = multigpu.balanced_partition(bounds, costs, min_rows=64)
+    assert new[0][0] == 0 and new[-1][1] == 4320
+    assert all(a[1] == b[0] for a, b in zip(new, new[1:]))
+    assert all(b % 4 == 0 for b, _ in new)
+    assert (new[3][1] - new[3][0]) < 540 < (new[0][1] - new[0][0])
+    density = [c / (e - b) for c, (b, e) in zip(costs, bounds)]
+
+    def model(b, e):
+        return sum(density[k] * max(0, min(e, be) - max(b, bb)) for k, (bb, be) in enumerate(bounds))
+
+    modelled = [model(b, e) for b, e in new]
+    assert max(modelled) - min(modelled) < 0.05 * sum(costs) / 8
+    # minimum height is honoured even for absurd costs
+    new = multigpu.balanced_partition(bounds, [1e-3, 1e-3, 1e-3, 100.0, 1e-3, 1e-3, 1e-3, 1e-3], min_rows=64)
+    assert all(e - b >= 64 for b, e in new) and new[-1][1] == 4320
+    # one strip: unchanged
+    assert multigpu.balanced_partition([(0, 1080)], [9.9], min_rows=64) == [(0, 1080)]

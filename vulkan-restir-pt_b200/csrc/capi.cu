@@ -381,6 +381,13 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	return RPT_OK;
 }
 
+static void disconnectPeers(RptFrame* f) {
+	for (RptFrame::Peer* p : { &f->up, &f->down }) {
+		if (p->connected && p->ipc) { cudaIpcCloseMemHandle(p->grisTemp); cudaIpcCloseMemHandle(p->diTemp); cudaIpcCloseMemHandle(p->flags); }
+		*p = RptFrame::Peer{};
+	}
+}
+
 RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device);
@@ -389,9 +396,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->tailFork) cudaEventDestroy(f->tailFork);
 	if (f->tailDone) cudaEventDestroy(f->tailDone);
 	if (f->tailStream) cudaStreamDestroy(f->tailStream);
-	for (RptFrame::Peer* p : { &f->up, &f->down }) {
-		if (p->connected && p->ipc) { cudaIpcCloseMemHandle(p->grisTemp); cudaIpcCloseMemHandle(p->diTemp); cudaIpcCloseMemHandle(p->flags); }
-	}
+	disconnectPeers(f);
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
@@ -718,6 +723,15 @@ RPT_API int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const Rp
 	int r = connectOne(f, f->up, up);
 	if (r != RPT_OK) return r;
 	return connectOne(f, f->down, down);
+}
+
+RPT_API int rpt_frame_disconnect_peers(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_disconnect_peers: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	disconnectPeers(f);
+	return RPT_OK;
 }
 
 RPT_API int rpt_frame_peer_error(RptFrame* f) {

@@ -189,6 +189,7 @@ DEVICE_API = {
     "rpt_sync": (C.c_int, [P]),
     "rpt_frame_export_peer": (C.c_int, [P, C.POINTER(PeerInfo)]),
     "rpt_frame_connect_peers": (C.c_int, [P, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
+    "rpt_frame_disconnect_peers": (C.c_int, [P]),
     "rpt_frame_peer_error": (C.c_int, [P]),
     "rpt_frame_timing": (C.c_int, [P, C.c_int]),
     "rpt_frame_pass_stats": (C.c_int, [P, C.POINTER(PassStats)]),

@@ -26,6 +26,42 @@ def partition(height, world):
     return out
 
 
+def balanced_partition(bounds, costs, min_rows, quantum=4):
+    """Strip boundaries that equalise the per-strip cost, from one measurement: `costs[r]` is the device time rank r
+    spent on its rows `bounds[r]` (waiting for neighbours excluded).  The cost is taken as uniform inside each measured
+    strip, so the cumulative cost is piecewise linear in the row index; the new boundaries are where it crosses
+    k/N of the total.  Rows are rounded to `quantum` and no strip gets fewer than `min_rows` (>= the halo, so that a
+    strip's boundary rows always come from its direct neighbour).  Pure function (tested on CPU)."""
+    world = len(bounds)
+    height = bounds[-1][1]
+    total = float(sum(costs))
+    if world == 1 or total <= 0:
+        return list(bounds)
+    cuts, r, acc = [], 0, 0.0
+    for k in range(1, world):
+        target = total * k / world
+        while r < world - 1 and acc + costs[r] < target:
+            acc += costs[r]
+            r += 1
+        b, e = bounds[r]
+        frac = (target - acc) / costs[r] if costs[r] > 0 else 0.0
+        cuts.append(b + min(max(frac, 0.0), 1.0) * (e - b))
+    rows = [int(round(c / quantum)) * quantum for c in cuts]
+    # enforce the minimum height from both ends
+    prev = 0
+    for k in range(world - 1):
+        rows[k] = max(rows[k], prev + min_rows)
+        prev = rows[k]
+    nxt = height
+    for k in range(world - 2, -1, -1):
+        rows[k] = min(rows[k], nxt - min_rows)
+        nxt = rows[k]
+    edges = [0] + rows + [height]
+    if any(edges[i + 1] - edges[i] < min(min_rows, height // world) for i in range(world)):
+        return list(bounds)   # film too small to honour the minimum: keep what we have
+    return [(edges[i], edges[i + 1]) for i in range(world)]
+
+
 def storage_rows(row_begin, row_end, height, halo):
     return max(row_begin - halo, 0), min(row_end + halo, height)
 
@@ -42,7 +78,10 @@ class StripLink:
         return restirpt.device_lib().rpt_frame_peer_error(self.frame)
 
     def close(self):
-        pass
+        """every rank drops its mappings of the neighbours' buffers, then a barrier: after it any strip may be destroyed"""
+        import torch.distributed as dist
+        restirpt.device_lib().rpt_frame_disconnect_peers(self.frame)
+        dist.barrier()
 
 
 def connect_strips(renderer, frame, rank, world):
