@@ -269,6 +269,8 @@ int rpt_set_camera(RptFrame* frame, const RptCamera* cur, const RptCamera* prev)
 /* ---- passes.  Each replaces one RayTracing::execute / pass ::render call of the reference ------------- */
 int rpt_gbuffer(RptFrame* f, const RptScene* s);                               /* GBufferPass::render, src/GBufferPass.cpp:22-56 */
 int rpt_di_naive(RptFrame* f, const RptScene* s);                              /* mNaiveDIPass,  shader di_naive.comp */
+int rpt_di_naive_rt(RptFrame* f, const RptScene* s);                           /* mNaiveDIPass in RayTracing-pipeline mode (src/RayTracing.h:28-30): shader di_naive.rgen,
+                                                                                   the one entry point whose estimator differs from its .comp twin */
 int rpt_gi_naive(RptFrame* f, const RptScene* s);                              /* mNaiveGIPass,  shader gi_naive.comp */
 int rpt_di_pathgen(RptFrame* f, const RptScene* s, const RptDISettings* st);   /* TestReSTIR::render step 1, src/TestReSTIR.cpp:9-36 */
 int rpt_di_temporal(RptFrame* f, const RptScene* s, const RptDISettings* st);  /*   step 2 */

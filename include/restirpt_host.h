@@ -49,6 +49,8 @@ RhRenderer* rh_renderer_create(const RhScene* s, uint32_t width, uint32_t height
 void rh_renderer_destroy(RhRenderer* r);
 void rh_renderer_set_methods(RhRenderer* r, int directMethod, int indirectMethod, int toneMapping,
                              int correctGamma, int accumulate);
+/* RayTracing::Mode of the reference (src/RayTracing.h:28-30): 0 = RayQuery (.comp shaders, default), 1 = RayTracing (.rgen) */
+void rh_renderer_set_pipeline_mode(RhRenderer* r, int mode);
 void rh_renderer_set_gris(RhRenderer* r, const RptGRISSettings* st);
 void rh_renderer_set_di(RhRenderer* r, const RptDISettings* st);
 void rh_renderer_clear_reservoirs(RhRenderer* r);

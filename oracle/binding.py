@@ -30,6 +30,7 @@ def oracle_lib():
         "orc_set_camera": (None, [P, P, P]),
         "orc_gbuffer": (None, [P, P]),
         "orc_di_naive": (None, [P, P]),
+        "orc_di_naive_rt": (None, [P, P]),
         "orc_gi_naive": (None, [P, P]),
         "orc_di_pathgen": (None, [P, P, P]),
         "orc_di_temporal": (None, [P, P, P]),

@@ -110,6 +110,7 @@ void orc_set_camera(OrcFrame* f, const RptCamera* cur, const RptCamera* prev) { 
 
 ORC_PASS(orc_gbuffer(OrcFrame* f, const OrcScene* s), passGBuffer(sc, fr, y0, y1))
 ORC_PASS(orc_di_naive(OrcFrame* f, const OrcScene* s), passDINaive(sc, fr, y0, y1))
+ORC_PASS(orc_di_naive_rt(OrcFrame* f, const OrcScene* s), passDINaiveRT(sc, fr, y0, y1))
 ORC_PASS(orc_gi_naive(OrcFrame* f, const OrcScene* s), passGINaive(sc, fr, y0, y1))
 ORC_PASS(orc_di_pathgen(OrcFrame* f, const OrcScene* s, const RptDISettings* st), passDIPathGen(sc, fr, *st, y0, y1))
 ORC_PASS(orc_di_temporal(OrcFrame* f, const OrcScene* s, const RptDISettings* st), passDITemporal(sc, fr, *st, y0, y1))

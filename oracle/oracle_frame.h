@@ -32,6 +32,7 @@ struct Ray { vec3 ori, dir; };
 // all passes; each is the CPU restatement of one reference shader entry point
 void passGBuffer(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1);
 void passDINaive(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1);
+void passDINaiveRT(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1);
 void passGINaive(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1);
 void passDIPathGen(const Scene& s, Frame2D& f, const RptDISettings& st, uint32_t y0, uint32_t y1);
 void passDITemporal(const Scene& s, Frame2D& f, const RptDISettings& st, uint32_t y0, uint32_t y1);

@@ -187,6 +187,31 @@ static vec3 naiveDirect(const Scene& s, const Frame2D& f, uint32_t x, uint32_t y
 	return clampColor(radiance);
 }
 
+// RT-pipeline mode (di_naive.rgen -> directIllumination, di_naive.glsl:9-52): one light sample, MIS weight computed and
+// then forced to 1 (:47), no BSDF sample
+static vec3 naiveDirectRT(const Scene& s, const Frame2D& f, uint32_t x, uint32_t y) {
+	Primary p = loadPrimary(f, x, y);
+	if (!p.valid) return V3(0.0f);
+	uint32_t rng = makeSeed(f.camera.seed, uvec2{ x, y });
+	vec3 radiance = V3(0.0f);
+	vec3 wo = -p.ray.dir;
+	const RptMaterial& mat = s.materials[p.matId];
+	if (!isBSDFDelta(mat)) {
+		LightSample ls = sampleLight(s, p.pos, sample4f(rng));
+		bool shadowed = s.traceShadow(p.pos, MinRayDistance, ls.wi, ls.dist - 1e-4f);
+		if (!shadowed && ls.pdf > 1e-6f) {
+			float weight = 1.0f;
+			radiance += ls.radiance * evalBSDF(mat, p.albedo, p.norm, wo, ls.wi) * satDot(p.norm, ls.wi) / ls.pdf * weight;
+		}
+	}
+	return clampColor(radiance);
+}
+
+void passDINaiveRT(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1) {
+	for (uint32_t y = y0; y < y1; y++) for (uint32_t x = 0; x < f.width; x++)
+		accumulate(f.directOutput, f, x, y, naiveDirectRT(s, f, x, y));
+}
+
 void passDINaive(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1) {
 	for (uint32_t y = y0; y < y1; y++) for (uint32_t x = 0; x < f.width; x++)
 		accumulate(f.directOutput, f, x, y, naiveDirect(s, f, x, y));

@@ -88,6 +88,7 @@ class Backend:
 METHOD_PASSES = {
     # (direct, indirect) method names -> pass list, as Renderer::drawFrame sequences them
     "naive": [("di_naive", None), ("gi_naive", None)],
+    "naive_rt": [("di_naive_rt", None), ("gi_naive", None)],   # RayTracing-pipeline mode: di_naive.rgen
     "di": [("di_pathgen", "di"), ("di_temporal", "di"), ("di_spatial", "di")],
     "gi": [("gi_restir", None)],
     "gris": [("gris_pathtrace", "gris"), ("gris_temporal", "gris"), ("gris_spatial", "gris")],

@@ -98,7 +98,7 @@ def test_oracle_bvh_equals_brute_force(pair):
 
 PASS_BUFFERS = {
     "gbuffer": ["DEPTH_NORMAL", "ALBEDO_MATID", "MOTION", "PRIMARY_ISEC"],
-    "di_naive": ["DIRECT_OUTPUT"], "gi_naive": ["INDIRECT_OUTPUT"],
+    "di_naive": ["DIRECT_OUTPUT"], "di_naive_rt": ["DIRECT_OUTPUT"], "gi_naive": ["INDIRECT_OUTPUT"],
     "di_pathgen": ["DI_THIS"], "di_temporal": ["DI_TEMP"], "di_spatial": ["DI_THIS", "DIRECT_OUTPUT"],
     "gi_restir": ["GI_THIS", "INDIRECT_OUTPUT"],
     "gris_pathtrace": ["GRIS_THIS"], "gris_temporal": ["GRIS_TEMP"], "gris_spatial": ["GRIS_THIS", "INDIRECT_OUTPUT"],
@@ -133,6 +133,18 @@ def test_gbuffer_and_naive_passes_bit_exact(pair):
     assert (depth > 0).mean() > 0.3
     out = shots[(1, "gi_naive", "INDIRECT_OUTPUT")]
     assert np.isfinite(out).all() and out[..., :3].mean() > 0
+
+
+def test_naive_direct_rt_pipeline_mode_bit_exact(pair):
+    """di_naive.rgen (RayTracing-pipeline mode, reference src/RayTracing.h:28-30): one light sample with weight 1 —
+    a different estimator from di_naive.comp, so the images must differ from the ray-query mode's but agree in the mean"""
+    name, sc, gpu, cpu = pair
+    rt = _compare_method(pair, "naive_rt", 2)
+    rq = _compare_method(pair, "naive", 2)
+    a, b = rt[(1, "di_naive_rt", "DIRECT_OUTPUT")][..., :3], rq[(1, "di_naive", "DIRECT_OUTPUT")][..., :3]
+    assert np.isfinite(a).all()
+    if b.mean() > 0:   # (a scene whose light is not directly visible from anywhere has both images black)
+        assert a.mean() > 0 and not np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("shift,sample", [(0, 0), (0, 2), (1, 2)])

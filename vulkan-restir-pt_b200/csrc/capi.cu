@@ -477,6 +477,7 @@ static SceneView sceneView(const RptScene* s) {
 	}
 SIMPLE_PASS(rpt_gbuffer, RPT_PASS_GBUFFER, launchGBuffer)
 SIMPLE_PASS(rpt_di_naive, RPT_PASS_DI_NAIVE, launchDINaive)
+SIMPLE_PASS(rpt_di_naive_rt, RPT_PASS_DI_NAIVE, launchDINaiveRT)
 SIMPLE_PASS(rpt_gi_naive, RPT_PASS_GI_NAIVE, launchGINaive)
 SIMPLE_PASS(rpt_gi_restir, RPT_PASS_GI_RESTIR, launchGIReSTIR)
 SIMPLE_PASS(rpt_visualize_as, RPT_PASS_VISUALIZE_AS, launchVisualizeAS)

@@ -9,6 +9,7 @@ void launchGBuffer(const FrameView& f, const SceneView& s, cudaStream_t st);
 void launchVisualizeAS(const FrameView& f, const SceneView& s, cudaStream_t st);
 void launchPostProcess(const FrameView& f, const RptPostSettings& p, uchar4* rgba8, cudaStream_t st);
 void launchDINaive(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchDINaiveRT(const FrameView& f, const SceneView& s, cudaStream_t st);
 void launchGINaive(const FrameView& f, const SceneView& s, cudaStream_t st);
 void launchDIPathGen(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
 void launchDITemporal(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);

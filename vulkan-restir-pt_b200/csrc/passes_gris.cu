@@ -273,6 +273,14 @@ RT_DEV void grisReuseAndMerge(const SceneView& s, const RptGRISSettings& st, GRI
 // :10-33) is kept directly in the pixel's output reservoir slot: it is only ever overwritten until the path ends.
 
 constexpr int ShadeBlock = 128;
+// resident blocks per SM the shading / reuse kernels are compiled for (register cap = 65536 / (128 * blocks)); they are
+// bound by the latency of dependent gathers, not by issue slots or DRAM (profiles/r1_08_*), so occupancy is worth a few spills
+#ifndef RT_BOUNCE_MINBLOCKS
+#define RT_BOUNCE_MINBLOCKS 4
+#endif
+#ifndef RT_REUSE_MINBLOCKS
+#define RT_REUSE_MINBLOCKS 4
+#endif
 constexpr uint32_t NeeNone = 0, NeeAccumulate = 1, NeeRcVertex = 2, NeeLightSampled = 3;
 
 struct PathState {
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_const
 }
 
 // bounce >= 1: one thread per slot of the bounce's extension queue
-__global__ void __launch_bounds__(ShadeBlock) grisBounceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
+__global__ void __launch_bounds__(ShadeBlock, RT_BOUNCE_MINBLOCKS) grisBounceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
 	const uint32_t n = f.wf.counters[4 * bounce];
 	const float sumPower = s.lightTable[0].prob;
 	const PathBuffers cur = pathBuffers(f, bounce);
@@ -829,7 +837,7 @@ RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptG
 	temporalStore(f, x, y, idx, resv);
 }
 
-__global__ void __launch_bounds__(ReuseBlock) grisTemporalGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisTemporalGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
 	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(ReuseBlock) grisTemporalGenKernel(const __grid
 	storeVisibilityRay(f.ru, 0, o, rayTask);
 }
 
-__global__ void __launch_bounds__(ReuseBlock) grisTemporalMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisTemporalMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
 	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
@@ -938,7 +946,7 @@ RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGR
 	accumulate(f.indirectOutput, f, x, y, radiance);
 }
 
-__global__ void __launch_bounds__(ReuseBlock) grisSpatialGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
 	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(ReuseBlock) grisSpatialGenKernel(const __grid_
 	}
 }
 
-__global__ void __launch_bounds__(ReuseBlock) grisSpatialMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialMergeKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
 	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;

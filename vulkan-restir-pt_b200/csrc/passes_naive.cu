@@ -67,6 +67,32 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) diNaiveKernel(const __
 	accumulate(f.directOutput, f, x, y, radiance);
 }
 
+// RT-pipeline mode of the reference (di_naive.rgen -> directIllumination, src/shader/di_naive.glsl:9-52): one light
+// sample, its MIS weight computed and then forced to 1 (:47), no BSDF sample.  The only pass whose .rgen and .comp entry
+// points run different estimators; the other .rgen files call the same functions as their .comp twins.
+__global__ void __launch_bounds__(PassBlockX* PassBlockY) diNaiveRTKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s) {
+	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
+	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
+	if (x >= f.width || y >= f.rowEnd) return;
+	const Primary p = loadPrimary(f, x, y);
+	float3 radiance = f3(0.0f);
+	if (p.valid) {
+		uint32_t rng = makeSeed(f.camera.seed, x, y);
+		const float3 wo = -p.ray.dir;
+		const Mat mat = loadMaterial(s, uint32_t(p.matId));
+		if (!isBSDFDelta(mat)) {
+			const LightSample ls = sampleLight(s, p.pos, sample4f(rng));
+			const bool shadowed = traceShadow(s, p.pos, MinRayDistance, ls.wi, ls.dist - 1e-4f);
+			if (!shadowed && ls.pdf > 1e-6f) {
+				const float weight = 1.0f;
+				radiance += ls.radiance * evalBSDF(mat, p.albedo, p.norm, wo, ls.wi) * satDot(p.norm, ls.wi) / ls.pdf * weight;
+			}
+		}
+		radiance = clampColor(radiance);
+	}
+	accumulate(f.directOutput, f, x, y, radiance);
+}
+
 __global__ void __launch_bounds__(PassBlockX* PassBlockY) giNaiveKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s) {
 	const uint32_t x = blockIdx.x * PassBlockX + threadIdx.x;
 	const uint32_t y = f.rowBegin + blockIdx.y * PassBlockY + threadIdx.y;
@@ -130,6 +156,9 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) giNaiveKernel(const __
 	accumulate(f.indirectOutput, f, x, y, radiance);
 }
 
+void launchDINaiveRT(const FrameView& f, const SceneView& s, cudaStream_t st) {
+	diNaiveRTKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s);
+}
 void launchDINaive(const FrameView& f, const SceneView& s, cudaStream_t st) {
 	diNaiveKernel<<<passGrid(f.width, f.rowEnd - f.rowBegin), dim3(PassBlockX, PassBlockY), 0, st>>>(f, s);
 }

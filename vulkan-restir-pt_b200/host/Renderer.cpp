@@ -51,7 +51,8 @@ void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
 	check(rpt_gbuffer(mFrame, mDeviceScene), "rpt_gbuffer");
 
 	if (settings.directMethod == RayTracingMethod::Naive) {
-		check(rpt_di_naive(mFrame, mDeviceScene), "rpt_di_naive");
+		if (settings.pipelineMode == 1) check(rpt_di_naive_rt(mFrame, mDeviceScene), "rpt_di_naive_rt");
+		else check(rpt_di_naive(mFrame, mDeviceScene), "rpt_di_naive");
 	}
 	else if (settings.directMethod == RayTracingMethod::ResampledDI) {
 		// TestReSTIR::render (src/TestReSTIR.cpp:9-36)

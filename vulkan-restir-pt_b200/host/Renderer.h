@@ -20,6 +20,9 @@ struct RendererSettings {   // reference src/Renderer.h:29-36, values after init
 	int toneMapping = 1;
 	bool correctGamma = true;
 	bool accumulate = false;
+	// RayTracing::Mode (reference src/RayTracing.h:28-30,48): RayQuery = the .comp entry points (default), RayTracing = the
+	// .rgen ones.  Only the naive direct pass runs a different estimator in the two modes (di_naive.rgen vs di_naive.comp).
+	int pipelineMode = 0;   // 0 RayQuery, 1 RayTracing
 };
 
 // called between the temporal and the spatial pass when the frame is one strip of a multi-GPU film:

@@ -78,6 +78,7 @@ void rh_renderer_set_methods(RhRenderer* r, int d, int i, int tm, int gamma, int
 	r->r->settings.directMethod = d; r->r->settings.indirectMethod = i; r->r->settings.toneMapping = tm;
 	r->r->settings.correctGamma = gamma != 0; r->r->settings.accumulate = acc != 0;
 }
+void rh_renderer_set_pipeline_mode(RhRenderer* r, int mode) { r->r->settings.pipelineMode = mode == 1 ? 1 : 0; }
 void rh_renderer_set_gris(RhRenderer* r, const RptGRISSettings* st) { r->r->grisSettings = *st; }
 void rh_renderer_set_di(RhRenderer* r, const RptDISettings* st) { r->r->diSettings = *st; }
 void rh_renderer_clear_reservoirs(RhRenderer* r) { r->r->clearReservoirs(); }

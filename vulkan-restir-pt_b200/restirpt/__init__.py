@@ -176,6 +176,7 @@ DEVICE_API = {
     "rpt_set_camera": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Camera)]),
     "rpt_gbuffer": (C.c_int, [P, P]),
     "rpt_di_naive": (C.c_int, [P, P]),
+    "rpt_di_naive_rt": (C.c_int, [P, P]),
     "rpt_gi_naive": (C.c_int, [P, P]),
     "rpt_di_pathgen": (C.c_int, [P, P, C.POINTER(DISettings)]),
     "rpt_di_temporal": (C.c_int, [P, P, C.POINTER(DISettings)]),
@@ -230,6 +231,7 @@ HOST_API = {
     "rh_renderer_create": (P, [P, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rh_renderer_destroy": (None, [P]),
     "rh_renderer_set_methods": (None, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "rh_renderer_set_pipeline_mode": (None, [P, C.c_int]),
     "rh_renderer_set_gris": (None, [P, C.POINTER(GRISSettings)]),
     "rh_renderer_set_di": (None, [P, C.POINTER(DISettings)]),
     "rh_renderer_clear_reservoirs": (None, [P]),
