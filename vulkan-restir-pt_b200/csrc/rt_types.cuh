@@ -74,7 +74,10 @@ struct WavefrontView {
 	uint32_t* tailList;               // pixels of the tail, one per slot of the extension queue of bounce WavefrontTailStart
 	uint32_t epoch;                   // changes with every path-tracing pass
 };
-constexpr int WavefrontTailStart = 7;
+#ifndef RT_TAIL_START
+#define RT_TAIL_START 7
+#endif
+constexpr int WavefrontTailStart = RT_TAIL_START;
 
 // Buffers of the wavefront reuse passes (temporal: 1 candidate per pixel, spatial: 3), indexed by candidate * capacity +
 // owned-pixel index (row-major over the owned rows): no compaction, every access is a full coalesced run.
