@@ -385,6 +385,14 @@ def run_cuda(args):
         lpf = kernels[dom]["launches_per_frame"]
         achieved = kernels[dom]["achieved_gbs"]
         total_rays = sum(v.closestRays + v.shadowRays for v in counters.values())
+        # DRAM bytes of one launch of the dominant kernel, measured once under ncu --set full (profiles/ncu_traffic.json)
+        traffic, traffic_src = None, None
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            if t:
+                traffic, traffic_src = t["bytes_per_launch"], t["source"] + f", a launch of {t['rays_in_launch']} rays"
+        except (OSError, ValueError, KeyError):
+            pass
         fps = 1000.0 * args.steps / dev_ms
         equiv = (fw * fh) / float(TILE_W * TILE_H)   # 1080p-equivalents per film frame (= N in the default weak-scaling mode)
         line = {
@@ -405,7 +413,7 @@ def run_cuda(args):
                     "h2d_bytes_per_step": 2 * 352, "d2h_bytes_per_step": strip_bytes},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom] / lpf, "kernel_ms": kernels[dom]["ms_per_frame"] / lpf,
                          "launches_per_frame": lpf,
                          "nodes_per_ray": c.nodeVisits / max(rays, 1), "tris_per_ray": c.triTests / max(rays, 1),

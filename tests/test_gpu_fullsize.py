@@ -81,3 +81,33 @@ def test_full_hd_film_strips_and_reservoir_invariants(bench_scene):
     assert ((res["flags"][lit] & 0xff) >= 1).all()          # rcVertexId
     assert (((res["flags"][lit] >> 8) & 0xff) <= 15).all()   # pathLength
     dev.lib.rpt_scene_destroy(scene_h)
+
+
+def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
+    """The paths alive after bounce 6 are finished by one in-line kernel (grisTailKernel); RPT_WAVEFRONT_TAIL=1 runs them
+    through nine more wavefront rounds instead.  Same stage functions, so the reservoirs must agree bit for bit — at full
+    size, where the tail holds tens of thousands of paths."""
+    w, h = 960, 540
+    dev = restirpt.Device(0)
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+    out = {}
+    for mode in ("inline", "wavefront"):
+        if mode == "wavefront":
+            monkeypatch.setenv("RPT_WAVEFRONT_TAIL", "1")
+        else:
+            monkeypatch.delenv("RPT_WAVEFRONT_TAIL", raising=False)
+        b = Backend("cuda", bench_scene, w, h, dev)
+        drv = FrameDriver(bench_scene.camera(w, h))
+        for _ in range(2):
+            cur, prev = drv.begin_frame()
+            b.set_camera(cur, prev)
+            for name in ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"):
+                b.run(name, None if name == "gbuffer" else gs)
+            b.flip()
+        wc = (C.c_uint32 * 64)()
+        dev.lib.rpt_wavefront_counters(b.frame, wc)
+        out[mode] = (b.read("GRIS_PREV"), b.read("INDIRECT_OUTPUT"), wc[4 * 7])
+        b.close()
+    assert out["inline"][2] > 1000, "the scene must have a tail for this test to mean anything"
+    assert bitwise_mismatch(out["inline"][0], out["wavefront"][0]) == 0
+    assert bitwise_mismatch(out["inline"][1], out["wavefront"][1]) == 0

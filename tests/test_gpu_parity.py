@@ -156,6 +156,16 @@ def test_restir_gi_bit_exact(pair):
     _compare_method(pair, "gi", 4, moves=DOLLY)
 
 
+def test_parity_scenes_reach_the_path_tracing_tail(pair):
+    """the bit-exact GRIS comparisons below only cover grisTailKernel if some paths survive bounce 6 on these small films"""
+    name, sc, gpu, cpu = pair
+    import ctypes as C
+    run_frames(gpu, sc.camera(gpu.w, gpu.h), "gris", 1)
+    wc = (C.c_uint32 * 64)()
+    gpu.lib.rpt_wavefront_counters(gpu.frame, wc)
+    assert wc[4 * 7] > 0, f"{name}: no path alive at bounce 7"
+
+
 @pytest.mark.parametrize("shift,temporal,spatial", [(2, 1, 1), (0, 1, 1), (2, 0, 1), (2, 1, 0)])
 def test_restir_pt_gris_bit_exact(pair, shift, temporal, spatial):
     shots = _compare_method(pair, "gris", 4, moves=DOLLY, gris=GRISSettings(shift, 1.0, temporal, spatial, 20))
