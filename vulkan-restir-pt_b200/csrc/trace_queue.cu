@@ -23,11 +23,17 @@ constexpr int TraceBlock = 128;
 constexpr uint32_t NoRay = 0xffffffffu;
 constexpr int FetchThreshold = 8;   // idle lanes per warp that trigger a fetch
 
+// resident blocks per SM the kernel is compiled for (0 = leave the register count to the compiler: 64 / 56 registers)
 #ifndef RT_TRACE_MINBLOCKS
-#define RT_TRACE_MINBLOCKS 10   // 48 registers (a few spills), 40 warps per SM: measured optimum of 8 / 10 / 12 / 16 (profiles/r1_10_*)
+#define RT_TRACE_MINBLOCKS 0
+#endif
+#if RT_TRACE_MINBLOCKS > 0
+#define RT_TRACE_BOUNDS __launch_bounds__(TraceBlock, RT_TRACE_MINBLOCKS)
+#else
+#define RT_TRACE_BOUNDS __launch_bounds__(TraceBlock)
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(TraceBlock, RT_TRACE_MINBLOCKS) traceQueueKernel(const __grid_constant__ SceneView s, const float4* __restrict__ rays,
+__global__ void RT_TRACE_BOUNDS traceQueueKernel(const __grid_constant__ SceneView s, const float4* __restrict__ rays,
                                                                 const uint32_t* __restrict__ countPtr, uint32_t countHost, uint32_t* __restrict__ head,
                                                                 RptIntersection* __restrict__ hits, uint8_t* __restrict__ occluded) {
 	const uint32_t n = countPtr ? *countPtr : countHost;
