@@ -133,6 +133,52 @@ def test_xml_and_obj_loader(tmp_path, built):
     assert np.allclose(cam.front[:], [0, 1, 0], atol=1e-5) and cam.filmSize[0] == 64
 
 
+def test_obj_objects_groups_and_mtl_materials(tmp_path, built):
+    """OBJ import with assimp's structure (ObjFileParser / ObjFileImporter) as Resource::createNewModelInstance sees it:
+    meshes per object and material, material list = DefaultMaterial + .mtl materials (+ undefined ones), the objects
+    visited in reverse order (the reference's node stack), textures from map_Kd, the XML material applied to every mesh."""
+    (tmp_path / "m").mkdir()
+    tex = bytes([255, 0, 0, 0, 255, 0, 0, 0, 255, 255, 255, 255])
+    (tmp_path / "m" / "tex.png.ppm").write_bytes(b"P6\n2 2\n255\n" + tex)
+    (tmp_path / "m" / "two.mtl").write_text(
+        "newmtl red\nKd 0.8 0.1 0.1\nKa 0 0 0\n\nnewmtl textured\nKd 0.5 0.5 0.5\nmap_Kd -s 1 1 1 tex.png\n")
+    (tmp_path / "m" / "two.obj").write_text(
+        "mtllib two.mtl\n"
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\nv 1 1 1\nv 0 1 1\nvn 0 0 1\nvt 0 0.25\n"
+        "f 1//1 2//1 3//1\n"                      # before any o / usemtl: object 'defaultobject', default material
+        "o first\nusemtl red\nf 1//1 3//1 4//1\n"
+        "usemtl textured\nf 5/1/1 6/1/1 7/1/1 8/1/1\n"   # second mesh of 'first' (a quad: 2 triangles)
+        "g second\nusemtl ghost\nf 5//1 7//1 8//1\n")   # a group is an object too; 'ghost' is not in the .mtl
+    xml_head = """<?xml version="1.0"?><scene name="t"><integrator type="path"><size width="32" height="32" /></integrator>
+<camera type="thinLens"><position value="0 -3 0" /><lookAt value="0 0 0" /><fov value="40" /></camera><modelInstances>"""
+    (tmp_path / "plain.xml").write_text(xml_head + """
+ <modelInstance path="m/two.obj" name="a" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /></modelInstance>
+</modelInstances></scene>""")
+    sc = restirpt.HostScene.xml(str(tmp_path / "plain.xml"))
+    d = sc.desc
+    assert d.numIndices == 15 and d.numVertices == 3 + 3 + 4 + 3 and d.numInstances == 1 and d.numTextures == 1
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), (d.numMaterials, 8))
+    # pool: [0] magenta placeholder, then DefaultMaterial, red, textured, ghost
+    assert d.numMaterials == 5
+    assert np.allclose(mats[1, :3], 0.6) and np.allclose(mats[2, :3], [0.8, 0.1, 0.1]) and np.allclose(mats[4, :3], 0.6)
+    tex_idx = mats.view(np.uint32)[:, 4]
+    assert tex_idx[3] == 0 and tex_idx[1] == 0xffffffff and tex_idx[2] == 0xffffffff
+    # objects in reverse order (second, first, defaultobject), meshes of an object in order: ghost | red, textured x2 | default
+    mi = np.ctypeslib.as_array(C.cast(d.materialIndices, C.POINTER(C.c_int32)), (d.numMaterialIndices,))
+    assert mi.tolist() == [4, 2, 3, 3, 1]
+    verts = np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (d.numVertices, 8))
+    assert np.allclose(verts[0, :3], [0, 0, 1])            # first vertex of the 'second' group's triangle (v5)
+    assert np.allclose(verts[6:10, 7], 0.75)               # the textured quad's vt 0.25, V flipped
+    # an XML <material> replaces the type of every mesh's material but keeps their colours / textures when it has no baseColor
+    (tmp_path / "override.xml").write_text(xml_head + """
+ <modelInstance path="m/two.obj" name="a" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" />
+  <material type="metalWorkflow"><metallic value="1.0" /><roughness value="0.3" /></material></modelInstance>
+</modelInstances></scene>""")
+    sc2 = restirpt.HostScene.xml(str(tmp_path / "override.xml"))
+    m2 = np.ctypeslib.as_array(C.cast(sc2.desc.materials, C.POINTER(C.c_float)), (sc2.desc.numMaterials, 8))
+    assert (m2.view(np.uint32)[1:5, 3] == 2).all() and np.allclose(m2[2, :3], [0.8, 0.1, 0.1]) and m2.view(np.uint32)[3, 4] == 0
+
+
 def test_png_writer_roundtrip(tmp_path, built):
     from PIL import Image
     img = (np.random.default_rng(0).random((17, 31, 4)) * 255).astype(np.uint8)

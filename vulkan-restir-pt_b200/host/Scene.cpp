@@ -165,17 +165,112 @@ uint32_t Scene::addModelFromTriangles(const std::vector<RptMeshVertex>& verts, c
 	return uint32_t(models[L].size() - 1);
 }
 
+// One material of an OBJ file's material list (assimp ObjFile::Material: diffuse defaults to 0.6)
+namespace {
+struct ObjMaterial {
+	std::string name;
+	vec3 kd = vec3(0.6f);
+	std::string mapKd;
+};
+struct ObjMesh {
+	int material = -1;   // index into the file's material list; -1 = none set (-> material 0, the default material)
+	std::vector<RptMeshVertex> verts;
+	std::vector<uint32_t> idx;
+};
+struct ObjObject {
+	std::string name;
+	std::vector<size_t> meshes;
+};
+
+std::string restOfLine(const char* q) {
+	q = skipSpace(q);
+	const char* e = q;
+	while (*e && *e != '\n' && *e != '\r') e++;
+	while (e > q && (e[-1] == ' ' || e[-1] == '\t')) e--;
+	return std::string(q, e);
+}
+std::string firstWord(const char* q) {
+	q = skipSpace(q);
+	const char* e = q;
+	while (*e && *e != '\n' && *e != '\r' && *e != ' ' && *e != '\t') e++;
+	return std::string(q, e);
+}
+std::string parentDirOf(const std::string& p) {
+	size_t k = p.find_last_of("/\\");
+	return k == std::string::npos ? std::string(".") : p.substr(0, k);
+}
+
+// .mtl: newmtl / Kd / map_Kd (assimp ObjFileMtlImporter; everything else is irrelevant to Resource::createNewModelInstance,
+// which reads AI_MATKEY_COLOR_DIFFUSE and the first diffuse texture only, reference src/Resource.cpp:150-176)
+void parseMtl(const std::string& mtlPath, std::vector<ObjMaterial>& lib) {
+	std::ifstream f(mtlPath, std::ios::binary);
+	if (!f) return;   // assimp logs an error and goes on: usemtl then creates named materials with default values
+	std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	int cur = -1;
+	const char* p = text.c_str();
+	const char* end = p + text.size();
+	while (p < end) {
+		const char* line = p;
+		const char* nl = static_cast<const char*>(std::memchr(p, '\n', size_t(end - p)));
+		p = nl ? nl + 1 : end;
+		line = skipSpace(line);
+		if (std::strncmp(line, "newmtl", 6) == 0 && (line[6] == ' ' || line[6] == '\t')) {
+			const std::string name = restOfLine(line + 6);
+			cur = -1;
+			for (size_t i = 0; i < lib.size(); i++) if (lib[i].name == name) cur = int(i);
+			if (cur < 0) { ObjMaterial m; m.name = name; lib.push_back(m); cur = int(lib.size() - 1); }
+		}
+		else if (cur >= 0 && line[0] == 'K' && line[1] == 'd' && (line[2] == ' ' || line[2] == '\t')) {
+			char* e;
+			lib[cur].kd.x = std::strtof(line + 3, &e); lib[cur].kd.y = std::strtof(e, &e); lib[cur].kd.z = std::strtof(e, &e);
+		}
+		else if (cur >= 0 && std::strncmp(line, "map_Kd", 6) == 0 && (line[6] == ' ' || line[6] == '\t')) {
+			// options (-s, -o, -bm ...) precede the file name: the name is the last token
+			std::string rest = restOfLine(line + 6);
+			size_t k = rest.find_last_of(" \t");
+			lib[cur].mapKd = k == std::string::npos ? rest : rest.substr(k + 1);
+		}
+	}
+}
+} // namespace
+
+// OBJ import with assimp's structure (ext/assimp/code/AssetLib/Obj/ObjFileParser.cpp, ObjFileImporter.cpp):
+//   * `o` / `g` start a new object, every object starts a mesh, `usemtl` starts another mesh when the current one already
+//     has faces of a different material; one aiMesh per non-empty mesh, one vertex per face corner;
+//   * the material list starts with "DefaultMaterial" (diffuse 0.6), followed by the .mtl materials in file order and by
+//     materials that are used but not defined; every one of them becomes a Material of the pool
+//     (reference src/Resource.cpp:150-176), meshInstance.materialIdx = pool offset + index (:228-233);
+//   * Resource::createNewModelInstance walks the node tree with a stack (src/Resource.cpp:129-147), i.e. it visits the
+//     objects in REVERSE file order; the meshes of one object stay in order;
+//   * post-process steps per mesh: fan triangulation, V flipped, flat normals where missing, FixInfacingNormals.
 uint32_t Scene::addModelFromOBJ(const std::string& objPath, bool isLight) {
 	std::ifstream f(objPath, std::ios::binary);
 	if (!f) throw std::runtime_error("OBJ: cannot open " + objPath);
 	std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+	const std::string dir = parentDirOf(objPath);
 
 	std::vector<vec3> P, N;
 	std::vector<vec2> T;
-	std::vector<RptMeshVertex> verts;
-	std::vector<uint32_t> idx;
 	std::vector<ObjCorner> face;
-	bool anyMissingNormal = false;
+	std::vector<ObjMaterial> lib(1);
+	lib[0].name = "DefaultMaterial";
+	std::vector<ObjMesh> meshes;
+	std::vector<ObjObject> objects;
+	int curObject = -1, curMesh = -1, curMaterial = -1;
+	std::string activeGroup;
+
+	auto createMesh = [&]() {
+		meshes.emplace_back();
+		curMesh = int(meshes.size() - 1);
+		if (curObject >= 0) objects[size_t(curObject)].meshes.push_back(size_t(curMesh));
+	};
+	auto createObject = [&](const std::string& name) {
+		objects.emplace_back();
+		objects.back().name = name;
+		curObject = int(objects.size() - 1);
+		createMesh();
+		if (curMaterial >= 0) meshes[size_t(curMesh)].material = curMaterial;
+	};
 
 	const char* p = text.c_str();
 	const char* end = p + text.size();
@@ -199,12 +294,42 @@ uint32_t Scene::addModelFromOBJ(const std::string& objPath, bool isLight) {
 			v.x = std::strtof(line + 3, &e); v.y = std::strtof(e, &e);
 			T.push_back(v);
 		}
+		else if (line[0] == 'o' && (line[1] == ' ' || line[1] == '\t')) {
+			const std::string name = firstWord(line + 2);
+			if (!name.empty()) {
+				curObject = -1;
+				for (size_t i = 0; i < objects.size(); i++) if (objects[i].name == name) { curObject = int(i); break; }
+				if (curObject < 0) createObject(name);
+			}
+		}
+		else if (line[0] == 'g' && (line[1] == ' ' || line[1] == '\t' || line[1] == '\r' || line[1] == '\n' || line[1] == 0)) {
+			const std::string name = restOfLine(line + 1);
+			if (activeGroup != name) { createObject(name); activeGroup = name; }
+		}
+		else if (std::strncmp(line, "usemtl", 6) == 0 && (line[6] == ' ' || line[6] == '\t')) {
+			const std::string name = restOfLine(line + 6);
+			if (name.empty() || (curMaterial >= 0 && lib[size_t(curMaterial)].name == name)) continue;
+			int found = -1;
+			for (size_t i = 0; i < lib.size(); i++) if (lib[i].name == name) found = int(i);
+			if (found < 0) { ObjMaterial m; m.name = name; lib.push_back(m); found = int(lib.size() - 1); }
+			curMaterial = found;
+			const bool needsNewMesh = curMesh < 0 ||
+				(meshes[size_t(curMesh)].material != -1 && meshes[size_t(curMesh)].material != found && !meshes[size_t(curMesh)].idx.empty());
+			if (needsNewMesh) createMesh();
+			meshes[size_t(curMesh)].material = found;
+		}
+		else if (std::strncmp(line, "mtllib", 6) == 0 && (line[6] == ' ' || line[6] == '\t')) {
+			parseMtl(dir + "/" + restOfLine(line + 6), lib);
+		}
 		else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
 			face.clear();
 			const char* q = line + 2;
 			ObjCorner c;
 			while (parseCorner(q, c, int(P.size()), int(T.size()), int(N.size()))) face.push_back(c);
 			if (face.size() < 3) continue;
+			if (curObject < 0) createObject("defaultobject");
+			if (curMesh < 0) createMesh();
+			ObjMesh& mesh = meshes[size_t(curMesh)];
 			// flat normal for corners without one (aiProcess_GenNormals; all shipped assets carry vn)
 			vec3 fn(0.f);
 			{
@@ -213,28 +338,68 @@ uint32_t Scene::addModelFromOBJ(const std::string& objPath, bool isLight) {
 				float l = length(n);
 				fn = l > 0.f ? n / l : vec3(0.f, 0.f, 1.f);
 			}
-			uint32_t base = uint32_t(verts.size());
+			uint32_t base = uint32_t(mesh.verts.size());
 			for (auto& k : face) {
 				RptMeshVertex mv;
 				vec3 pos = P[k.v];
 				vec3 nrm = fn;
-				if (k.vn >= 0 && k.vn < int(N.size())) nrm = N[k.vn]; else anyMissingNormal = true;
+				if (k.vn >= 0 && k.vn < int(N.size())) nrm = N[k.vn];
 				vec2 uv;
 				if (k.vt >= 0 && k.vt < int(T.size())) { uv = T[k.vt]; uv.y = 1.0f - uv.y; }   // aiProcess_FlipUVs
 				mv.pos[0] = pos.x; mv.pos[1] = pos.y; mv.pos[2] = pos.z; mv.uvx = uv.x;
 				mv.norm[0] = nrm.x; mv.norm[1] = nrm.y; mv.norm[2] = nrm.z; mv.uvy = uv.y;
-				verts.push_back(mv);
+				mesh.verts.push_back(mv);
 			}
 			for (uint32_t k = 1; k + 1 < face.size(); k++) {   // fan from corner 0 (convex polygons)
-				idx.push_back(base); idx.push_back(base + k); idx.push_back(base + k + 1);
+				mesh.idx.push_back(base); mesh.idx.push_back(base + k); mesh.idx.push_back(base + k + 1);
 			}
 		}
 	}
-	(void)anyMissingNormal;
-	fixInfacingNormals(verts, idx);
-	uint32_t id = addModelFromTriangles(verts, idx, isLight, vec3(0.6f));
-	models[isLight ? 1 : 0][id].path = objPath;
-	return id;
+
+	// ---- Resource::createNewModelInstance (src/Resource.cpp:100-181) ----
+	const int L = isLight ? 1 : 0;
+	ModelInstance model;
+	model.meshOffset = uint32_t(meshInstances[L].size());
+	model.refId = uint32_t(models[L].size());
+	model.path = objPath;
+	const uint32_t materialOffset = uint32_t(materials.size());
+	for (size_t o = objects.size(); o-- > 0;) {          // the reference's node stack pops the last child first
+		for (size_t m : objects[o].meshes) {
+			ObjMesh& src = meshes[m];
+			if (src.idx.empty()) continue;
+			fixInfacingNormals(src.verts, src.idx);
+			MeshInstance mesh;
+			mesh.vertexOffset = uint32_t(vertices[L].size());
+			mesh.vertexCount = uint32_t(src.verts.size());
+			mesh.indexOffset = uint32_t(indices[L].size());
+			mesh.indexCount = uint32_t(src.idx.size());
+			mesh.materialIdx = int(materialOffset) + (src.material >= 0 ? src.material : 0);
+			vertices[L].insert(vertices[L].end(), src.verts.begin(), src.verts.end());
+			const size_t firstIndex = indices[L].size();
+			indices[L].insert(indices[L].end(), src.idx.begin(), src.idx.end());
+			for (size_t k = firstIndex; k < indices[L].size(); k++) indices[L][k] += mesh.vertexOffset;
+			if (!isLight) materialIndices.insert(materialIndices.end(), src.idx.size() / 3, mesh.materialIdx);
+			meshInstances[L].push_back(mesh);
+			model.numMeshes++;
+			model.numIndices += mesh.indexCount;
+			model.numVertices += mesh.vertexCount;
+		}
+	}
+	if (model.numMeshes == 0) throw std::runtime_error("OBJ: no faces in " + objPath);
+	if (!isLight) {
+		for (const ObjMaterial& om : lib) {
+			RptMaterial m = defaultMaterial();
+			m.baseColor[0] = om.kd.x; m.baseColor[1] = om.kd.y; m.baseColor[2] = om.kd.z;
+			m.textureIdx = InvalidResourceIdx;
+			if (!om.mapKd.empty()) {
+				uint32_t loaded;
+				if (loadTextureFile(dir + "/" + om.mapKd, 0u, &loaded)) m.textureIdx = loaded;
+			}
+			materials.push_back(m);
+		}
+	}
+	models[L].push_back(model);
+	return uint32_t(models[L].size() - 1);
 }
 
 void Scene::setModelMaterial(uint32_t modelIdx, RptMaterial mat, bool overrideColor, vec3 baseColor, uint32_t textureIdx) {
