@@ -75,7 +75,8 @@ def main():
           f"nodes/ray {c.nodeVisits/max(rays,1):.1f} tris/ray {c.triTests/max(rays,1):.1f} hits {c.shadedHits/1e6:.2f} M  max nodes of one queued ray {c.maxNodeVisits}")
     wc = (C.c_uint32 * 64)()
     dev.lib.rpt_wavefront_counters(b.frame, wc)
-    print("wavefront rays per bounce (extension/shadow):", " ".join(f"{b_}:{wc[4*b_]}/{wc[4*b_+1]}" for b_ in range(1, 15)))
+    print("wavefront queue slots per bounce (each = path state + extension ray + the previous vertex's shadow ray):",
+          " ".join(f"{b_}:{wc[4*b_]}" for b_ in range(1, 15)))
     print(f"Mrays/s {rays/1e6/(total/frames/1000):.1f}")
     img = b.postprocess(PostSettings(1, 1, 1, 0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
