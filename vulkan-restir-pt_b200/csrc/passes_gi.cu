@@ -88,7 +88,9 @@ RT_DEV void finishPath(const FrameView& f, uint32_t o, const GIPath& p) {
 }
 
 // roulette + BSDF sample of the current vertex (gi_resample_temporal.glsl:146-169), then hand the path to the next bounce
-RT_DEV void scatterAndContinue(const FrameView& f, GIPath& p, const Surface& surf, const Mat& mat, uint32_t pix, uint32_t o) {
+// sh0 / sh1 = the shadow ray of this vertex's light sample (an empty interval when there is none): it shares the slot of the
+// next bounce's queue with the path state and the extension ray
+RT_DEV void scatterAndContinue(const FrameView& f, GIPath& p, const Surface& surf, const Mat& mat, uint32_t pix, uint32_t o, float4 sh0, float4 sh1) {
 	const int bounce = p.bounce;
 	bool go = true;
 	float3 rayOri = f3(0.0f);
@@ -132,6 +134,10 @@ RT_DEV void scatterAndContinue(const FrameView& f, GIPath& p, const Surface& sur
 		rq[0] = make_float4(0.f, 0.f, 0.f, 1.0f);
 		rq[1] = make_float4(0.f, 0.f, 1.f, 0.0f);
 	}
+	if (bounce > 0) {   // (the G-buffer vertex draws no light sample: the shadow queue of bounce 0 is never traced)
+		float4* sq = f.wf.shadowRays[bounce & 1] + 2 * size_t(nslot);
+		sq[0] = sh0; sq[1] = sh1;
+	}
 	f.wf.pix[parity][nslot] = pix;
 	storePath(f, parity, nslot, p);
 }
@@ -164,7 +170,8 @@ __global__ void __launch_bounds__(GIBlock) giBeginKernel(const __grid_constant__
 	recordPlane(f, 2)[o] = make_float4(0.f, 0.f, __uint_as_float(InvalidHitIndex), 0.f);     // psIsec
 	const Surface surf = primarySurface(pr);
 	const Mat mat = loadMaterial(s, uint32_t(pr.matId));
-	scatterAndContinue(f, p, surf, mat, pix, o);
+	const float4 none0 = make_float4(0.f, 0.f, 0.f, 1.0f), none1 = make_float4(0.f, 0.f, 1.f, 0.0f);
+	scatterAndContinue(f, p, surf, mat, pix, o, none0, none1);
 }
 
 __global__ void __launch_bounds__(GIBlock) giBounceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, int bounce) {
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(GIBlock) giBounceKernel(const __grid_constant_
 		loadPath(f, parity, slot, p);
 		// (1) the light sample of the previous vertex
 		if (p.neePending) {
-			if (f.wf.occluded[(bounce - 1) & 1][p.shadowIdx] == 0) p.rcLo += p.nee;
+			if (f.wf.occluded[(bounce - 1) & 1][slot] == 0) p.rcLo += p.nee;
 			p.neePending = false;
 		}
 		if (p.zombie) { finishPath(f, o, p); continue; }
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(GIBlock) giBounceKernel(const __grid_constant_
 			continue;
 		}
 		// (3) light sample (:107-144); the shader traces its shadow ray even when the sample cannot contribute
+		float4 sh0 = make_float4(0.f, 0.f, 0.f, 1.0f), sh1 = make_float4(0.f, 0.f, 1.f, 0.0f);
 		if (!isBSDFDelta(mat)) {
 			const LightSample ls = sampleLight(s, surf.pos, sample4f(p.rng));
 			if (ls.pdf > 1e-6f) {
@@ -213,14 +221,12 @@ __global__ void __launch_bounds__(GIBlock) giBounceKernel(const __grid_constant_
 				const float weight = MISWeight(ls.pdf, bsdfPdf);
 				p.nee = ls.radiance * evalBSDF(mat, surf.albedo, surf.norm, -p.dir, ls.wi) * satDot(surf.norm, ls.wi) / ls.pdf * weight * p.throughputAfter;
 				p.neePending = true;
-				p.shadowIdx = queueAppend(f.wf.counters + 4 * bounce + 1);
-				float4* rq = f.wf.shadowRays[parity] + 2 * size_t(p.shadowIdx);
-				rq[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
-				rq[1] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
+				sh0 = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
+				sh1 = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
 			}
 		}
 		// (4)
-		scatterAndContinue(f, p, surf, mat, pix, o);
+		scatterAndContinue(f, p, surf, mat, pix, o, sh0, sh1);
 	}
 }
 
@@ -319,7 +325,7 @@ void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st) {
 	// bounce 15 only drains the paths whose last light sample is still pending
 	for (int bounce = 1; bounce <= 15; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
-		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c - 4 + 1, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);
+		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);   // (slot-aligned with this bounce's queue)
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
 		giBounceKernel<<<bounceBlocks, GIBlock, 0, st>>>(f, s, bounce);
 	}

@@ -568,13 +568,13 @@ RT_DEV void shadeAndContinue(const FrameView& f, const SceneView& s, const RptGR
                              const VertexOut& vo, uint32_t pix, RptGRISReservoir* __restrict__ slot) {
 	const int bounce = st.bounce;
 	st.neeKind = NeeNone;
+	// the light sample's shadow ray; an empty interval (reported unoccluded without touching the BVH) when there is none
+	float4 sh0 = make_float4(0.f, 0.f, 0.f, 1.0f), sh1 = make_float4(0.f, 0.f, 1.f, 0.0f);
 	if (bounce > 0 && !isBSDFDelta(mat)) {
 		const LightSample ls = sampleLight(s, surf.pos, vo.lightRandSample);
 		if (neePrepare(st, surf, mat, ls, vo.resvRandSample)) {
-			st.shadowIdx = queueAppend(f.wf.counters + 4 * bounce + 1);
-			float4* rq = f.wf.shadowRays[bounce & 1] + 2 * size_t(st.shadowIdx);
-			rq[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
-			rq[1] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
+			sh0 = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, MinRayDistance);
+			sh1 = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, ls.dist - MinRayDistance);
 		}
 	}
 	float3 rayOri = f3(0.0f);
@@ -586,6 +586,8 @@ RT_DEV void shadeAndContinue(const FrameView& f, const SceneView& s, const RptGR
 		return;
 	}
 	st.zombie = !go;
+	// one slot of the next bounce's queue holds the path state, its extension ray AND the shadow ray of this vertex's light
+	// sample: one atomic per vertex, and the next kernel reads the visibility bit at its own slot index (coalesced)
 	const uint32_t nslot = queueAppend(f.wf.counters + 4 * (bounce + 1));
 	float4* rq = f.wf.rays[(bounce + 1) & 1] + 2 * size_t(nslot);
 	if (go) {
@@ -595,6 +597,10 @@ RT_DEV void shadeAndContinue(const FrameView& f, const SceneView& s, const RptGR
 	else {   // zombie: an empty interval, the traversal kernel reports a miss without touching the BVH
 		rq[0] = make_float4(0.f, 0.f, 0.f, 1.0f);
 		rq[1] = make_float4(0.f, 0.f, 1.f, 0.0f);
+	}
+	if (bounce > 0) {   // (the G-buffer vertex draws no light sample: the shadow queue of bounce 0 is never traced)
+		float4* sq = f.wf.shadowRays[bounce & 1] + 2 * size_t(nslot);
+		sq[0] = sh0; sq[1] = sh1;
 	}
 	f.wf.pix[(bounce + 1) & 1][nslot] = pix;
 	if (bounce + 1 == WavefrontTailStart) { f.wf.tailList[nslot] = pix; f.wf.tailMark[pix] = f.wf.epoch; }
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(ShadeBlock, RT_BOUNCE_MINBLOCKS) grisBounceKer
 		loadPathState(cur, slotIdx, st);
 		// (1) the light sample of the previous vertex
 		if (st.neeKind != NeeNone) {
-			if (f.wf.occluded[(bounce - 1) & 1][st.shadowIdx] == 0) neeApply(cur, pix, st, st.zombie ? st.bounce : st.bounce - 1, slot);   // index of the vertex that drew the sample
+			if (f.wf.occluded[(bounce - 1) & 1][slotIdx] == 0) neeApply(cur, pix, st, st.zombie ? st.bounce : st.bounce - 1, slot);   // index of the vertex that drew the sample
 			st.neeKind = NeeNone;
 		}
 		if (st.zombie) { finishPath(cur, pix, st, slot); continue; }
@@ -700,7 +706,7 @@ __global__ void __launch_bounds__(TailBlock) grisTailKernel(const __grid_constan
 		// the two rays queued by the last wavefront bounce: the light sample's shadow ray and the extension ray
 		float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
 		if (st.neeKind != NeeNone) {
-			const float4* rq = f.wf.shadowRays[(first - 1) & 1] + 2 * size_t(st.shadowIdx);
+			const float4* rq = f.wf.shadowRays[(first - 1) & 1] + 2 * size_t(slotIdx);
 			sh0 = rq[0]; sh1 = rq[1];
 		}
 		float3 rayOri = f3(f.wf.rays[first & 1][2 * size_t(slotIdx)]);
@@ -1044,7 +1050,7 @@ void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const Rp
 	for (int bounce = firstBounce; bounce <= lastBounce; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
 		if (clock && bounce > 1) clock->tick(RPT_KERNEL_TRACE_ANY);
-		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c - 4 + 1, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);
+		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);   // (slot-aligned with this bounce's queue)
 		if (clock && bounce < 15) clock->tick(RPT_KERNEL_TRACE_CLOSEST);
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
 		if (clock) clock->tick(RPT_KERNEL_GRIS_BOUNCE);

@@ -51,6 +51,8 @@ __global__ void RT_TRACE_BOUNDS traceQueueKernel(const __grid_constant__ SceneVi
 
 	for (;;) {
 		// ---- dynamic fetch ----------------------------------------------------------------------------------
+		// (Measured and rejected, profiles/r1_12_*: issuing the queue atomic one loop iteration before its result is used, so
+		// that its round trip overlaps a traversal step — the lanes that wait idle for it cost more than the stall saves.)
 		const unsigned idleMask = __ballot_sync(FullWarp, rayIdx == NoRay);
 		if (!dry && __popc(idleMask) >= FetchThreshold) {
 			const int leader = __ffs(int(idleMask)) - 1;
@@ -62,13 +64,13 @@ __global__ void RT_TRACE_BOUNDS traceQueueKernel(const __grid_constant__ SceneVi
 			if (rayIdx == NoRay) {
 				const uint32_t idx = base + uint32_t(__popc(idleMask & ((1u << lane) - 1u)));
 				if (idx < n) {
-					if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
 					const float4 a = __ldcs(rays + 2 * size_t(idx)), b = __ldcs(rays + 2 * size_t(idx) + 1);
 					if (rayIsDegenerate(f3(a), a.w, f3(b), b.w)) {
 						if (MODE == TraceAny) occluded[idx] = 0;
 						else { RptIntersection o; o.bary[0] = 0.f; o.bary[1] = 0.f; o.instanceIdx = InvalidHitIndex; o.triangleIdx = 0; hits[idx] = o; }
 					}
 					else {
+						if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);   // (empty-interval placeholders are not rays)
 						rayIdx = idx;
 						r = makeTravRay(f3(a), a.w, f3(b));
 						tmaxOrig = b.w;
