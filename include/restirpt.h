@@ -250,6 +250,9 @@ int rpt_version(void);
  * Builds the flattened world-space compressed wide BVH on the GPU. */
 int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* desc, RptScene** out);
 void rpt_scene_destroy(RptScene* scene);
+/* dynamic scenes (new; the reference is static): new transforms / radiance of the object instances, same
+ * geometry ranges; rebuilds the acceleration structure on the GPU.  Synchronises the device. */
+int rpt_scene_update_instances(RptScene* scene, const RptObjectInstance* instances, uint32_t numInstances);
 int rpt_scene_bvh_stats(const RptScene* scene, RptBvhStats* out);
 
 /* ---- frame resources (replaces Renderer::createRayImage + GBufferPass::createResource,

@@ -29,6 +29,9 @@ void rh_scene_destroy(RhScene* s);
 void rh_scene_desc(const RhScene* s, RptSceneDesc* out);   /* pointers stay valid until rh_scene_destroy */
 void rh_scene_camera(const RhScene* s, RptCamera* out);
 uint32_t rh_scene_num_triangles(const RhScene* s);
+/* dynamic scenes (new): place object model `objectIdx` anew (translate, scale, rotate in degrees: the XML <transform>
+ * attributes, reference src/Model.cpp:11-21); returns 0, or -1 with rh_last_error */
+int rh_scene_set_object_transform(RhScene* s, uint32_t objectIdx, const float pos[3], const float scale[3], const float rotDeg[3]);
 
 /* Camera (reference src/Camera.cpp) operating on the raw 352-byte block */
 void rh_camera_init(RptCamera* cam, const float pos[3], const float angleDeg[3], float fovDeg,
@@ -58,6 +61,8 @@ void rh_renderer_camera_move(RhRenderer* r, const float delta[3]);
 void rh_renderer_camera(RhRenderer* r, RptCamera* out);
 typedef void (*RhHaloExchangeFn)(void* user, RptFrame* frame, RptBufferId buffer);
 void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* user);
+/* push the scene's object instances to the device and rebuild the acceleration structure (rpt_scene_update_instances) */
+int rh_renderer_update_instances(RhRenderer* r, const RhScene* s);
 int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out);   /* 0 ok, -1 error */
 RptFrame* rh_renderer_frame(RhRenderer* r);
 RptScene* rh_renderer_scene(RhRenderer* r);

@@ -179,6 +179,24 @@ def test_obj_objects_groups_and_mtl_materials(tmp_path, built):
     assert (m2.view(np.uint32)[1:5, 3] == 2).all() and np.allclose(m2[2, :3], [0.8, 0.1, 0.1]) and m2.view(np.uint32)[3, 4] == 0
 
 
+def test_set_object_transform_rewrites_the_instance(built):
+    """dynamic scenes: rh_scene_set_object_transform rebuilds transform / inverse / inverse-transpose of one ObjectInstance
+    (reference src/Model.cpp:11-21: T * Rz * Rx(+90) * Ry * S(x, z, y)) and leaves the others alone"""
+    sc = restirpt.HostScene.cornell()
+    n = sc.desc.numInstances
+    before = np.ctypeslib.as_array(C.cast(sc.desc.instances, C.POINTER(C.c_float)), (n, 56)).copy()
+    sc.set_object_transform(6, (0.25, -0.5, 0.125), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+    after = np.ctypeslib.as_array(C.cast(sc.desc.instances, C.POINTER(C.c_float)), (n, 56)).copy()
+    assert np.array_equal(before[:6], after[:6])
+    M = after[6, :16].reshape(4, 4).T
+    Minv = after[6, 16:32].reshape(4, 4).T
+    MinvT = after[6, 32:48].reshape(4, 4).T
+    assert np.allclose(M[:3, 3], [0.25, -0.5, 0.125]) and np.allclose(M @ Minv, np.eye(4), atol=1e-5) and np.allclose(MinvT, Minv.T)
+    assert np.array_equal(before[6, 48:].view(np.uint32), after[6, 48:].view(np.uint32))   # radiance, index range untouched
+    with pytest.raises(restirpt.RestirptError):
+        sc.set_object_transform(99, (0, 0, 0))
+
+
 def test_png_writer_roundtrip(tmp_path, built):
     from PIL import Image
     img = (np.random.default_rng(0).random((17, 31, 4)) * 255).astype(np.uint8)

@@ -212,3 +212,37 @@ def test_degenerate_rays_are_misses(pair):
     assert np.array_equal(a["instanceIdx"], b["instanceIdx"]) and np.array_equal(b["instanceIdx"], c["instanceIdx"])
     assert (a["instanceIdx"][[0, 1, 3, 4, 5, 6, 7]] == 0xffffffff).all()
     assert np.array_equal(gpu.trace_shadow(rays), cpu.trace_shadow(rays))
+
+
+def test_dynamic_scene_update_equals_a_fresh_scene(device):
+    """rpt_scene_update_instances (new transforms, BVH rebuilt on the GPU) must leave the device scene in the state a scene
+    created from scratch with those transforms has — closest-hit ids and a ReSTIR PT frame bit for bit — and that state
+    must still match the oracle"""
+    import ctypes as C
+    sc = restirpt.HostScene.cornell()
+    w, h = 96, 54
+    moved = Backend("cuda", sc, w, h, device)
+    sc.set_object_transform(6, (0.2, 0.15, 0.3), (1.0, 1.0, 1.0), (25.0, 0.0, 0.0))   # lift and turn the short box
+    restirpt.check(device.ctx, device.lib.rpt_scene_update_instances(moved.scene, sc.desc.instances, sc.desc.numInstances),
+                   "rpt_scene_update_instances")
+    fresh = Backend("cuda", sc, w, h, device)
+    cpu = Backend("oracle", sc, w, h)
+    cam = sc.camera(w, h)
+    o, d = camera_rays(cam, w, h)
+    rays = np.zeros((w * h, 8), dtype=np.float32)
+    rays[:, 0:3] = o; rays[:, 3] = 1e-4; rays[:, 4:7] = d.reshape(-1, 3); rays[:, 7] = 1e7
+    a, b, c = moved.trace_closest(rays), fresh.trace_closest(rays), cpu.trace_closest(rays)
+    assert np.array_equal(a, b) and np.array_equal(a["instanceIdx"], c["instanceIdx"]) and np.array_equal(a["triangleIdx"], c["triangleIdx"])
+    for bk in (moved, fresh, cpu):
+        run_frames(bk, cam, "gris", 2)
+    for buf in ("GRIS_PREV", "INDIRECT_OUTPUT", "DEPTH_NORMAL_PREV"):
+        assert bitwise_mismatch(moved.read(buf), fresh.read(buf)) == 0, buf
+        assert bitwise_mismatch(moved.read(buf), cpu.read(buf)) == 0, buf
+    # the geometry range of an instance cannot change
+    bad = (restirpt.ObjectInstance * sc.desc.numInstances).from_address(sc.desc.instances)
+    tampered = (restirpt.ObjectInstance * sc.desc.numInstances)()
+    C.memmove(tampered, bad, C.sizeof(tampered))
+    tampered[0].indexCount += 3
+    assert device.lib.rpt_scene_update_instances(moved.scene, tampered, sc.desc.numInstances) < 0
+    for bk in (moved, fresh, cpu):
+        bk.close()

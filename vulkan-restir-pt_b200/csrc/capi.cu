@@ -27,7 +27,8 @@ struct RptCtx {
 struct RptScene {
 	RptCtx* ctx = nullptr;
 	SceneView view{};
-	std::vector<void*> allocations;
+	std::vector<void*> allocations;   // everything but the acceleration structure
+	BuildInputs buildInputs{};        // device views kept for rpt_scene_update_instances
 	RptBvhStats stats{};
 };
 
@@ -176,6 +177,16 @@ static cudaError_t upload(RptScene* sc, const T* host, size_t n, const T** dev, 
 	return e;
 }
 
+static void adoptBvh(RptScene* sc, const BuildOutputs& bo) {
+	sc->view.nodes = bo.nodes; sc->view.tris = bo.tris;
+	sc->stats.numTriangles = bo.numTris;
+	sc->stats.numNodes = bo.numNodes;
+	sc->stats.nodeBytes = uint64_t(bo.numNodes) * sizeof(WideNode);
+	sc->stats.triBytes = uint64_t(bo.numTris) * sizeof(TriRecord);
+	sc->stats.buildMs = bo.buildMs;
+	sc->stats.sahCost = 0.0f;
+}
+
 RPT_API int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* d, RptScene** out) {
 	if (!ctx || !d || !out) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: NULL argument");
 	*out = nullptr;
@@ -234,17 +245,40 @@ RPT_API int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* d, RptScene** out)
 		if (bo.tris) cudaFree(bo.tris);
 		return bail(e, "buildBvh");
 	}
-	sc->allocations.push_back(bo.nodes);
-	sc->allocations.push_back(bo.tris);
-	v.nodes = bo.nodes; v.tris = bo.tris;
+	sc->buildInputs = in;
+	adoptBvh(sc, bo);
 	v.counters = nullptr;
-	sc->stats.numTriangles = bo.numTris;
-	sc->stats.numNodes = bo.numNodes;
-	sc->stats.nodeBytes = uint64_t(bo.numNodes) * sizeof(WideNode);
-	sc->stats.triBytes = uint64_t(bo.numTris) * sizeof(TriRecord);
-	sc->stats.buildMs = bo.buildMs;
-	sc->stats.sahCost = 0.0f;
 	*out = sc;
+	return RPT_OK;
+}
+
+// Dynamic scenes (the reference is static): new transforms / radiance for the object instances, geometry
+// unchanged.  The single-level structure is rebuilt from scratch on the GPU — flatten, sort, PLOC, collapse: 11 ms for the
+// 383 k triangles of VeachAjar — so there is no refit drift to manage.  Synchronises the device: no pass may be in flight.
+// (Triangle lights are stored in world space and are not moved by this call.)
+RPT_API int rpt_scene_update_instances(RptScene* s, const RptObjectInstance* instances, uint32_t numInstances) {
+	if (!s || !instances) return fail(s ? s->ctx : nullptr, RPT_ERR_INVALID, "rpt_scene_update_instances: NULL argument");
+	RptCtx* ctx = s->ctx;
+	if (numInstances != s->buildInputs.numInstances) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_update_instances: the instance count cannot change");
+	CU(ctx, cudaSetDevice(ctx->device));
+	CU(ctx, cudaDeviceSynchronize());
+	std::vector<RptObjectInstance> old(numInstances);
+	CU(ctx, cudaMemcpy(old.data(), s->view.instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyDeviceToHost));
+	for (uint32_t k = 0; k < numInstances; k++) {
+		if (old[k].indexOffset != instances[k].indexOffset || old[k].indexCount != instances[k].indexCount)
+			return fail(ctx, RPT_ERR_INVALID, "rpt_scene_update_instances: an instance's geometry range (indexOffset / indexCount) cannot change");
+	}
+	CU(ctx, cudaMemcpy(const_cast<RptObjectInstance*>(s->view.instances), instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyHostToDevice));
+	BuildOutputs bo;
+	cudaError_t e = buildBvh(s->buildInputs, ctx->stream, &bo);
+	if (e != cudaSuccess) {
+		if (bo.nodes) cudaFree(bo.nodes);
+		if (bo.tris) cudaFree(bo.tris);
+		return cudaFail(ctx, e, "buildBvh");
+	}
+	cudaFree(const_cast<WideNode*>(s->view.nodes));
+	cudaFree(const_cast<TriRecord*>(s->view.tris));
+	adoptBvh(s, bo);
 	return RPT_OK;
 }
 
@@ -252,6 +286,8 @@ RPT_API void rpt_scene_destroy(RptScene* s) {
 	if (!s) return;
 	cudaSetDevice(s->ctx->device);
 	for (void* p : s->allocations) cudaFree(p);
+	if (s->view.nodes) cudaFree(const_cast<WideNode*>(s->view.nodes));
+	if (s->view.tris) cudaFree(const_cast<TriRecord*>(s->view.tris));
 	delete s;
 }
 

@@ -31,6 +31,11 @@ Renderer::~Renderer() {
 	if (mCtx) rpt_ctx_destroy(mCtx);
 }
 
+void Renderer::updateInstances(const Scene& scene) {
+	check(rpt_scene_update_instances(mDeviceScene, scene.objectInstances.data(), uint32_t(scene.objectInstances.size())),
+	      "rpt_scene_update_instances");
+}
+
 void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
 	// processGUI tail (src/Renderer.cpp:654-660): without accumulation the camera is re-updated every
 	// frame, which zeroes frameIndex so every frame is shown un-accumulated

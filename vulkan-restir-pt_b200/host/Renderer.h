@@ -39,6 +39,8 @@ public:
 
 	// one frame; rgba8Out may be null (no read-back).  seed = this frame's Camera::seed
 	void drawFrame(uint32_t seed, uint8_t* rgba8Out);
+	// dynamic scenes: push the scene's current object instances to the device and rebuild the acceleration structure
+	void updateInstances(const Scene& scene);
 	void clearReservoirs() { mClearNext = true; }   // GUI "clear" → Camera::setClearFlag
 	void setHaloExchange(HaloExchangeFn fn, void* user) { mHaloFn = fn; mHaloUser = user; }
 

@@ -481,6 +481,19 @@ void Scene::commitInstance(uint32_t modelIdx, bool isLight, vec3 power) {
 	}
 }
 
+void Scene::setObjectTransform(uint32_t modelIdx, vec3 pos, vec3 scale, vec3 rotationDeg) {
+	if (modelIdx >= models[0].size() || modelIdx >= objectInstances.size()) throw std::runtime_error("Scene: no such object model");
+	ModelInstance& model = models[0][modelIdx];
+	model.pos = pos; model.scale = scale; model.rotation = rotationDeg;
+	const mat4 transform = model.modelMatrix();
+	const mat4 inv = inverse(transform);
+	const mat4 invT = transpose(inv);
+	RptObjectInstance& inst = objectInstances[modelIdx];   // one instance per object model, in model order (commitInstance)
+	std::memcpy(inst.transform, &transform, 64);
+	std::memcpy(inst.transformInv, &inv, 64);
+	std::memcpy(inst.transformInvT, &invT, 64);
+}
+
 void Scene::buildLightDataStructure() {
 	std::vector<float> power(triangleLights.size());
 	for (size_t i = 0; i < triangleLights.size(); i++) {

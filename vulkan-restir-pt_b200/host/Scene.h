@@ -56,6 +56,9 @@ public:
 	// finalises instance `modelIdx` (transform already set on the ModelInstance): appends an ObjectInstance or
 	// the world-space TriangleLights of power `power` (reference Scene::loadModels, src/Scene.cpp:192-300)
 	void commitInstance(uint32_t modelIdx, bool isLight, vec3 power);
+	// dynamic scenes: a new placement for object model `modelIdx` (its ObjectInstance is rewritten in place; the device
+	// scene follows with Renderer::updateInstances / rpt_scene_update_instances)
+	void setObjectTransform(uint32_t modelIdx, vec3 pos, vec3 scale, vec3 rotationDeg);
 	void setModelMaterial(uint32_t modelIdx, RptMaterial mat, bool overrideColor, vec3 baseColor, uint32_t textureIdx);
 	uint32_t addTexture(HostImage img);                       // returns texture index
 	bool loadTextureFile(const std::string& path, uint32_t filter, uint32_t* outIdx);

@@ -41,6 +41,13 @@ void rh_scene_destroy(RhScene* s) { delete s; }
 void rh_scene_desc(const RhScene* s, RptSceneDesc* out) { *out = s->scene.desc(); }
 void rh_scene_camera(const RhScene* s, RptCamera* out) { *out = s->scene.camera.data(); }
 uint32_t rh_scene_num_triangles(const RhScene* s) { return s->scene.numTriangles(); }
+int rh_scene_set_object_transform(RhScene* s, uint32_t objectIdx, const float pos[3], const float scale[3], const float rotDeg[3]) {
+	try {
+		s->scene.setObjectTransform(objectIdx, vec3(pos[0], pos[1], pos[2]), vec3(scale[0], scale[1], scale[2]), vec3(rotDeg[0], rotDeg[1], rotDeg[2]));
+		return 0;
+	}
+	catch (const std::exception& e) { gLastError = e.what(); return -1; }
+}
 
 void rh_camera_init(RptCamera* cam, const float pos[3], const float angle[3], float fov,
                     uint32_t w, uint32_t h, float nearZ, float farZ) {
@@ -85,6 +92,10 @@ void rh_renderer_clear_reservoirs(RhRenderer* r) { r->r->clearReservoirs(); }
 void rh_renderer_camera_move(RhRenderer* r, const float d[3]) { r->r->camera().move(vec3(d[0], d[1], d[2])); }
 void rh_renderer_camera(RhRenderer* r, RptCamera* out) { *out = r->r->camera().data(); }
 void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* user) { r->r->setHaloExchange(fn, user); }
+int rh_renderer_update_instances(RhRenderer* r, const RhScene* s) {
+	try { r->r->updateInstances(s->scene); return 0; }
+	catch (const std::exception& e) { gLastError = e.what(); return -1; }
+}
 int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out) {
 	try {
 		r->r->drawFrame(seed, rgba8Out);

@@ -167,6 +167,7 @@ DEVICE_API = {
     "rpt_ctx_destroy": (None, [P]),
     "rpt_scene_create": (C.c_int, [P, C.POINTER(SceneDesc), C.POINTER(P)]),
     "rpt_scene_destroy": (None, [P]),
+    "rpt_scene_update_instances": (C.c_int, [P, P, C.c_uint32]),
     "rpt_scene_bvh_stats": (C.c_int, [P, C.POINTER(BvhStats)]),
     "rpt_frame_create": (C.c_int, [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(P)]),
     "rpt_frame_destroy": (None, [P]),
@@ -232,6 +233,8 @@ HOST_API = {
     "rh_renderer_destroy": (None, [P]),
     "rh_renderer_set_methods": (None, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rh_renderer_set_pipeline_mode": (None, [P, C.c_int]),
+    "rh_renderer_update_instances": (C.c_int, [P, P]),
+    "rh_scene_set_object_transform": (C.c_int, [P, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rh_renderer_set_gris": (None, [P, C.POINTER(GRISSettings)]),
     "rh_renderer_set_di": (None, [P, C.POINTER(DISettings)]),
     "rh_renderer_clear_reservoirs": (None, [P]),
@@ -313,6 +316,13 @@ class HostScene:
     @staticmethod
     def xml(path):
         return HostScene(host_lib().rh_scene_load_xml(path.encode()))
+
+    def set_object_transform(self, object_idx, pos, scale=(1.0, 1.0, 1.0), rot_deg=(0.0, 0.0, 0.0)):
+        """place object model `object_idx` anew (the XML <transform> attributes); self.desc stays valid (same arrays)"""
+        f3 = C.c_float * 3
+        if host_lib().rh_scene_set_object_transform(self.handle, object_idx, f3(*pos), f3(*scale), f3(*rot_deg)) != 0:
+            raise RestirptError(host_lib().rh_last_error().decode())
+        host_lib().rh_scene_desc(self.handle, C.byref(self.desc))
 
     def camera(self, width=None, height=None):
         cam = Camera()
