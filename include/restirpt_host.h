@@ -3,7 +3,7 @@
  * headless Renderer, i.e. the host classes of the reference (src/Scene.*, src/Resource.*, src/Model.*,
  * src/Material.*, src/Camera.*, src/util/AliasTable.h, src/Renderer.*) rebuilt over include/restirpt.h.
  * It exists so that tests, bench.py and other-language callers can drive the same host code; C++ callers
- * use vulkan-restir-pt_b200/host/*.h directly.
+ * use the headers under vulkan-restir-pt_b200/host/ directly.
  */
 #ifndef RESTIRPT_HOST_H
 #define RESTIRPT_HOST_H
