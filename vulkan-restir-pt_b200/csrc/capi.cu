@@ -393,7 +393,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		auto wfs = wavefrontSlots(f);
 		const size_t wfBytes[] = { px * PathStateWords * 16, px * PathStateWords * 16, f->pixels() * 32, px * 32, px * 32, px * 4, px * 4, px * 16,
 		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), f->pixels() * 4, px * 4,
-		                           px * 3 * ShiftTaskWords * 16, px * 3 * 32, px * 3, px * 4, px * 4, 16 * sizeof(uint32_t) };
+		                           px * 3 * ShiftTaskWords * 16, px * 3 * 32, px * 3, px * 3 * 4, px * 4, 16 * sizeof(uint32_t) };
 		for (size_t i = 0; i < wfs.size(); i++) {
 			e = cudaMalloc(wfs[i], wfBytes[i]);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }

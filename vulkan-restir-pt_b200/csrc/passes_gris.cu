@@ -173,12 +173,13 @@ struct ShiftTask {
 	float3 rcPrevWo, rcPrevThroughput;
 };
 
+template <bool CanTrace = true>
 RT_DEV void shiftPrepare(const SceneView& s, const RptGRISSettings& st, const Surface& dstPrimarySurf, float2 dstUv, const Ray& primaryRay,
                          const GRISResv& src, ShiftTask& t) {
 	t.status = TaskInvalid;
 	if (!src.sampleValid()) return;
 	RcData rc;
-	traceReplayPath(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
+	traceReplayPath<CanTrace>(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
 	if (rc.prevInstance == InvalidHitIndex) return;
 	if (rc.prevInstance == SpecialHitIndex) t.rcPrevSurf = dstPrimarySurf;
 	else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, t.rcPrevSurf);
@@ -952,31 +953,71 @@ RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGR
 	accumulate(f.indirectOutput, f, x, y, radiance);
 }
 
-__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+// [gen] of the spatial pass is itself two kernels.  Placing the three neighbours is a sequential chain per pixel (the
+// random numbers of neighbour i+1 depend on whether neighbour i's reservoir was well-formed) but a short one: disk sample,
+// bilinear G-buffer lookup, one 16-byte word of the neighbour's reservoir.  The shift of each chosen neighbour — reservoir
+// fetch, replay, two surface fetches (instance -> indices -> vertices -> material -> texture) — is independent of the other
+// two, so it runs as one thread per (pixel, neighbour): three times the loads in flight for the same work
+// (profiles/r1_17_*: the one-kernel form spent 40 % of its stall samples waiting for the neighbour's reservoir).
+constexpr uint32_t TaskPending = 2;   // grisSpatialPickKernel -> grisSpatialShiftKernel: neighbour chosen, shift not yet prepared
+
+__global__ void __launch_bounds__(ReuseBlock) grisSpatialPickKernel(const __grid_constant__ FrameView f, const RptGRISSettings st) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
 	const uint32_t x = o % f.width, y = f.rowBegin + o / f.width;
 	const Primary p = loadPrimary(f, x, y);
 	const bool active = p.valid && st.spatialReuse != 0;
 	uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 2u;
-	const Surface dstPrimarySurf = primarySurface(p);
+	float4* word = f.ru.task + 2 * size_t(f.ru.capacity) * 3 + o;
 	for (uint32_t i = 0; i < 3; i++) {
-		const ShiftTask* rayTask = nullptr;
-		ShiftTask t;
-		bool stored = false;
+		uint32_t packed = TaskSkip << 30;
 		Neighbor nb;
 		if (active && spatialCandidate(f, p, rng, nb)) {
-			const GRISResv nr = loadGRIS(f.grisTemp + nb.pixel);
-			if (nr.valid()) {
-				shiftPrepare(s, st, dstPrimarySurf, p.uv, p.ray, nr, t);
-				storeShiftTask(f.ru, i, o, t, uint32_t(nb.pixel));
-				stored = true;
-				rayTask = &t;
+			const float w = reinterpret_cast<const float4*>(f.grisTemp + nb.pixel)[5].y;   // GRISResv::valid()
+			if (!isnan_(w) && w >= 0) {
+				packed = uint32_t(nb.pixel) | (TaskPending << 30);
 				sample1f(rng);   // the merge's random number, assumed drawn (verified in the merge kernel)
 			}
 		}
-		if (!stored) storeSkipTask(f.ru, i, o);
-		storeVisibilityRay(f.ru, i, o, rayTask);
+		word[size_t(i) * f.ru.capacity] = make_float4(0.f, 0.f, 0.f, __uint_as_float(packed));
+	}
+}
+
+template <bool CanTrace>
+RT_DEV void spatialShiftOne(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t i, uint32_t o, uint32_t srcPixel, const GRISResv& nr) {
+	const Primary p = loadPrimary(f, o % f.width, f.rowBegin + o / f.width);
+	ShiftTask t;
+	shiftPrepare<CanTrace>(s, st, primarySurface(p), p.uv, p.ray, nr, t);
+	storeShiftTask(f.ru, i, o, t, srcPixel);
+	storeVisibilityRay(f.ru, i, o, &t);
+}
+
+// one thread per (pixel, neighbour); blockIdx.y = neighbour index.  Source samples that reconnect at the first bounce
+// (most) need no replay ray and are shifted here; the others go to a list for grisSpatialShiftListKernel, so that this
+// kernel carries no traversal code and the replay rays run in full warps instead of 4 lanes of 32.
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialShiftKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x, i = blockIdx.y;
+	if (o >= f.ru.capacity) return;
+	const uint32_t packed = __float_as_uint(f.ru.task[2 * size_t(f.ru.capacity) * 3 + size_t(i) * f.ru.capacity + o].w);
+	if ((packed >> 30) != TaskPending) {
+		storeVisibilityRay(f.ru, i, o, nullptr);
+		return;
+	}
+	const uint32_t srcPixel = packed & 0x3fffffffu;
+	const GRISResv nr = loadGRIS(f.grisTemp + srcPixel);
+	if (nr.sampleValid() && flagsRcVertexId(nr.flags()) != 1u) {
+		f.ru.shadeList[atomicAdd(f.ru.counters + 3, 1u)] = i * f.ru.capacity + o;
+		return;
+	}
+	spatialShiftOne<false>(f, s, st, i, o, srcPixel, nr);
+}
+
+__global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialShiftListKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = f.ru.counters[3];
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const uint32_t e = f.ru.shadeList[k], i = e / f.ru.capacity, o = e % f.ru.capacity;
+		const uint32_t srcPixel = __float_as_uint(f.ru.task[2 * size_t(f.ru.capacity) * 3 + size_t(e)].w) & 0x3fffffffu;
+		spatialShiftOne<true>(f, s, st, i, o, srcPixel, loadGRIS(f.grisTemp + srcPixel));
 	}
 }
 
@@ -1086,10 +1127,13 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock) {
 	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
+	static const int shiftListBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialShiftListKernel), ReuseBlock);
 	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
-	grisSpatialGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
+	grisSpatialPickKernel<<<blocks, ReuseBlock, 0, st>>>(f, p);
+	grisSpatialShiftKernel<<<dim3(blocks, 3), ReuseBlock, 0, st>>>(f, s, p);
+	grisSpatialShiftListKernel<<<shiftListBlocks, ReuseBlock, 0, st>>>(f, s, p);
 	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);

@@ -86,9 +86,10 @@ struct ReuseView {
 	float4* task;                     // ShiftTaskWords planes of 3 * capacity float4
 	float4* rays;                     // visibility rays, 2 float4 per candidate
 	uint8_t* occluded;
-	uint32_t* shadeList;              // pixels whose final shading needs a replay ray (rare) ...
+	uint32_t* shadeList;              // pixels whose final shading needs a replay ray (rare) ...  (3 * capacity entries: the spatial
+	                                  // pass first uses it for the (pixel, neighbour) pairs whose shift needs replay rays, counter [3])
 	uint32_t* redoList;               // ... and pixels whose speculated random-number sequence did not hold (very rare)
-	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head
+	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head, [3] spatial shift replay list size
 	uint32_t capacity;                // owned pixels
 };
 
