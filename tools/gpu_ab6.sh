@@ -7,7 +7,7 @@ for L in "$@"; do
   D=""; [ "$L" != "default" ] && D="$PWD/$L"
   echo "== $L" >> gpurun_out/ab6.log
   env RPT_LIB_DIR=$D timeout 600 python -m pytest tests -m gpu -x -q -k "closest or queue or shadow or degenerate or gris or fullsize or golden" 2>&1 | tail -3 >> gpurun_out/ab6.log
-  env RPT_LIB_DIR=$D timeout 300 python tools/gpu_tracebench.py 2>&1 | tail -4 >> gpurun_out/ab6.log
+  [ -n "$TRACEBENCH" ] && env RPT_LIB_DIR=$D timeout 300 python tools/gpu_tracebench.py 2>&1 | tail -4 >> gpurun_out/ab6.log
   env RPT_LIB_DIR=$D timeout 600 python bench.py --steps 60 --warmup 20 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:

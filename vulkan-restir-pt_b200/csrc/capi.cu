@@ -627,7 +627,10 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
 		FrameKernelClock clock(f);
-		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr);
+		joinTail(f);   // (the tail stream and its events are free again from here)
+		const bool side = getenv("RPT_SPATIAL_ONE_STREAM") == nullptr;   // A/B switch
+		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
+		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone);
 	}
 	peerAfter(f, HookGrisSpatial);
 	PASS_EPILOGUE("rpt_gris_spatial")

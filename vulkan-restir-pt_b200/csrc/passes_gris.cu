@@ -960,6 +960,7 @@ RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGR
 // two, so it runs as one thread per (pixel, neighbour): three times the loads in flight for the same work
 // (profiles/r1_17_*: the one-kernel form spent 40 % of its stall samples waiting for the neighbour's reservoir).
 constexpr uint32_t TaskPending = 2;   // grisSpatialPickKernel -> grisSpatialShiftKernel: neighbour chosen, shift not yet prepared
+constexpr uint32_t TaskReplay = 1;    // the same for grisSpatialShiftListKernel (the value of TaskRay, which only exists after the shift)
 
 __global__ void __launch_bounds__(ReuseBlock) grisSpatialPickKernel(const __grid_constant__ FrameView f, const RptGRISSettings st) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
@@ -973,9 +974,13 @@ __global__ void __launch_bounds__(ReuseBlock) grisSpatialPickKernel(const __grid
 		uint32_t packed = TaskSkip << 30;
 		Neighbor nb;
 		if (active && spatialCandidate(f, p, rng, nb)) {
-			const float w = reinterpret_cast<const float4*>(f.grisTemp + nb.pixel)[5].y;   // GRISResv::valid()
+			const float4* q = reinterpret_cast<const float4*>(f.grisTemp + nb.pixel);
+			const float w = q[5].y;   // GRISResv::valid()
 			if (!isnan_(w) && w >= 0) {
-				packed = uint32_t(nb.pixel) | (TaskPending << 30);
+				// a source sample that reconnects beyond the first bounce needs replay rays: grisSpatialShiftListKernel
+				const bool replay = __float_as_uint(q[0].z) != InvalidHitIndex && flagsRcVertexId(__float_as_uint(q[2].w)) != 1u;
+				packed = uint32_t(nb.pixel) | ((replay ? TaskReplay : TaskPending) << 30);
+				if (replay) f.ru.shadeList[atomicAdd(f.ru.counters + 3, 1u)] = i * f.ru.capacity + o;
 				sample1f(rng);   // the merge's random number, assumed drawn (verified in the merge kernel)
 			}
 		}
@@ -993,23 +998,20 @@ RT_DEV void spatialShiftOne(const FrameView& f, const SceneView& s, const RptGRI
 }
 
 // one thread per (pixel, neighbour); blockIdx.y = neighbour index.  Source samples that reconnect at the first bounce
-// (most) need no replay ray and are shifted here; the others go to a list for grisSpatialShiftListKernel, so that this
-// kernel carries no traversal code and the replay rays run in full warps instead of 4 lanes of 32.
+// (most) need no replay ray and are shifted here; the others are on the list of grisSpatialShiftListKernel, which runs
+// next to this kernel on a second stream — so this kernel carries no traversal code (80 registers instead of 128) and the
+// replay rays run in full warps instead of 4 lanes of 32.
 __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialShiftKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x, i = blockIdx.y;
 	if (o >= f.ru.capacity) return;
 	const uint32_t packed = __float_as_uint(f.ru.task[2 * size_t(f.ru.capacity) * 3 + size_t(i) * f.ru.capacity + o].w);
+	if ((packed >> 30) == TaskReplay) return;
 	if ((packed >> 30) != TaskPending) {
 		storeVisibilityRay(f.ru, i, o, nullptr);
 		return;
 	}
 	const uint32_t srcPixel = packed & 0x3fffffffu;
-	const GRISResv nr = loadGRIS(f.grisTemp + srcPixel);
-	if (nr.sampleValid() && flagsRcVertexId(nr.flags()) != 1u) {
-		f.ru.shadeList[atomicAdd(f.ru.counters + 3, 1u)] = i * f.ru.capacity + o;
-		return;
-	}
-	spatialShiftOne<false>(f, s, st, i, o, srcPixel, nr);
+	spatialShiftOne<false>(f, s, st, i, o, srcPixel, loadGRIS(f.grisTemp + srcPixel));
 }
 
 __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialShiftListKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
@@ -1125,15 +1127,31 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 	grisTemporalMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
 }
-void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock) {
+void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock,
+                       cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
 	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
-	static const int shiftListBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialShiftListKernel), ReuseBlock);
+	const bool twoStreams = side != nullptr && fork != nullptr && join != nullptr;
+	// next to the dense kernel the list kernel gets a part of every SM (blocks of 128 threads x 128 registers: a quarter of
+	// the register file each), alone all of it
+	static const int shiftListFull = persistentBlocks(reinterpret_cast<const void*>(grisSpatialShiftListKernel), ReuseBlock);
+	static const int shiftListPart = [] {
+		int dev = 0, sms = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		const char* e = getenv("RPT_SHIFTLIST_BLOCKS_PER_SM");   // experiments; default = measured optimum (profiles/README.md)
+		return (sms > 0 ? sms : 148) * (e ? std::max(1, atoi(e)) : 3);
+	}();
+	const int shiftListBlocks = twoStreams ? shiftListPart : shiftListFull;
 	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
 	grisSpatialPickKernel<<<blocks, ReuseBlock, 0, st>>>(f, p);
+	// the replay list (latency-bound: a few long dependent chains) next to the dense shift kernel
+	if (twoStreams) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
+	grisSpatialShiftListKernel<<<shiftListBlocks, ReuseBlock, 0, twoStreams ? side : st>>>(f, s, p);
+	if (twoStreams) cudaEventRecord(join, side);
 	grisSpatialShiftKernel<<<dim3(blocks, 3), ReuseBlock, 0, st>>>(f, s, p);
-	grisSpatialShiftListKernel<<<shiftListBlocks, ReuseBlock, 0, st>>>(f, s, p);
+	if (twoStreams) cudaStreamWaitEvent(st, join, 0);
 	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
