@@ -335,8 +335,17 @@ def run_cuda(args):
             if stats.kernelLaunches[k]:
                 kernels[name] = {"ms_per_frame": stats.kernelMs[k] / steps, "launches_per_frame": stats.kernelLaunches[k] / steps}
         tail_wait = kernels.pop("tail_wait", None)   # not a kernel: the frame's stream waiting for the path tracer's tail
-        # (the spatial pass's shade-list and redo-list kernels run inside the reuse_merge span: + 2 launches per frame)
-        launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 2) * steps)
+        # The path tracer's traversal launches: bounce 1's extension rays alone ("trace_closest" spans), then per bounce the
+        # extension rays of bounce b and the shadow rays of vertex b-1 side by side on two streams ("trace_pair" spans: two
+        # launches each).  Reported as one entry, "trace_paths"; "trace_any" is then the reuse passes' visibility launches.
+        pair = kernels.pop("trace_pair", None)
+        if pair:
+            first = kernels.pop("trace_closest")
+            kernels = {"trace_paths": {"ms_per_frame": first["ms_per_frame"] + pair["ms_per_frame"],
+                                       "launches_per_frame": first["launches_per_frame"] + 2 * pair["launches_per_frame"]}, **kernels}
+        # (the spatial pass's pick / shift / shift-list kernels share the reuse_gen span and its merge / shade-list / redo-list
+        # kernels the reuse_merge span: + 4 launches per frame)
+        launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 4) * steps)
         timed = {k: v for k, v in kernels.items() if k != "gris_tail"}
         dom = max(timed, key=lambda k: timed[k]["ms_per_frame"])
         # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record in/out,
@@ -358,7 +367,8 @@ def run_cuda(args):
             "gbuffer": ray_bytes(cg, "all") + 272 * cg.shadedHits + px * (28 + 16),
             "postprocess": px * 36,
             "trace_closest": ray_bytes(cp, "closest"),
-            "trace_any": ray_bytes(cp, "any") + ray_bytes(ct, "any") + ray_bytes(cs, "any"),
+            "trace_any": (0 if pair else ray_bytes(cp, "any")) + ray_bytes(ct, "any") + ray_bytes(cs, "any"),
+            "trace_paths": ray_bytes(cp, "closest") + ray_bytes(cp, "any"),
             "gris_begin": px * (24 + state_bytes // 2 + 36),
             "gris_bounce": 272 * cp.shadedHits + cp.closestRays * state_bytes + px * 96,
             # gen: G-buffer + candidate reservoirs in, shift task (7 x 16 B) + visibility ray (32 B) out per candidate, the
@@ -368,7 +378,8 @@ def run_cuda(args):
             "reuse_merge": px * ((112 + 96 + 96 + 1 + 96) + (96 + 3 * (112 + 96 + 1) + 96 + 32)),
         }
         nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "trace_closest": cp.closestRays,
-                 "trace_any": cp.shadowRays + ct.shadowRays + cs.shadowRays}
+                 "trace_any": (0 if pair else cp.shadowRays) + ct.shadowRays + cs.shadowRays,
+                 "trace_paths": cp.closestRays + cp.shadowRays}
         # the path tracer's tail (paths alive after bounce 6, run in line by one kernel on a second stream concurrently with the
         # temporal pass) is latency-bound and tiny: reported with its time only
         tail = kernels.pop("gris_tail", None)

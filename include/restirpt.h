@@ -226,7 +226,9 @@ typedef enum RptKernelId {
 	RPT_KERNEL_REUSE_GEN = 5,   /* temporal / spatial reuse: candidate + shift preparation kernels */
 	RPT_KERNEL_REUSE_MERGE = 6, /* temporal / spatial reuse: merge, shading and list kernels */
 	RPT_KERNEL_TAIL_WAIT = 7,   /* not a kernel: time the frame's stream waited for the path tracer's tail */
-	RPT_KERNEL_COUNT = 8
+	RPT_KERNEL_TRACE_PAIR = 8,  /* two traversal launches side by side on two streams: the extension rays of bounce b (closest hit)
+	                               and the shadow rays of vertex b-1 (any hit); one count per pair */
+	RPT_KERNEL_COUNT = 9
 } RptKernelId;
 
 typedef struct RptPassStats {

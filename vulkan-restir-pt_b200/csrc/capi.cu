@@ -515,7 +515,15 @@ SIMPLE_PASS(rpt_gbuffer, RPT_PASS_GBUFFER, launchGBuffer)
 SIMPLE_PASS(rpt_di_naive, RPT_PASS_DI_NAIVE, launchDINaive)
 SIMPLE_PASS(rpt_di_naive_rt, RPT_PASS_DI_NAIVE, launchDINaiveRT)
 SIMPLE_PASS(rpt_gi_naive, RPT_PASS_GI_NAIVE, launchGINaive)
-SIMPLE_PASS(rpt_gi_restir, RPT_PASS_GI_RESTIR, launchGIReSTIR)
+RPT_API int rpt_gi_restir(RptFrame* f, const RptScene* s) {
+	PASS_PROLOGUE("rpt_gi_restir")
+	{
+		PassTimer timer(f, RPT_PASS_GI_RESTIR);
+		const bool overlap = getenv("RPT_TRACE_ONE_STREAM") == nullptr;   // A/B switch
+		launchGIReSTIR(makeView(f), sceneView(s), f->stream, overlap ? f->tailStream : nullptr, f->tailFork, f->tailDone);
+	}
+	PASS_EPILOGUE("rpt_gi_restir")
+}
 SIMPLE_PASS(rpt_visualize_as, RPT_PASS_VISUALIZE_AS, launchVisualizeAS)
 
 // hand-over hooks around the temporal / spatial passes of a striped frame (no-ops without connected peers)
@@ -581,7 +589,9 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_PATHTRACE);
 		FrameKernelClock clock(f);
-		launchGRISPathTraceBounces(view, scene, *st, 0, WavefrontTailStart - 1, f->stream, f->timing ? &clock : nullptr);
+		const bool overlap = getenv("RPT_TRACE_ONE_STREAM") == nullptr;   // A/B switch (profiles/r1_18_*)
+		launchGRISPathTraceBounces(view, scene, *st, 0, WavefrontTailStart - 1, f->stream, f->timing ? &clock : nullptr,
+		                           overlap ? f->tailStream : nullptr, f->tailFork, f->tailDone);
 	}
 	CU(f->ctx, cudaEventRecord(f->tailFork, f->stream));
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));

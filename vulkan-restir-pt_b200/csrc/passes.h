@@ -14,12 +14,12 @@ void launchGINaive(const FrameView& f, const SceneView& s, cudaStream_t st);
 void launchDIPathGen(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
 void launchDITemporal(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
 void launchDISpatial(const FrameView& f, const SceneView& s, const RptDISettings& p, cudaStream_t st);
-void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st);
+void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 // path tracing bounces [firstBounce, lastBounce] of the wavefront (bounce 0 = the G-buffer vertex); the C ABI layer
 // runs the long tail [WavefrontTailStart, 15] on a second stream
 struct KernelClock { virtual void tick(int rptKernelId) = 0; virtual ~KernelClock() = default; };   // called before every launch
 void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
-                                KernelClock* clock = nullptr);
+                                KernelClock* clock = nullptr, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
 // tailMode 0: every pixel; 1: every pixel whose path is not in the tail; 2: only the pixels of the tail list
 void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0, KernelClock* clock = nullptr);

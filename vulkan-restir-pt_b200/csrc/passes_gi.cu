@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(GIBlock) giShadeKernel(const __grid_constant__
 
 } // namespace
 
-void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st) {
+void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+	const bool twoStreams = side != nullptr && fork != nullptr && join != nullptr;
 	static const int bounceBlocks = persistentBlocks(reinterpret_cast<const void*>(giBounceKernel), GIBlock);
 	const uint32_t rows = f.rowEnd - f.rowBegin;
 	const uint32_t slots = ((f.width + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
@@ -325,8 +326,13 @@ void launchGIReSTIR(const FrameView& f, const SceneView& s, cudaStream_t st) {
 	// bounce 15 only drains the paths whose last light sample is still pending
 	for (int bounce = 1; bounce <= 15; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
-		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);   // (slot-aligned with this bounce's queue)
+		// shadow rays of vertex b-1 next to the extension rays of bounce b, as in launchGRISPathTraceBounces
+		const bool overlap = twoStreams && bounce > 1 && bounce < 15;
+		if (overlap) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
+		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], overlap ? side : st);   // (slot-aligned with this bounce's queue)
+		if (overlap) cudaEventRecord(join, side);
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		if (overlap) cudaStreamWaitEvent(st, join, 0);
 		giBounceKernel<<<bounceBlocks, GIBlock, 0, st>>>(f, s, bounce);
 	}
 	giResolveKernel<<<blocks, GIBlock, 0, st>>>(f, s);

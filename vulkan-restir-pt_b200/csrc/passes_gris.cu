@@ -1079,7 +1079,8 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) grisSpatialRedoKernel(
 }
 
 void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const RptGRISSettings& p, int firstBounce, int lastBounce, cudaStream_t st,
-                                KernelClock* clock) {
+                                KernelClock* clock, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+	const bool twoStreams = side != nullptr && fork != nullptr && join != nullptr;
 	static const int bounceBlocks = persistentBlocks(reinterpret_cast<const void*>(grisBounceKernel), ShadeBlock);
 	if (firstBounce == 0) {
 		const uint32_t rows = f.rowEnd - f.rowBegin;
@@ -1092,10 +1093,16 @@ void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const Rp
 	// bounce 15 only drains the paths whose last light sample is still pending
 	for (int bounce = firstBounce; bounce <= lastBounce; bounce++) {
 		uint32_t* c = f.wf.counters + 4 * bounce;
-		if (clock && bounce > 1) clock->tick(RPT_KERNEL_TRACE_ANY);
-		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], st);   // (slot-aligned with this bounce's queue)
-		if (clock && bounce < 15) clock->tick(RPT_KERNEL_TRACE_CLOSEST);
+		// the shadow rays of vertex b-1 and the extension rays of bounce b are independent: on two streams the drain of the
+		// one kernel (its last, longest rays) overlaps the body of the other
+		const bool overlap = twoStreams && bounce > 1 && bounce < 15;
+		if (clock && bounce > 1) clock->tick(overlap ? RPT_KERNEL_TRACE_PAIR : RPT_KERNEL_TRACE_ANY);
+		if (overlap) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
+		if (bounce > 1) launchTraceQueueAny(s, f.wf.shadowRays[(bounce - 1) & 1], c + 0, 0, c - 4 + 3, f.wf.occluded[(bounce - 1) & 1], overlap ? side : st);   // (slot-aligned with this bounce's queue)
+		if (overlap) cudaEventRecord(join, side);
+		if (clock && bounce < 15 && !overlap) clock->tick(RPT_KERNEL_TRACE_CLOSEST);
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
+		if (overlap) cudaStreamWaitEvent(st, join, 0);
 		if (clock) clock->tick(RPT_KERNEL_GRIS_BOUNCE);
 		grisBounceKernel<<<bounceBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 	}

@@ -104,11 +104,12 @@ class PeerInfo(C.Structure):
 
 
 class PassStats(C.Structure):
-    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12), ("kernelMs", C.c_double * 8),
-                ("kernelLaunches", C.c_uint64 * 8)]
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12), ("kernelMs", C.c_double * 9),
+                ("kernelLaunches", C.c_uint64 * 9)]
 
 
-KERNEL_NAMES = ["trace_closest", "trace_any", "gris_begin", "gris_bounce", "gris_tail", "reuse_gen", "reuse_merge", "tail_wait"]
+KERNEL_NAMES = ["trace_closest", "trace_any", "gris_begin", "gris_bounce", "gris_tail", "reuse_gen", "reuse_merge", "tail_wait",
+                "trace_pair"]
 PASS_NAMES = ["gbuffer", "di_naive", "gi_naive", "di_pathgen", "di_temporal", "di_spatial", "gi_restir",
               "gris_pathtrace", "gris_temporal", "gris_spatial", "visualize_as", "postprocess"]
 
