@@ -111,3 +111,36 @@ def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
     assert out["inline"][2] > 1000, "the scene must have a tail for this test to mean anything"
     assert bitwise_mismatch(out["inline"][0], out["wavefront"][0]) == 0
     assert bitwise_mismatch(out["inline"][1], out["wavefront"][1]) == 0
+
+
+@pytest.mark.parametrize("method", ["gris", "gi"])
+def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, method):
+    """By default the frame forks work onto a second stream (the any-hit launch of vertex b-1's shadow rays next to the
+    closest-hit launch of bounce b; the spatial pass's replay-list kernel next to its dense shift kernel).
+    RPT_TRACE_ONE_STREAM / RPT_SPATIAL_ONE_STREAM put everything back on the frame's stream.  The fork / join events
+    carry every dependency, so the two schedules must produce the same bits — at a film size where the kernels really
+    run side by side."""
+    w, h = 960, 540
+    dev = restirpt.Device(0)
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+    passes = {"gris": ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"), "gi": ("gbuffer", "gi_restir")}[method]
+    out = {}
+    for mode in ("two", "one"):
+        for var in ("RPT_TRACE_ONE_STREAM", "RPT_SPATIAL_ONE_STREAM"):
+            if mode == "one":
+                monkeypatch.setenv(var, "1")
+            else:
+                monkeypatch.delenv(var, raising=False)
+        b = Backend("cuda", bench_scene, w, h, dev)
+        drv = FrameDriver(bench_scene.camera(w, h))
+        for _ in range(3):
+            cur, prev = drv.begin_frame()
+            b.set_camera(cur, prev)
+            for name in passes:
+                b.run(name, gs if name.startswith("gris_") else None)
+            b.flip()
+        out[mode] = (b.read("GRIS_PREV" if method == "gris" else "GI_PREV"), b.read("INDIRECT_OUTPUT"))
+        b.close()
+    assert out["two"][1][..., :3].mean() > 0
+    assert bitwise_mismatch(out["two"][0], out["one"][0]) == 0
+    assert bitwise_mismatch(out["two"][1], out["one"][1]) == 0
