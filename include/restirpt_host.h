@@ -69,6 +69,11 @@ RptScene* rh_renderer_scene(RhRenderer* r);
 RptCtx* rh_renderer_ctx(RhRenderer* r);
 
 int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
+/* Texture decoding of the scene front-end: zvk::HostImage::createFromFile(path, Int8, filter, 4) (reference src/Resource.cpp:26,
+   stb_image underneath).  PNG, JPEG (baseline and progressive) or binary PPM -> width x height RGBA8, released with
+   rh_free_image; NULL on failure (rh_last_error). */
+uint8_t* rh_read_image(const char* path, uint32_t* width, uint32_t* height);
+void rh_free_image(uint8_t* rgba8);
 
 #ifdef __cplusplus
 }

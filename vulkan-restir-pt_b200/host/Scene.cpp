@@ -424,9 +424,9 @@ bool Scene::loadTextureFile(const std::string& p, uint32_t filter, uint32_t* out
 		if (textures[i].path == p) { *outIdx = i; return true; }
 	}
 	HostImage img;
-	// JPEG/PNG decoding is not available in C++ here (no stb in the image): tools/prepare_assets.py
-	// writes a binary PPM sidecar "<file>.ppm" next to each texture.
-	if (!readPPM(p + ".ppm", img) && !readPPM(p, img)) return false;
+	// A binary PPM side-car "<file>.ppm" (tools/prepare_assets.py writes them with PIL's decoder) wins when present, so that
+	// measured workloads keep their texels; otherwise the file itself is decoded (Image.cpp: PNG, JPEG, PPM).
+	if (!readPPM(p + ".ppm", img) && !readImage(p, img)) return false;
 	img.filter = filter;
 	img.path = p;
 	*outIdx = addTexture(std::move(img));

@@ -101,5 +101,7 @@ void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint3
 // PNG writer (stored deflate blocks; no zlib needed) and PPM reader
 bool writePNG(const std::string& path, const uint8_t* rgba8, uint32_t w, uint32_t h);
 bool readPPM(const std::string& path, HostImage& out);
+// PNG / JPEG / binary PPM by content (Image.cpp): what the reference's stb_image call yields, 8-bit RGBA
+bool readImage(const std::string& path, HostImage& out, std::string* error = nullptr);
 
 } // namespace rpt

@@ -2,6 +2,8 @@
 #include "../../include/restirpt_host.h"
 #include "Renderer.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <string>
 
@@ -111,5 +113,16 @@ RptScene* rh_renderer_scene(RhRenderer* r) { return r->r->deviceScene(); }
 RptCtx* rh_renderer_ctx(RhRenderer* r) { return r->r->ctx(); }
 
 int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h) { return writePNG(path, rgba8, w, h) ? 0 : -1; }
+uint8_t* rh_read_image(const char* path, uint32_t* width, uint32_t* height) {
+	HostImage img;
+	std::string err;
+	if (!path || !width || !height || !readImage(path, img, &err)) { gLastError = err.empty() ? "rh_read_image: NULL argument" : err; return nullptr; }
+	uint8_t* out = static_cast<uint8_t*>(std::malloc(img.rgba8.size()));
+	if (!out) { gLastError = "rh_read_image: out of memory"; return nullptr; }
+	std::memcpy(out, img.rgba8.data(), img.rgba8.size());
+	*width = img.width; *height = img.height;
+	return out;
+}
+void rh_free_image(uint8_t* rgba8) { std::free(rgba8); }
 
 } // extern "C"

@@ -247,6 +247,8 @@ HOST_API = {
     "rh_renderer_scene": (P, [P]),
     "rh_renderer_ctx": (P, [P]),
     "rh_write_png": (C.c_int, [C.c_char_p, P, C.c_uint32, C.c_uint32]),
+    "rh_read_image": (P, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rh_free_image": (None, [P]),
 }
 
 
@@ -385,3 +387,16 @@ def read_buffer(lib, frame, buf_id, width, rows, prefix="rpt"):
     if status != 0:
         raise RestirptError(f"{prefix}_read({buf_id}) failed: {status}")
     return out
+
+
+def read_image(path):
+    """Decode a PNG / JPEG / binary PPM with the host library (rh_read_image): (height, width, 4) uint8."""
+    host = host_lib()
+    w, h = C.c_uint32(), C.c_uint32()
+    ptr = host.rh_read_image(os.fsencode(path), C.byref(w), C.byref(h))
+    if not ptr:
+        raise RestirptError(host.rh_last_error().decode())
+    try:
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        host.rh_free_image(ptr)
