@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Extract the reference's one shipped scene (res/model/VeachAjar.zip) into assets/_ref/ (git-ignored, but it
-travels to the GPU box with gpurun) and write binary-PPM sidecars for its JPEG/PNG textures, which the C++ host
-reads (no image decoder is available to C++ in this image).  Data only — no reference source is copied.
+travels to the GPU box with gpurun) and write binary-PPM sidecars for its JPEG/PNG textures.  The C++ host decodes
+PNG and JPEG itself (host/Image.cpp) but prefers a sidecar when there is one: the measured workloads and the golden
+fixtures were made with these PIL-decoded texels.  Data only — no reference source is copied.
 
 The archive uses zip method 95 (XZ), which python's zipfile refuses, so members are decoded by hand.
 Runs only where /root/reference exists (the build container); on the GPU box the prepared files are used."""
