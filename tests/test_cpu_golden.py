@@ -58,3 +58,20 @@ def test_bench_reference_arm_prints_the_contract_line(built):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+def test_bench_cpu_baseline_leg_and_its_fallback(built, monkeypatch):
+    """the main arm's `cpu_baseline` comes from the reference arm run as a child process; if the child cannot run, from the
+    same loop in-process — either way a positive frames/s figure with its sample description"""
+    import subprocess
+    import bench
+    scene, _ = bench.load_scene()
+    a = bench.cpu_baseline_leg(scene)
+    assert a["value"] > 0 and a["kind"] == "port" and a["cores"] >= 1 and "process of its own" in a["sample"]
+
+    def boom(*args, **kwargs):
+        raise OSError("no child processes today")
+    monkeypatch.setattr(subprocess, "run", boom)
+    b = bench.cpu_baseline_leg(scene)
+    assert b["value"] > 0 and b["kind"] == "port" and "process of its own" not in b["sample"]
+    assert 0.2 < a["value"] / b["value"] < 5.0
