@@ -548,7 +548,8 @@ struct JDecoder {
 			for (int y = 0; y < height; y++) std::memcpy(&out[size_t(y) * width], &c.plane[size_t(y) * pw], size_t(width));
 			return out;
 		}
-		if (exact && fx == 2 && (fy == 1 || fy == 2)) {   // triangle filter: 3/4 of the nearer sample, 1/4 of the farther one, per axis
+		if (exact && fx == 2 && (fy == 1 || fy == 2) && c.cw > 2) {   // triangle filter: 3/4 of the nearer sample, 1/4 of the farther one, per axis
+			// (planes of one or two columns are replicated below, as the common decoders do)
 			std::vector<int> row(size_t(c.cw));
 			for (int y = 0; y < height; y++) {
 				const int sy = fy == 2 ? y >> 1 : y;
