@@ -20,6 +20,7 @@ namespace rpt {
 namespace {
 
 struct DecodeError : std::runtime_error { using std::runtime_error::runtime_error; };
+constexpr uint64_t MaxPixels = 1ull << 28;   // 16k x 16k: a damaged header must not turn into a 20 GB allocation
 
 bool readFile(const std::string& p, std::vector<uint8_t>& out) {
 	FILE* f = std::fopen(p.c_str(), "rb");
@@ -189,7 +190,7 @@ void decodePNG(const std::vector<uint8_t>& file, HostImage& out) {
 		if (!std::memcmp(type, "IHDR", 4)) {
 			if (len < 13) throw DecodeError("bad IHDR");
 			w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
-			if (data[10] != 0 || data[11] != 0 || interlace > 1 || w == 0 || h == 0 || w > 65535 || h > 65535) throw DecodeError("unsupported PNG header");
+			if (data[10] != 0 || data[11] != 0 || interlace > 1 || w == 0 || h == 0 || w > 65535 || h > 65535 || uint64_t(w) * h > MaxPixels) throw DecodeError("unsupported PNG header");
 			haveHdr = true;
 		}
 		else if (!std::memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
@@ -357,7 +358,7 @@ struct JDecoder {
 		if (len < 6 || d[0] != 8) throw DecodeError("only 8-bit JPEG is supported");
 		height = be16(d + 1); width = be16(d + 3);
 		const int nc = d[5];
-		if ((nc != 1 && nc != 3) || width == 0 || height == 0 || len < 6 + 3 * nc) throw DecodeError("unsupported JPEG frame (components / size)");
+		if ((nc != 1 && nc != 3) || width == 0 || height == 0 || len < 6 + 3 * nc || uint64_t(width) * uint64_t(height) > MaxPixels) throw DecodeError("unsupported JPEG frame (components / size)");
 		comps.resize(size_t(nc));
 		for (int i = 0; i < nc; i++) {
 			JComp& c = comps[size_t(i)];
@@ -378,6 +379,7 @@ struct JDecoder {
 	void block(JBits& b, JComp& c, int16_t* q, const JHuff* hd, const JHuff* ha, int ss, int se, int ah, int al, int& eobrun) {
 		if (!progressive) {
 			const int t = jdecode(b, *hd);
+			if (t > 15) throw DecodeError("bad JPEG DC size category");
 			c.dcPred += jextend(b.get(t), t);
 			q[0] = int16_t(c.dcPred);
 			for (int k = 1; k < 64;) {
@@ -392,6 +394,7 @@ struct JDecoder {
 		if (ss == 0) {   // DC scans
 			if (ah == 0) {
 				const int t = jdecode(b, *hd);
+				if (t > 15) throw DecodeError("bad JPEG DC size category");
 				c.dcPred += jextend(b.get(t), t);
 				q[0] = int16_t(c.dcPred * (1 << al));
 			}
