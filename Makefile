@@ -1,7 +1,8 @@
-# Build of the three shared libraries (all in-tree, git-ignored, shipped to the GPU box by gpurun):
+# Build of the three shared libraries and the headless executable (all in-tree, git-ignored, shipped to the GPU box by gpurun):
 #   vulkan-restir-pt_b200/lib/librestirpt.so        CUDA kernels + C ABI (include/restirpt.h), sm_100a only
 #   vulkan-restir-pt_b200/lib/librestirpt_host.so   C++ host (Scene / Camera / Renderer), include/restirpt_host.h
-#   oracle/liboracle.so                             CPU oracle — TEST INFRASTRUCTURE, never linked by the two above
+#   vulkan-restir-pt_b200/bin/restirpt_render       the reference's main.cpp, headless (scene -> frames -> PNG)
+#   oracle/liboracle.so                             CPU oracle — TEST INFRASTRUCTURE, never linked by the three above
 PKG := vulkan-restir-pt_b200
 LIBDIR ?= $(PKG)/lib
 # experiment builds: make cuda host LIBDIR=<dir> BUILD=<dir> EXTRA=-D<macro>; loaded with RPT_LIB_DIR=<dir>
@@ -19,16 +20,17 @@ ORCFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -mfma -Iinclude -pthrea
 
 CUDA_SRCS := $(wildcard $(PKG)/csrc/*.cu)
 CUDA_HDRS := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/restirpt.h
-HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
+HOST_SRCS := $(filter-out $(PKG)/host/main.cpp,$(wildcard $(PKG)/host/*.cpp))
 HOST_HDRS := $(wildcard $(PKG)/host/*.h) include/restirpt.h include/restirpt_host.h
 ORC_SRCS := $(wildcard oracle/*.cpp)
 ORC_HDRS := $(wildcard oracle/*.h) include/restirpt.h
 
-all: cuda host oracle
+all: cuda host oracle cli
 
 cuda: $(LIBDIR)/librestirpt.so
 host: $(LIBDIR)/librestirpt_host.so
 oracle: oracle/liboracle.so
+cli: $(PKG)/bin/restirpt_render
 
 CUDA_OBJS := $(patsubst $(PKG)/csrc/%.cu,$(BUILD)/%.o,$(CUDA_SRCS))
 
@@ -44,10 +46,15 @@ $(LIBDIR)/librestirpt_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/librestirpt.s
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(HOSTFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lrestirpt -Wl,-rpath,'$$ORIGIN'
 
+# the headless executable (reference src/main.cpp): host library + CUDA library, found next to it through the rpath
+$(PKG)/bin/restirpt_render: $(PKG)/host/main.cpp $(HOST_HDRS) $(LIBDIR)/librestirpt_host.so
+	@mkdir -p $(PKG)/bin
+	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/main.cpp -L$(LIBDIR) -lrestirpt_host -lrestirpt -Wl,-rpath,'$$ORIGIN/../lib'
+
 oracle/liboracle.so: $(ORC_SRCS) $(ORC_HDRS)
 	$(CXX) $(ORCFLAGS) -shared -o $@ $(ORC_SRCS)
 
 clean:
-	rm -f $(LIBDIR)/*.so oracle/liboracle.so
+	rm -f $(LIBDIR)/*.so oracle/liboracle.so $(PKG)/bin/restirpt_render
 
-.PHONY: all cuda host oracle clean
+.PHONY: all cuda host oracle cli clean
