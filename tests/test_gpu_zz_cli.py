@@ -13,6 +13,8 @@ BIN = os.path.join(restirpt.REPO_ROOT, "vulkan-restir-pt_b200", "bin", "restirpt
 
 
 def test_cli_renders_a_screenshot(built, tmp_path):
+    if not os.path.exists(BIN):
+        pytest.skip("restirpt_render is not built on this box (tests/test_cpu_cli.py checks the build)")
     out = str(tmp_path / "shot.png")
     r = subprocess.run([BIN, "cornell", "--size", "96x54", "--frames", "6", "--seeds", "hash2", "--direct", "naive", "--out", out],
                        capture_output=True, text=True, timeout=300)
