@@ -32,6 +32,8 @@ void usage() {
 		"  --shift S             reconnection | replay | hybrid                   (ReSTIR PT, default hybrid)\n"
 		"  --temporal 0|1        temporal reuse (default 1)      --spatial 0|1   spatial reuse (default 1)\n"
 		"  --cap N               reservoir M cap (default 20)    --rr-scale X    Russian-roulette scale (default 1)\n"
+		"  --di-sample S         light | bsdf | both  (ReSTIR DI candidate sampling, default light)\n"
+		"  --di-temporal 0|1     ReSTIR DI temporal reuse (default 0)   --di-spatial 0|1   spatial reuse (default 1)\n"
 		"  --pipeline            RayTracing-pipeline mode of the naive direct pass (di_naive.rgen)\n"
 		"  --accumulate          running mean over the frames (the reference's ground-truth mode)\n"
 		"  --tonemap T           0 none | 1 filmic | 2 ACES (default 1)   --no-gamma\n"
@@ -64,6 +66,7 @@ int main(int argc, char** argv) {
 	int device = 0;
 	RendererSettings settings;
 	RptGRISSettings gris = { 2, 1.0f, 1, 1, 20 };
+	RptDISettings di = { 0, 0, 0, 1 };   // src/TestReSTIR.h:29
 	try {
 		bool haveScene = false;
 		for (int i = 1; i < argc; i++) {
@@ -89,6 +92,9 @@ int main(int argc, char** argv) {
 			else if (a == "--spatial") gris.spatialReuse = std::atoi(value().c_str()) != 0;
 			else if (a == "--cap") gris.cap = uint32_t(std::max(1, std::atoi(value().c_str())));
 			else if (a == "--rr-scale") gris.rrScale = float(std::atof(value().c_str()));
+			else if (a == "--di-sample") di.sampleType = uint32_t(choice("--di-sample", value(), { { "light", 0 }, { "bsdf", 1 }, { "both", 2 } }));
+			else if (a == "--di-temporal") di.temporalReuse = std::atoi(value().c_str()) != 0;
+			else if (a == "--di-spatial") di.spatialReuse = std::atoi(value().c_str()) != 0;
 			else if (a == "--pipeline") settings.pipelineMode = 1;
 			else if (a == "--accumulate") settings.accumulate = true;
 			else if (a == "--tonemap") settings.toneMapping = choice("--tonemap", value(), { { "0", 0 }, { "1", 1 }, { "2", 2 } });
@@ -121,6 +127,7 @@ int main(int argc, char** argv) {
 		Renderer renderer(scene, width, height, device);
 		renderer.settings = settings;
 		renderer.grisSettings = gris;
+		renderer.diSettings = di;
 		std::vector<uint8_t> rgba(out.empty() ? 0 : size_t(width) * height * 4);
 		std::mt19937 rng;
 		const auto t0 = std::chrono::steady_clock::now();
