@@ -179,6 +179,23 @@ def test_obj_objects_groups_and_mtl_materials(tmp_path, built):
     assert (m2.view(np.uint32)[1:5, 3] == 2).all() and np.allclose(m2[2, :3], [0.8, 0.1, 0.1]) and m2.view(np.uint32)[3, 4] == 0
 
 
+def test_obj_face_with_a_missing_vertex_is_an_error(tmp_path, built):
+    """found by fuzzing the loader under AddressSanitizer (profiles/r1_21_host_sanitizers.txt): an index past the vertex
+    list (or 0) used to read outside the array; assimp rejects such files too"""
+    (tmp_path / "m").mkdir()
+    head = """<?xml version="1.0"?><scene name="t"><integrator type="path"><size width="32" height="32" /></integrator>
+<camera type="thinLens"><position value="0 -3 0" /><lookAt value="0 0 0" /><fov value="40" /></camera><modelInstances>
+ <modelInstance path="m/bad.obj" name="a" type="object"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /></modelInstance>
+</modelInstances></scene>"""
+    (tmp_path / "s.xml").write_text(head)
+    for faces in ("f 1 2 9\n", "f 0 1 2\n", "f 1 2 -7\n"):
+        (tmp_path / "m" / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\n" + faces)
+        with pytest.raises(restirpt.RestirptError, match="does not exist"):
+            restirpt.HostScene.xml(str(tmp_path / "s.xml"))
+    (tmp_path / "m" / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -1\n")   # negative = relative: fine
+    assert restirpt.HostScene.xml(str(tmp_path / "s.xml")).desc.numIndices == 3
+
+
 def test_set_object_transform_rewrites_the_instance(built):
     """dynamic scenes: rh_scene_set_object_transform rebuilds transform / inverse / inverse-transpose of one ObjectInstance
     (reference src/Model.cpp:11-21: T * Rz * Rx(+90) * Ry * S(x, z, y)) and leaves the others alone"""

@@ -327,6 +327,8 @@ uint32_t Scene::addModelFromOBJ(const std::string& objPath, bool isLight) {
 			ObjCorner c;
 			while (parseCorner(q, c, int(P.size()), int(T.size()), int(N.size()))) face.push_back(c);
 			if (face.size() < 3) continue;
+			for (const ObjCorner& k : face)   // (assimp: "OBJ: vertex index out of range")
+				if (k.v < 0 || k.v >= int(P.size())) throw std::runtime_error("OBJ: " + objPath + ": a face references a vertex that does not exist");
 			if (curObject < 0) createObject("defaultobject");
 			if (curMesh < 0) createMesh();
 			ObjMesh& mesh = meshes[size_t(curMesh)];
