@@ -225,3 +225,17 @@ def test_random_files_against_pil(tmp_path, built):
             im.save(buf, format="PNG", compress_level=int(rng.integers(0, 10)))
             mine = _decode(tmp_path, "f.png", buf.getvalue())
             assert np.array_equal(mine, np.asarray(PIL.open(io.BytesIO(buf.getvalue())).convert("RGBA"))), f"file {it} ({w}x{h}, {mode})"
+
+
+def test_ppm_header_larger_than_the_file_is_rejected_quickly(tmp_path, built):
+    """a damaged size field must not turn into a multi-gigabyte allocation (found by fuzzing: profiles/r1_21_host_sanitizers.txt)"""
+    import time
+    p = tmp_path / "big.ppm"
+    p.write_bytes(b"P6\n60000 60000\n255\n" + bytes(300))
+    t0 = time.perf_counter()
+    with pytest.raises(restirpt.RestirptError):
+        restirpt.read_image(str(p))
+    assert time.perf_counter() - t0 < 1.0
+    ok = tmp_path / "ok.ppm"
+    ok.write_bytes(b"P6\n# comment\n2 1\n255\n" + bytes([1, 2, 3, 4, 5, 6]))
+    assert restirpt.read_image(str(ok)).tolist() == [[[1, 2, 3, 255], [4, 5, 6, 255]]]

@@ -885,8 +885,15 @@ bool readPPM(const std::string& p, HostImage& out) {
 		return std::fscanf(f, "%d", &v) == 1;
 	};
 	ok = ok && readInt(w) && readInt(h) && readInt(maxv) && maxv == 255 && w > 0 && h > 0;
-	if (ok) {
+	if (ok) {   // the header must not promise more than the file holds (a damaged size would otherwise allocate gigabytes)
 		std::fgetc(f);
+		const long here = std::ftell(f);
+		std::fseek(f, 0, SEEK_END);
+		const long size = std::ftell(f);
+		std::fseek(f, here, SEEK_SET);
+		ok = here >= 0 && size >= here && uint64_t(w) * uint64_t(h) * 3u <= uint64_t(size - here);
+	}
+	if (ok) {
 		std::vector<uint8_t> rgb(size_t(w) * h * 3);
 		ok = std::fread(rgb.data(), 1, rgb.size(), f) == rgb.size();
 		if (ok) {
