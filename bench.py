@@ -202,137 +202,261 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------------------
-def run_cuda(args):
-    import torch
-    import restirpt
-    from restirpt import GRISSettings, PassStats, Counters, PASS_NAMES, KERNEL_NAMES, P
-    from restirpt import multigpu
+class Arm:
+    """One process = one GPU = one strip of the film.  Holds the libraries, the scene and the torch.distributed plumbing."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU oracle)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self, args):
+        import torch
+        import restirpt
+        self.torch, self.restirpt, self.args = torch, restirpt, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if self.world != args.gpus:
+            if self.world == 1 and args.gpus > 1:
+                raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+            args.gpus = self.world
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU oracle)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.host, self.dev_lib = restirpt.host_lib(), restirpt.device_lib()
+        self.scene, self.scene_name = load_scene()
+        self.gs = restirpt.GRISSettings(2, 1.0, 1, 1, 20)
 
-    host, dev_lib = restirpt.host_lib(), restirpt.device_lib()
-    scene, scene_name = load_scene()
-    fw, fh = film_for(world)
-    strong = bool(args.film)
-    if strong:   # BASELINE.json config 4: a fixed film (3840x2160) cut into N strips
-        fw, fh = (int(v) for v in args.film.lower().split("x"))
-    halo = HALO if world > 1 else 0
-    gs = GRISSettings(2, 1.0, 1, 1, 20)
-
-    def open_strip(row0, row1):
-        r = host.rh_renderer_create(scene.handle, fw, fh, local_rank, row0, row1, halo)
+    # ---- plumbing -------------------------------------------------------------------------------------------------
+    def open_strip(self, fw, fh, row0, row1, connect=True):
+        from restirpt import multigpu, P
+        halo = HALO if self.world > 1 else 0
+        r = self.host.rh_renderer_create(self.scene.handle, fw, fh, self.local_rank, row0, row1, halo)
         if not r:
-            raise SystemExit("renderer creation failed: " + host.rh_last_error().decode())
-        host.rh_renderer_set_methods(r, 0, 3, 1, 1, 0)   # direct None, indirect ResampledPT, filmic, gamma, no accumulation
-        host.rh_renderer_set_gris(r, C.byref(gs))
-        frame = P(host.rh_renderer_frame(r))
-        link = multigpu.connect_strips(r, frame, rank, world) if world > 1 else None
+            raise SystemExit("renderer creation failed: " + self.host.rh_last_error().decode())
+        self.host.rh_renderer_set_methods(r, 0, 3, 1, 1, 0)   # direct None, indirect ResampledPT, filmic, gamma, no accumulation
+        self.host.rh_renderer_set_gris(r, C.byref(self.gs))
+        frame = P(self.host.rh_renderer_frame(r))
+        link = multigpu.connect_strips(r, frame, self.rank, self.world) if (self.world > 1 and connect) else None
         return r, frame, link
 
-    # N > 1: the strips start equal and are re-cut so that every GPU has the same amount of work (the pots and the door
-    # cost several times more per row than floor and ceiling).  Calibration = a few untimed frames per round with per-pass
-    # device timing (time spent waiting for a neighbour is outside the pass timers), costs all-gathered, boundaries moved
-    # to the equal-cost points (multigpu.balanced_partition), strips re-created.  Done before the warm-up, never timed.
-    bounds = multigpu.partition(fh, world)
-    balance_rounds = 0 if world == 1 or args.no_balance else 3
-    balance_log = []
-    for round_no in range(balance_rounds + 1):
-        r, frame, link = open_strip(*bounds[rank])
-        if round_no == balance_rounds:
-            break
-        import torch.distributed as dist
-        for i in range(6):
-            if i == 2:
-                dev_lib.rpt_sync(frame)
-                dev_lib.rpt_frame_timing(frame, 1)
-            if host.rh_renderer_draw_frame(r, restirpt.hash2(1000 + i), None) != 0:
-                raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
-        st = PassStats()
-        dev_lib.rpt_frame_pass_stats(frame, C.byref(st))
-        cost = sum(st.ms[i] for i in range(12))
-        costs = [None] * world
-        dist.all_gather_object(costs, cost)
-        balance_log.append({"rows": [b[1] - b[0] for b in bounds], "ms_per_frame": [round(c / 4, 3) for c in costs]})
-        bounds = multigpu.balanced_partition(bounds, costs, min_rows=max(2 * HALO, 64))
-        link.close()
-        host.rh_renderer_destroy(r)
-        dist.barrier()
-    row0, row1 = bounds[rank]
-    rows = row1 - row0
-    ctx = P(host.rh_renderer_ctx(r))
-    stream = torch.cuda.ExternalStream(dev_lib.rpt_frame_stream(frame), device=torch.device("cuda", local_rank))
+    def close_strip(self, r, link):
+        if link:
+            if link.error():
+                print(f"[rank {self.rank}] WARNING: a device-side strip hand-over timed out", file=sys.stderr)
+            link.close()
+        self.host.rh_renderer_destroy(r)
+        if self.dist:
+            self.dist.barrier()
 
-    frame_no = [0]
+    def barrier(self, frame):
+        self.dev_lib.rpt_sync(frame)
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    def draw(out_ptr):
-        frame_no[0] += 1
-        if host.rh_renderer_draw_frame(r, restirpt.hash2(frame_no[0]), out_ptr) != 0:
-            raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
-
-    def barrier():
-        dev_lib.rpt_sync(frame)
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
+    def max_over_ranks(self, ms):
+        if not self.dist:
             return ms
-        import torch.distributed as dist
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
-        draw(None)
-    barrier()
+    # ---- one measurement of a film --------------------------------------------------------------------------------
+    def measure(self, fw, fh, steps, warmup, want_clocks=False, bounds=None):
+        """Cuts the fw x fh film into `world` cost-balanced strips, warms up, then times `steps` device-resident frames and
+        `steps` end-to-end frames (camera upload + RGBA8 strip read back to pinned memory every frame).  Times are CUDA-event
+        times on the frame's stream, max over ranks."""
+        torch, restirpt, host, dev_lib = self.torch, self.restirpt, self.host, self.dev_lib
+        from restirpt import multigpu, PassStats, P
+        world, rank = self.world, self.rank
+        # N > 1: the strips start equal and are re-cut so that every GPU has the same amount of work (the pots and the door
+        # cost several times more per row than floor and ceiling).  Calibration = a few untimed frames per round with per-pass
+        # device timing (time spent waiting for a neighbour is outside the pass timers), costs all-gathered, boundaries moved
+        # to the equal-cost points (multigpu.balanced_partition), strips re-created.  Done before the warm-up, never timed.
+        balance_log = []
+        if bounds is None:
+            bounds = multigpu.partition(fh, world)
+            rounds = 0 if world == 1 or self.args.no_balance else 3
+            for _ in range(rounds):
+                r, frame, link = self.open_strip(fw, fh, *bounds[rank])
+                for i in range(6):
+                    if i == 2:
+                        dev_lib.rpt_sync(frame)
+                        dev_lib.rpt_frame_timing(frame, 1)
+                    if host.rh_renderer_draw_frame(r, restirpt.hash2(1000 + i), None) != 0:
+                        raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
+                st = PassStats()
+                dev_lib.rpt_frame_pass_stats(frame, C.byref(st))
+                cost = sum(st.ms[i] for i in range(12))
+                costs = [None] * world
+                self.dist.all_gather_object(costs, cost)
+                balance_log.append({"rows": [b[1] - b[0] for b in bounds], "ms_per_frame": [round(c / 4, 3) for c in costs]})
+                bounds = multigpu.balanced_partition(bounds, costs, min_rows=max(2 * HALO, 64))
+                self.close_strip(r, link)
+        r, frame, link = self.open_strip(fw, fh, *bounds[rank])
+        row0, row1 = bounds[rank]
+        rows = row1 - row0
+        stream = torch.cuda.ExternalStream(dev_lib.rpt_frame_stream(frame), device=torch.device("cuda", self.local_rank))
+        frame_no = [0]
 
-    # ---- timed region 1: device-resident frames (no read-back), per-pass events enabled -------------------------
-    dev_lib.rpt_frame_timing(frame, 1)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        draw(None)
-    e1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    stats = PassStats()
-    dev_lib.rpt_frame_pass_stats(frame, C.byref(stats))
-    dev_lib.rpt_frame_timing(frame, 0)
+        def draw(out_ptr):
+            frame_no[0] += 1
+            if host.rh_renderer_draw_frame(r, restirpt.hash2(frame_no[0]), out_ptr) != 0:
+                raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
 
-    # ---- timed region 2: end to end through the host Renderer with the RGBA8 strip read back every frame ---------
-    strip_bytes = fw * rows * 4
-    pinned = torch.empty(strip_bytes, dtype=torch.uint8).pin_memory()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        draw(P(pinned.data_ptr()))
-    e1.record(stream)
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    clock_info = clocks.stop() if clocks else None
+        for _ in range(max(warmup, 3)):
+            draw(None)
+        self.barrier(frame)
+
+        # ---- timed region 1: device-resident frames (no read-back), per-pass events enabled ---------------------------
+        dev_lib.rpt_frame_timing(frame, 1)
+        clocks = ClockSampler(self.local_rank) if (want_clocks and rank == 0) else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier(frame)
+        e0.record(stream)
+        for _ in range(steps):
+            draw(None)
+        e1.record(stream)
+        self.barrier(frame)
+        dev_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        stats = PassStats()
+        dev_lib.rpt_frame_pass_stats(frame, C.byref(stats))
+        dev_lib.rpt_frame_timing(frame, 0)
+
+        # ---- timed region 2: end to end through the host Renderer with the RGBA8 strip read back every frame -----------
+        strip_bytes = fw * rows * 4
+        pinned = torch.empty(strip_bytes, dtype=torch.uint8).pin_memory()
+        self.barrier(frame)
+        e0.record(stream)
+        for _ in range(steps):
+            draw(P(pinned.data_ptr()))
+        e1.record(stream)
+        self.barrier(frame)
+        e2e_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        clock_info = clocks.stop() if clocks else None
+        return {"r": r, "frame": frame, "link": link, "bounds": bounds, "rows": rows, "dev_ms": dev_ms, "e2e_ms": e2e_ms,
+                "stats": stats, "strip_bytes": strip_bytes, "clocks": clock_info, "balance_log": balance_log, "film": (fw, fh)}
+
+    # ---- N > 1: is the image the strips make the image one GPU makes? ------------------------------------------------
+    def check_strips(self, fw, fh, bounds):
+        """"N-GPU image == 1-GPU image bit-for-bit" on the real thing — N processes, N GPUs, CUDA-IPC peer
+        stores, device-side epoch flags.  Fresh strips render 2 frames with a static camera and 2 with a dolly (temporal reuse
+        then follows motion vectors across the cuts: the mirrored final reservoirs are exercised).  Every frame's RGBA8 rows are
+        gathered on rank 0's GPU (rpt_frame_gather_*: the post-process kernels store straight into the film image there) and
+        compared with rank 0's own render of the uncut film; the float output and the final reservoirs are compared through
+        SHA-256 digests of each strip's rows."""
+        import hashlib
+        restirpt, host, dev_lib, dist = self.restirpt, self.host, self.dev_lib, self.dist
+        from restirpt import GatherInfo, P
+        rank, world = self.rank, self.world
+        moves = [None, None, (0.0, 0.0, 0.002), (0.001, 0.0005, 0.002)]
+
+        def digests(frame, rows_lo, rows_hi, store_lo):
+            out = []
+            for name in ("INDIRECT_OUTPUT", "GRIS_PREV"):
+                b, e = C.c_uint32(), C.c_uint32()
+                dev_lib.rpt_frame_rows(frame, C.byref(b), C.byref(e))
+                a = restirpt.read_buffer(dev_lib, frame, restirpt.BUF[name], fw, e.value - b.value)
+                out.append(hashlib.sha256(np.ascontiguousarray(a[rows_lo - store_lo: rows_hi - store_lo]).tobytes()).hexdigest())
+            return out
+
+        r, frame, link = self.open_strip(fw, fh, *bounds[rank])
+        info = GatherInfo()
+        if rank == 0:
+            st = dev_lib.rpt_frame_gather_create(frame, world, C.byref(info))
+            if st != 0:
+                raise SystemExit("rpt_frame_gather_create failed: " + dev_lib.rpt_last_error(None).decode())
+        blobs = [bytes(info)]
+        dist.broadcast_object_list(blobs, src=0)
+        info = GatherInfo.from_buffer_copy(blobs[0])
+        if dev_lib.rpt_frame_gather_connect(frame, C.byref(info), rank) != 0:
+            raise SystemExit("rpt_frame_gather_connect failed: " + dev_lib.rpt_last_error(None).decode())
+        dist.barrier()
+        films, strip_digests = [], []
+        film = np.zeros((fh, fw, 4), dtype=np.uint8)
+        for i, mv in enumerate(moves):
+            if mv is not None:
+                host.rh_renderer_camera_move(r, (C.c_float * 3)(*mv))
+            if host.rh_renderer_draw_frame(r, restirpt.hash2(7000 + i), None) != 0:
+                raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
+            if rank == 0:
+                if dev_lib.rpt_gather_output(frame, film.ctypes.data_as(P)) != 0:
+                    raise SystemExit("rpt_gather_output failed: " + dev_lib.rpt_last_error(None).decode())
+                films.append(film.copy())
+            b, e = C.c_uint32(), C.c_uint32()
+            dev_lib.rpt_frame_rows(frame, C.byref(b), C.byref(e))
+            strip_digests.append(digests(frame, bounds[rank][0], bounds[rank][1], b.value))
+        all_digests = [None] * world
+        dist.all_gather_object(all_digests, strip_digests)
+        dist.barrier()
+        dev_lib.rpt_frame_gather_disconnect(frame)
+        dist.barrier()
+        self.close_strip(r, link)
+
+        result = None
+        if rank == 0:
+            # the same four frames on the uncut film, on this rank's GPU alone
+            r1 = host.rh_renderer_create(self.scene.handle, fw, fh, self.local_rank, 0, fh, 0)
+            if not r1:
+                raise SystemExit("renderer creation failed: " + host.rh_last_error().decode())
+            host.rh_renderer_set_methods(r1, 0, 3, 1, 1, 0)
+            host.rh_renderer_set_gris(r1, C.byref(self.gs))
+            f1 = P(host.rh_renderer_frame(r1))
+            img = np.zeros((fh, fw, 4), dtype=np.uint8)
+            same_img, same_buf, diff_px = [], [], []
+            for i, mv in enumerate(moves):
+                if mv is not None:
+                    host.rh_renderer_camera_move(r1, (C.c_float * 3)(*mv))
+                if host.rh_renderer_draw_frame(r1, restirpt.hash2(7000 + i), img.ctypes.data_as(P)) != 0:
+                    raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
+                same_img.append(bool(np.array_equal(img, films[i])))
+                diff_px.append(int(np.any(img != films[i], axis=-1).sum()))
+                same_buf.append(all(digests(f1, lo, hi, 0) == all_digests[k][i] for k, (lo, hi) in enumerate(bounds)))
+            host.rh_renderer_destroy(r1)
+            result = {"static_camera": bool(all(same_img[:2]) and all(same_buf[:2])),
+                      "moving_camera": bool(all(same_img[2:]) and all(same_buf[2:])),
+                      "frames": len(moves), "rgba8_pixels_differing_per_frame": diff_px,
+                      "float_output_and_reservoir_digests_equal_per_frame": same_buf,
+                      "how": "N strips on N GPUs (CUDA-IPC peer stores, device-side epoch flags), film gathered on GPU 0 by "
+                             "rpt_gather_output, compared bit for bit with the uncut film rendered on GPU 0 alone"}
+        if self.dist:
+            self.dist.barrier()
+        return result
+
+
+def ncu_reference(kernel):
+    """ncu figures of one launch of `kernel`, regenerated by tools/ncu_traffic.py from the round's .ncu-rep captures
+    (profiles/ncu_traffic.json; the capture command is in its header)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
+def run_cuda(args):
+    arm = Arm(args)
+    torch, restirpt, host, dev_lib = arm.torch, arm.restirpt, arm.host, arm.dev_lib
+    from restirpt import PassStats, Counters, PASS_NAMES, KERNEL_NAMES, P
+    rank, world, gs, scene = arm.rank, arm.world, arm.gs, arm.scene
+    fw, fh = film_for(world)
+    strong = bool(args.film)
+    if strong:   # a fixed film cut into N strips as the headline (the default run reports config 4 as config.strong_4k instead)
+        fw, fh = (int(v) for v in args.film.lower().split("x"))
+    halo = HALO if world > 1 else 0
+
+    m = arm.measure(fw, fh, args.steps, args.warmup, want_clocks=True)
+    r, frame, link, bounds, rows = m["r"], m["frame"], m["link"], m["bounds"], m["rows"]
+    dev_ms, e2e_ms, stats, strip_bytes, clock_info, balance_log = m["dev_ms"], m["e2e_ms"], m["stats"], m["strip_bytes"], m["clocks"], m["balance_log"]
+    ctx = P(host.rh_renderer_ctx(r))
 
     # ---- instrumented (untimed) frame: ray / node / triangle counters per pass for the algorithmic bytes ----------
     counters = {}
     drv_passes = [("gbuffer", None), ("gris_pathtrace", gs), ("gris_temporal", gs), ("gris_spatial", gs)]
     scene_h = P(host.rh_renderer_scene(r))
-    dev_lib.rpt_counters_enable(ctx, 1)
+    dev_lib.rpt_counters_enable(ctx, 1)   # (every rank issues the same passes, so connected strips stay in lock step)
     for name, st in drv_passes:
         dev_lib.rpt_counters_reset(ctx)
         fn = getattr(dev_lib, "rpt_" + name)
@@ -343,6 +467,37 @@ def run_cuda(args):
         counters[name] = c
     dev_lib.rpt_counters_enable(ctx, 0)
 
+    # memory roofs measured live on this GPU: L2 (a 24 MB buffer = the size of VeachAjar's BVH + triangles) and HBM reads (4 GB)
+    l2_gbs, l2_ns, hbm_read_gbs, hbm_ns = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    if rank == 0:
+        dev_lib.rpt_membench(ctx, 24 << 20, 200, C.byref(l2_gbs), C.byref(l2_ns))
+        dev_lib.rpt_membench(ctx, 4 << 30, 2, C.byref(hbm_read_gbs), C.byref(hbm_ns))
+    arm.barrier(frame)   # neighbours may still be storing into this rank's halo rows
+    arm.close_strip(r, link)
+
+    # ---- BASELINE.json config 4: the fixed 3840x2160 film cut into N strips (strong scaling), every N ------------------
+    strong_4k = None
+    if not strong and not args.no_4k:
+        if (fw, fh) == (3840, 2160):
+            m4 = m
+        else:
+            m4 = arm.measure(3840, 2160, max(args.steps // 2, 10), max(args.warmup // 2, 5))
+            arm.barrier(m4["frame"])
+            arm.close_strip(m4["r"], m4["link"])
+        steps4 = args.steps if m4 is m else max(args.steps // 2, 10)
+        strong_4k = {"film": "3840x2160", "frames_per_s": 1000.0 * steps4 / m4["dev_ms"], "ms_per_frame": m4["dev_ms"] / steps4,
+                     "e2e_frames_per_s": 1000.0 * steps4 / m4["e2e_ms"], "steps": steps4,
+                     "strip_rows": [b[1] - b[0] for b in m4["bounds"]],
+                     "note": "BASELINE.json config 4 (fixed film, N cost-balanced strips): divide by the N=1 line's figure for the "
+                             "strong-scaling efficiency"}
+
+    # ---- N > 1: strips == uncut film, on the real transport --------------------------------------------------------
+    strip_check = None
+    if world > 1 and not args.no_check:
+        cw, ch = (fw, fh)
+        strip_check = arm.check_strips(cw, ch, bounds)
+
+    rc = 0
     if rank == 0:
         px = fw * rows
         steps = args.steps
@@ -371,104 +526,119 @@ def run_cuda(args):
         launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 4) * steps)
         timed = {k: v for k, v in kernels.items() if k != "gris_tail"}
         dom = max(timed, key=lambda k: timed[k]["ms_per_frame"])
-        # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record in/out,
-        # 272 B per shaded hit, plus the kernel's per-pixel stream traffic; counts from the instrumented frame below
-        cp, cs, ct, cg = (counters[k] for k in ("gris_pathtrace", "gris_spatial", "gris_temporal", "gbuffer"))
-
-        def ray_bytes(c, kind):
-            if kind == "closest":
-                return 80 * (c.nodeVisits - c.shadowNodeVisits) + 48 * (c.triTests - c.shadowTriTests) + 48 * c.closestRays
-            if kind == "any":
-                return 80 * c.shadowNodeVisits + 48 * c.shadowTriTests + 33 * c.shadowRays
-            return 80 * c.nodeVisits + 48 * c.triTests + 48 * (c.closestRays + c.shadowRays)
-
-        state_bytes = 11 * 16 * 2 + 16 + 8 + 1 + 64   # path state planes in + out, hit, pixel ids, visibility byte, two ray records
-        def closest_bytes(c):
-            return ray_bytes(c, "closest") - 48 * c.closestRays   # in-line rays: no ray record in memory
-
-        alg = {
-            "gbuffer": ray_bytes(cg, "all") + 272 * cg.shadedHits + px * (28 + 16),
-            "postprocess": px * 36,
-            "trace_closest": ray_bytes(cp, "closest"),
-            "trace_any": (0 if pair else ray_bytes(cp, "any")) + ray_bytes(ct, "any") + ray_bytes(cs, "any"),
-            "trace_paths": ray_bytes(cp, "closest") + ray_bytes(cp, "any"),
-            "gris_begin": px * (24 + state_bytes // 2 + 36),
-            "gris_bounce": 272 * cp.shadedHits + cp.closestRays * state_bytes + px * 96,
-            # gen: G-buffer + candidate reservoirs in, shift task (7 x 16 B) + visibility ray (32 B) out per candidate, the
-            # in-line replay rays and their surface fetches; merge: tasks + reservoirs in, reservoir (+ radiance RMW) out
-            "reuse_gen": closest_bytes(ct) + closest_bytes(cs) + 272 * (ct.shadedHits + cs.shadedHits)
-                         + px * ((24 + 4 + 24 + 96 + 144) + (24 + 3 * (24 + 96) + 3 * 144)),
-            "reuse_merge": px * ((112 + 96 + 96 + 1 + 96) + (96 + 3 * (112 + 96 + 1) + 96 + 32)),
-        }
-        nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "trace_closest": cp.closestRays,
-                 "trace_any": (0 if pair else cp.shadowRays) + ct.shadowRays + cs.shadowRays,
-                 "trace_paths": cp.closestRays + cp.shadowRays}
-        # the path tracer's tail (paths alive after bounce 6, run in line by one kernel on a second stream concurrently with the
-        # temporal pass) is latency-bound and tiny: reported with its time only
         tail = kernels.pop("gris_tail", None)
-        for name, v in kernels.items():
-            v["algorithmic_gb_per_frame"] = alg[name] / 1e9
-            v["achieved_gbs"] = alg[name] / (v["ms_per_frame"] * 1e-3) / 1e9
-            if name in nrays:
-                v["mrays_per_s"] = nrays[name] / 1e6 / (v["ms_per_frame"] * 1e-3)
+        roofline = None
+        total_rays = sum(v.closestRays + v.shadowRays for v in counters.values())
+        if True:
+            # algorithmic bytes: 80 B per CWBVH node + 48 B per triangle a ray must fetch, 48 B ray record in/out,
+            # 272 B per shaded hit, plus the kernel's per-pixel stream traffic; counts from the instrumented frame above
+            cp, cs, ct, cg = (counters[k] for k in ("gris_pathtrace", "gris_spatial", "gris_temporal", "gbuffer"))
+
+            def ray_bytes(c, kind):
+                if kind == "closest":
+                    return 80 * (c.nodeVisits - c.shadowNodeVisits) + 48 * (c.triTests - c.shadowTriTests) + 48 * c.closestRays
+                if kind == "any":
+                    return 80 * c.shadowNodeVisits + 48 * c.shadowTriTests + 33 * c.shadowRays
+                return 80 * c.nodeVisits + 48 * c.triTests + 48 * (c.closestRays + c.shadowRays)
+
+            state_bytes = 11 * 16 * 2 + 16 + 8 + 1 + 64   # path state planes in + out, hit, pixel ids, visibility byte, two ray records
+
+            def closest_bytes(c):
+                return ray_bytes(c, "closest") - 48 * c.closestRays   # in-line rays: no ray record in memory
+
+            alg = {
+                "gbuffer": ray_bytes(cg, "all") + 272 * cg.shadedHits + px * (28 + 16),
+                "postprocess": px * 36,
+                "trace_closest": ray_bytes(cp, "closest"),
+                "trace_any": (0 if pair else ray_bytes(cp, "any")) + ray_bytes(ct, "any") + ray_bytes(cs, "any"),
+                "trace_paths": ray_bytes(cp, "closest") + ray_bytes(cp, "any"),
+                "gris_begin": px * (24 + state_bytes // 2 + 36),
+                "gris_bounce": 272 * cp.shadedHits + cp.closestRays * state_bytes + px * 96,
+                # gen: G-buffer + candidate reservoirs in, shift task (7 x 16 B) + visibility ray (32 B) out per candidate, the
+                # in-line replay rays and their surface fetches; merge: tasks + reservoirs in, reservoir (+ radiance RMW) out
+                "reuse_gen": closest_bytes(ct) + closest_bytes(cs) + 272 * (ct.shadedHits + cs.shadedHits)
+                             + px * ((24 + 4 + 24 + 96 + 144) + (24 + 3 * (24 + 96) + 3 * 144)),
+                "reuse_merge": px * ((112 + 96 + 96 + 1 + 96) + (96 + 3 * (112 + 96 + 1) + 96 + 32)),
+            }
+            nrays = {"gbuffer": cg.closestRays + cg.shadowRays, "trace_closest": cp.closestRays,
+                     "trace_any": (0 if pair else cp.shadowRays) + ct.shadowRays + cs.shadowRays,
+                     "trace_paths": cp.closestRays + cp.shadowRays}
+            for name, v in kernels.items():
+                v["algorithmic_gb_per_frame"] = alg[name] / 1e9
+                v["achieved_gbs"] = alg[name] / (v["ms_per_frame"] * 1e-3) / 1e9
+                if name in nrays:
+                    v["mrays_per_s"] = nrays[name] / 1e6 / (v["ms_per_frame"] * 1e-3)
+            peak, peak_src = measured_peak_gbs()
+            c = {"gbuffer": cg}.get(dom, cp)
+            rays = c.closestRays + c.shadowRays
+            lpf = kernels[dom]["launches_per_frame"]
+            achieved = kernels[dom]["achieved_gbs"]
+            kernel_ms = kernels[dom]["ms_per_frame"] / lpf
+            # ncu figures of the dominant kernel's largest launch (profiles/ncu_traffic.json, regenerated by tools/ncu_traffic.py
+            # from this round's captures): DRAM and L2 bytes, issue-slot utilisation, active lanes per instruction
+            ref = ncu_reference(dom) or {}
+            l2_frac = issue_frac = None
+            if ref.get("lts_bytes_per_launch") and ref.get("duration_us") and l2_gbs.value > 0:
+                l2_frac = ref["lts_bytes_per_launch"] / (ref["duration_us"] * 1e-6) / 1e9 / l2_gbs.value
+            if ref.get("issue_active_pct") and ref.get("threads_per_inst"):
+                issue_frac = ref["issue_active_pct"] / 100.0 * ref["threads_per_inst"] / 32.0
+            roofline = {
+                "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ref.get("dram_bytes_per_launch"), "traffic_source": ref.get("source"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom] / lpf, "kernel_ms": kernel_ms, "launches_per_frame": lpf,
+                "kernel_ms_note": "span of the kernel's launches in the frame / launches (launches on two streams overlap); "
+                                  "the ncu duration of the largest launch is in `ncu`",
+                "nodes_per_ray": c.nodeVisits / max(rays, 1), "tris_per_ray": c.triTests / max(rays, 1),
+                # roofs that apply to an L2-resident scene: measured live on this GPU by rpt_membench
+                "l2": {"peak_gbs": l2_gbs.value, "peak_how": "rpt_membench: all SMs read a 24 MB buffer 200 times with 16-byte loads (ld.global.cg)",
+                       "latency_ns": l2_ns.value, "algorithmic_frac": achieved / l2_gbs.value if l2_gbs.value > 0 else None,
+                       "ncu_lts_frac": l2_frac},
+                "hbm_read_gbs": hbm_read_gbs.value, "hbm_latency_ns": hbm_ns.value,
+                "issue": {"frac": issue_frac, "how": "ncu issue-slot utilisation x active lanes per instruction / 32: the share of the "
+                                                       "SMs' lane-issue capacity doing work — the roof this kernel is actually under"},
+                "ncu": ref or None,
+                "note": "VeachAjar's BVH + triangles (23 MB) are L2-resident and mostly L1-hit: the traversal kernels are bound by "
+                        "instruction issue, not by HBM or L2 bandwidth; `frac` is the nominal algorithmic-bytes figure the contract asks for",
+            }
         if tail:
             kernels["gris_tail (concurrent stream)"] = tail
-        peak, peak_src = measured_peak_gbs()
-        c = {"gbuffer": cg}.get(dom, cp)
-        rays = c.closestRays + c.shadowRays
-        lpf = kernels[dom]["launches_per_frame"]
-        achieved = kernels[dom]["achieved_gbs"]
-        total_rays = sum(v.closestRays + v.shadowRays for v in counters.values())
-        # DRAM bytes of one launch of the dominant kernel, measured once under ncu --set full (profiles/ncu_traffic.json)
-        traffic, traffic_src = None, None
-        try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-            if t:
-                traffic, traffic_src = t["bytes_per_launch"], t["source"] + f", a launch of {t['rays_in_launch']} rays"
-        except (OSError, ValueError, KeyError):
-            pass
         fps = 1000.0 * args.steps / dev_ms
         equiv = (fw * fh) / float(TILE_W * TILE_H)   # 1080p-equivalents per film frame (= N in the default weak-scaling mode)
         line = {
             "metric": METRIC, "value": fps * equiv, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{scene_name}, film {fw}x{fh} ({world} strip(s){'' if world == 1 else ', cost-balanced heights ' + str([b[1] - b[0] for b in bounds])}), direct None, indirect "
+            "vs_baseline": None, "dtype": "f32",
+            "data": "reference asset (VeachAjar, res/model/VeachAjar.zip of the reference repository)" if "VeachAjar" in arm.scene_name and "absent" not in arm.scene_name else "synthetic",
+            "config": {"workload": f"{arm.scene_name}, film {fw}x{fh} ({world} strip(s){'' if world == 1 else ', cost-balanced heights ' + str([b[1] - b[0] for b in bounds])}), direct None, indirect "
                                    "ResampledPT {Hybrid, rrScale 1, temporal 1, spatial 1, cap 20}, seed hash2(frame+1), static camera",
                        "film_frames_per_s": fps, "halo_rows": halo, "strip_balance_rounds": balance_log,
-                       "halo_exchange": (link.describe() if link else "none (single GPU)"),
+                       "halo_exchange": ("temporal kernels store boundary rows of the temp reservoirs, spatial kernels those of the final "
+                                         "reservoirs, into the neighbours' halo rows through CUDA-IPC peer memory (NVLink); hand-over ordered "
+                                         "by device-side epoch flags; no per-frame collective") if world > 1 else "none (single GPU)",
                        "l2_policy": "inputs larger than L2: per-frame working set (G-buffer + 3 reservoir buffers + path state + outputs "
                                     "~1.8 GB at 1080p) exceeds the 126 MB L2; every frame uses a new seed",
                        "mrays_per_s_per_gpu": total_rays / 1e6 * fps,
                        "rays_per_pixel": total_rays / px,
                        "pass_ms": per_pass_ms, "kernels": kernels,
-                       "tail_wait_ms_per_frame": (tail_wait["ms_per_frame"] if tail_wait else 0.0)},
+                       "tail_wait_ms_per_frame": (tail_wait["ms_per_frame"] if tail_wait else 0.0),
+                       "strong_4k": strong_4k, "strip_image_equal": strip_check},
             "e2e": {"value": 1000.0 * args.steps / e2e_ms * equiv, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 352, "d2h_bytes_per_step": strip_bytes},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom] / lpf, "kernel_ms": kernels[dom]["ms_per_frame"] / lpf,
-                         "launches_per_frame": lpf,
-                         "nodes_per_ray": c.nodeVisits / max(rays, 1), "tris_per_ray": c.triTests / max(rays, 1),
-                         "note": "VeachAjar's BVH + triangles (23 MB) are L2-resident: the traversal kernels are instruction-issue / "
-                                 "latency-bound, not HBM-bound (profiles/); the fraction is reported against the HBM copy peak as the contract asks"},
+            "roofline": roofline,
             "clocks": clock_info,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(scene)
         print(json.dumps(line), flush=True)
-
-    barrier()   # neighbours may still be storing into this rank's halo rows
-    if link:
-        if link.error():
-            print(f"[rank {rank}] WARNING: a device-side strip hand-over timed out", file=sys.stderr)
-        link.close()
-    host.rh_renderer_destroy(r)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        if strip_check and not (strip_check["static_camera"] and strip_check["moving_camera"]):
+            print("bench.py: the image made by the strips differs from the uncut film (config.strip_image_equal)", file=sys.stderr)
+            rc = 3
+    if arm.dist:
+        arm.dist.barrier()
+        arm.dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 def main():
@@ -479,6 +649,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal strips (skip the cost calibration)")
+    ap.add_argument("--no-4k", action="store_true", help="skip the second timed region on the fixed 3840x2160 film (config.strong_4k)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the strips-vs-uncut-film image comparison")
     ap.add_argument("--film", default="", help="WxH: fixed film cut into N strips (strong scaling, e.g. 3840x2160 = config 4); "
                                                "default: N x 1920x1080 pixels (weak scaling)")
     args = ap.parse_args()

@@ -29,7 +29,8 @@ typedef enum RptStatus {
 	RPT_ERR_NO_DEVICE = -2,  /* no CUDA device: the library never falls back to the CPU */
 	RPT_ERR_CUDA = -3,       /* sticky CUDA error, see rpt_last_error */
 	RPT_ERR_OOM = -4,
-	RPT_ERR_UNSUPPORTED = -5
+	RPT_ERR_UNSUPPORTED = -5,
+	RPT_ERR_PEER = -6        /* a multi-GPU hand-over timed out on the device (sticky until the peers are disconnected) */
 } RptStatus;
 
 /* ---- data layouts (reference src/shader/layouts.glsl, host mirrors in the src headers) ------------------------- */
@@ -312,11 +313,16 @@ typedef struct RptPeerInfo {
 	uint8_t grisTempHandle[64];   /* cudaIpcMemHandle_t of the GRIS temp reservoir buffer */
 	uint8_t diTempHandle[64];     /* ... of the DI temp reservoir buffer */
 	uint8_t flagsHandle[64];      /* ... of the epoch flags */
+	uint8_t grisHandle[2][64];    /* ... of the two ping-pong buffers of the final GRIS / DI / GI reservoirs: the boundary rows of */
+	uint8_t diHandle[2][64];      /*     the spatial (GI: temporal) pass output are mirrored into the neighbours' halo rows, so that */
+	uint8_t giHandle[2][64];      /*     previous-frame lookups that cross a cut stay GPU-local and still find their history */
 	uint64_t grisTempPtr, diTempPtr, flagsPtr;   /* raw device pointers, used when pid matches */
+	uint64_t grisPtr[2], diPtr[2], giPtr[2];
 	uint64_t pid;
 	int32_t device;
 	uint32_t rowBegin, rowEnd, storeBegin, storeEnd;
-	uint32_t pad[3];
+	uint32_t cur;                 /* ping-pong phase at export time (both strips must flip in lock step from here on) */
+	uint32_t pad[2];
 } RptPeerInfo;
 int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out);
 /* up = the strip above (smaller rows), down = the strip below; NULL at the film edge */
@@ -324,7 +330,31 @@ int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const RptPeerInf
 /* drop the mappings of the neighbours' buffers again (every rank calls this, then a barrier, before any strip is
  * destroyed or re-partitioned); also done by rpt_frame_destroy */
 int rpt_frame_disconnect_peers(RptFrame* f);
-int rpt_frame_peer_error(RptFrame* f);   /* non-zero if a device-side hand-over wait timed out */
+/* non-zero if a device-side hand-over wait timed out (a neighbour died or was not driven in lock step).  The condition is
+ * sticky: from then on every pass of this frame fails with RPT_ERR_PEER until the peers are disconnected. */
+int rpt_frame_peer_error(RptFrame* f);
+/* 1 when a connected neighbour lives in this process (its passes are enqueued by the same host thread): such strips must be
+ * driven stage by stage — every strip's temporal pass before any strip's spatial pass (rh_draw_strips does) */
+int rpt_frame_peers_in_process(const RptFrame* f);
+
+/* ---- final image gather (new; SURVEY.md §8(e) step 4, "rpt_gather_output" of §8(b)) -----------------------------
+ * The root strip allocates one full-film RGBA8 image; every strip (the root included) connects to it, after which
+ * rpt_postprocess stores its rows straight into that image through NVLink peer memory (fused post-process + gather: no
+ * staging copy, no collective) and raises an arrival flag.  rpt_gather_output on the root waits on the device for all
+ * strips of the current frame, copies the film to the host and releases the image for the next frame.  Once connected,
+ * the root must gather every frame (the strips wait for the release before they overwrite the image). */
+typedef struct RptGatherInfo {
+	uint8_t imageHandle[64];      /* cudaIpcMemHandle_t of the film image on the root's GPU */
+	uint8_t flagsHandle[64];      /* ... of the arrival / release flags */
+	uint64_t imagePtr, flagsPtr;  /* raw device pointers, used when pid matches */
+	uint64_t pid;
+	int32_t device;
+	uint32_t width, height, numStrips;
+} RptGatherInfo;
+int rpt_frame_gather_create(RptFrame* root, uint32_t numStrips, RptGatherInfo* out);
+int rpt_frame_gather_connect(RptFrame* f, const RptGatherInfo* root, uint32_t stripIndex);
+int rpt_frame_gather_disconnect(RptFrame* f);   /* every strip, then a barrier, before the root frame is destroyed */
+int rpt_gather_output(RptFrame* root, uint8_t* rgba8FullFilm);   /* width*height*4 bytes on the host; implicit sync */
 
 /* ---- ray queries exposed directly (new; closest-hit primitive-ID parity, traversal microbench) -------- */
 /* rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} floats on the HOST; out: n RptIntersection on the host */
@@ -340,6 +370,12 @@ int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t 
 /* queue sizes of the last wavefront path-tracing pass (new; diagnostics): out64[4*b + 0] = extension rays traced
  * for bounce b, out64[4*b + 1] = shadow rays of bounce b; implicit sync */
 int rpt_wavefront_counters(RptFrame* f, uint32_t* out64);
+
+/* memory-system microbenchmark (new): all SMs read a buffer of `bytes` bytes `iterations` times with 16-byte
+ * loads -> GB/s (a buffer that fits B200's 126 MB L2 gives the L2 bandwidth, the roof of the traversal kernels on an L2-resident
+ * scene; a multi-GB one the HBM read bandwidth), and one thread chases pointers through it -> ns per dependent load.
+ * Either output may be NULL. */
+int rpt_membench(RptCtx* ctx, size_t bytes, int iterations, float* streamGBs, float* chaseNs);
 
 int rpt_counters_enable(RptCtx* ctx, int on);
 int rpt_counters_reset(RptCtx* ctx);

@@ -64,10 +64,19 @@ void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* use
 /* push the scene's object instances to the device and rebuild the acceleration structure (rpt_scene_update_instances) */
 int rh_renderer_update_instances(RhRenderer* r, const RhScene* s);
 int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out);   /* 0 ok, -1 error */
+/* One frame on all strips of a film that live in this process (connected with rpt_frame_connect_peers): stage by stage —
+ * every strip's G-buffer / candidate / temporal passes first, then every strip's spatial pass, post-process and flip — so that
+ * each device-side hand-over wait finds its signal already enqueued.  rh_renderer_draw_frame refuses such strips.
+ * rgba8Outs: NULL, or one pointer (possibly NULL) per strip. */
+int rh_draw_strips(RhRenderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs);
 RptFrame* rh_renderer_frame(RhRenderer* r);
 RptScene* rh_renderer_scene(RhRenderer* r);
 RptCtx* rh_renderer_ctx(RhRenderer* r);
 
+/* canonical text dump of the element tree the host's XML reader sees ("<depth> <name> <attr>=<value> ...\n"); returns the bytes
+ * needed including the terminator (0 on error) and writes at most `capacity` bytes.  Test aid: compared with the reference's
+ * parser (pugixml) by tests/test_cpu_ref_pins.py */
+size_t rh_xml_dump(const char* path, char* out, size_t capacity);
 int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
 /* Texture decoding of the scene front-end: zvk::HostImage::createFromFile(path, Int8, filter, 4) (reference src/Resource.cpp:26,
    stb_image underneath).  PNG, JPEG (baseline and progressive) or binary PPM -> width x height RGBA8, released with

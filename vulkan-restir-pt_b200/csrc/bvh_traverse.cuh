@@ -81,14 +81,28 @@ RT_DEV bool rayIsDegenerate(float3 o, float tmin, float3 d, float tmax) {
 	return !(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f);
 }
 
+RT_DEV float fastRcp(float x) {
+	float y;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+
 RT_DEV TravRay makeTravRay(float3 o, float tmin, float3 d) {
 	TravRay r;
 	r.o = o; r.d = d; r.tmin = tmin;
 	// reciprocal direction; components too close to zero are pushed away from it so 1/d stays finite
 	const float tiny = 1e-20f;
+#ifdef RT_FAST_RCP
+	// the reciprocal direction only feeds the conservative box tests (never the triangle test): MUFU.RCP's 1 ulp is inside the
+	// slab padding of nodeStep (1e-6 relative against ~3.6e-7 of accumulated rounding), and saves three IEEE divisions per ray
+	r.idx = fastRcp(abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+	r.idy = fastRcp(abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+	r.idz = fastRcp(abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+#else
 	r.idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
 	r.idy = 1.0f / (abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
 	r.idz = 1.0f / (abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+#endif
 	r.octinv = 7u ^ ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
 	return r;
 }
@@ -159,22 +173,26 @@ struct TriHit {
 	uint32_t instanceIdx, triangleIdx, flat;
 };
 
-// Möller–Trumbore in the fixed operation order of the numeric contract; accepted iff tmin < t < tmax
-RT_DEV bool triTest(const SceneView& s, const TravRay& r, uint32_t triIndex, float tmax, TriHit& h) {
+// Möller–Trumbore in the fixed operation order of the numeric contract; accepted iff tmin < t < tmax.
+// (o, d, tmin) given directly: the warp-cooperative triangle rounds of trace_queue.cu test OTHER lanes' rays.
+RT_DEV bool triTestRay(const SceneView& s, float3 o, float3 d, float tmin, uint32_t triIndex, float tmax, TriHit& h) {
 	const float4* tp = reinterpret_cast<const float4*>(s.tris + triIndex);
 	const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
 	const float3 v0 = f3(t0), e1 = f3(t1), e2 = f3(t2);
-	const float3 p = cross(r.d, e2);
+	const float3 p = cross(d, e2);
 	const float det = dot(e1, p);
 	const float inv = 1.0f / det;
-	const float3 sv = r.o - v0;
+	const float3 sv = o - v0;
 	const float u = dot(sv, p) * inv;
 	const float3 q = cross(sv, e1);
-	const float v = dot(r.d, q) * inv;
+	const float v = dot(d, q) * inv;
 	const float t = dot(e2, q) * inv;
 	h.t = t; h.u = u; h.v = v;
 	h.instanceIdx = __float_as_uint(t0.w); h.triangleIdx = __float_as_uint(t1.w); h.flat = __float_as_uint(t2.w);
-	return u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > r.tmin && t < tmax;
+	return u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > tmin && t < tmax;
+}
+RT_DEV bool triTest(const SceneView& s, const TravRay& r, uint32_t triIndex, float tmax, TriHit& h) {
+	return triTestRay(s, r.o, r.d, r.tmin, triIndex, tmax, h);
 }
 
 // Running result of one ray (closest hit with the order-independent tie rule, any hit, or candidate count)

@@ -22,6 +22,8 @@ struct RptCtx {
 	cudaStream_t stream = nullptr;         // scene builds and raw ray queries
 	unsigned long long* counters = nullptr;
 	bool countersOn = false;
+	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
+	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false;
 };
 
 struct RptScene {
@@ -60,9 +62,24 @@ struct RptFrame {
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
+		RptGRISReservoir* gris[2] = { nullptr, nullptr };   // the neighbour's ping-pong buffers of final reservoirs,
+		RptDIReservoir* di[2] = { nullptr, nullptr };       // indexed like OUR `cur` (the phase difference at connect
+		RptGIReservoir* gi[2] = { nullptr, nullptr };       // time is folded in)
 		uint32_t storeBegin = 0;
 	} up, down;
-	uint32_t grisEpoch = 0, diEpoch = 0;
+	uint32_t grisEpoch = 0, diEpoch = 0, giEpoch = 0;
+	uint32_t* hostError = nullptr;             // mapped pinned word: a device-side wait timed out (sticky)
+	uint32_t* hostErrorDev = nullptr;          // its device address
+	// final image gather (rpt_frame_gather_*): the film image + flags on the root strip's GPU
+	struct Gather {
+		bool connected = false, ipc = false, root = false;
+		uchar4* image = nullptr; uint32_t* flags = nullptr;
+		uint32_t strip = 0, numStrips = 0;
+		uint32_t epoch = 0;                    // post-process passes since the connection (strip side)
+		uint32_t gathered = 0;                 // rpt_gather_output calls since the creation (root side)
+	} gather;
+	uchar4* gatherImageOwned = nullptr;        // root: the allocation behind gather.image
+	uint32_t* gatherFlagsOwned = nullptr;
 
 	// per-pass timing
 	struct Pending { int pass; cudaEvent_t a, b; bool poolB; };
@@ -154,6 +171,9 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	CU(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
 	CU(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
+	ctx->traceOneStream = getenv("RPT_TRACE_ONE_STREAM") != nullptr;
+	ctx->wavefrontTail = getenv("RPT_WAVEFRONT_TAIL") != nullptr;
+	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
 	*out = ctx;
 	return RPT_OK;
 }
@@ -385,6 +405,9 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	e = cudaMalloc(&f->flags, PeerFlagCount * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(f->flags, 0, PeerFlagCount * sizeof(uint32_t));
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc peer flags"); }
+	if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&f->hostError), sizeof(uint32_t), cudaHostAllocMapped);
+	if (e == cudaSuccess) { *f->hostError = 0u; e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->hostErrorDev), f->hostError, 0); }
+	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaHostAlloc peer error word"); }
 	e = cudaMalloc(&f->work, WorkCounterCount * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(f->work, 0, WorkCounterCount * sizeof(uint32_t));
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc work counters"); }
@@ -419,9 +442,21 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 
 static void disconnectPeers(RptFrame* f) {
 	for (RptFrame::Peer* p : { &f->up, &f->down }) {
-		if (p->connected && p->ipc) { cudaIpcCloseMemHandle(p->grisTemp); cudaIpcCloseMemHandle(p->diTemp); cudaIpcCloseMemHandle(p->flags); }
+		if (p->connected && p->ipc) {
+			for (void* q : { (void*)p->grisTemp, (void*)p->diTemp, (void*)p->flags, (void*)p->gris[0], (void*)p->gris[1],
+			                 (void*)p->di[0], (void*)p->di[1], (void*)p->gi[0], (void*)p->gi[1] })
+				if (q) cudaIpcCloseMemHandle(q);
+		}
 		*p = RptFrame::Peer{};
 	}
+	// a timed-out hand-over is forgiven with the connection that caused it
+	if (f->hostError) *f->hostError = 0u;
+	if (f->flags) cudaMemset(f->flags, 0, PeerFlagCount * sizeof(uint32_t));
+	f->grisEpoch = f->diEpoch = f->giEpoch = 0;
+}
+static void disconnectGather(RptFrame* f) {
+	if (f->gather.connected && f->gather.ipc) { cudaIpcCloseMemHandle(f->gather.image); cudaIpcCloseMemHandle(f->gather.flags); }
+	f->gather = RptFrame::Gather{};
 }
 
 RPT_API void rpt_frame_destroy(RptFrame* f) {
@@ -433,6 +468,10 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->tailDone) cudaEventDestroy(f->tailDone);
 	if (f->tailStream) cudaStreamDestroy(f->tailStream);
 	disconnectPeers(f);
+	disconnectGather(f);
+	if (f->gatherImageOwned) cudaFree(f->gatherImageOwned);
+	if (f->gatherFlagsOwned) cudaFree(f->gatherFlagsOwned);
+	if (f->hostError) cudaFreeHost(f->hostError);
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
@@ -487,6 +526,15 @@ static FrameView makeView(RptFrame* f) {
 	v.peerGrisDown = f->down.connected ? f->down.grisTemp : nullptr;
 	v.peerDiDown = f->down.connected ? f->down.diTemp : nullptr;
 	v.peerDownStoreBegin = f->down.storeBegin;
+	// the neighbours' final-reservoir buffers of this frame, and the rows whose previous-frame state is therefore valid here:
+	// a connected side contributes its halo rows except the outermost one (the bilinear G-buffer tap of a lookup in row y also
+	// reads row y-1 or y+1; at a film edge the wrap rows are stored, see depthNormalRow)
+	v.peerGrisThisUp = f->up.connected ? f->up.gris[c] : nullptr;     v.peerGrisThisDown = f->down.connected ? f->down.gris[c] : nullptr;
+	v.peerDiThisUp = f->up.connected ? f->up.di[c] : nullptr;         v.peerDiThisDown = f->down.connected ? f->down.di[c] : nullptr;
+	v.peerGiThisUp = f->up.connected ? f->up.gi[c] : nullptr;         v.peerGiThisDown = f->down.connected ? f->down.gi[c] : nullptr;
+	v.prevRowBegin = f->up.connected ? (f->storeBegin == 0 ? 0 : f->storeBegin + 1) : f->rowBegin;
+	v.prevRowEnd = f->down.connected ? (f->storeEnd == f->height ? f->height : f->storeEnd - 1) : f->rowEnd;
+	v.gatherImage = f->gather.connected ? f->gather.image : nullptr;
 	return v;
 }
 
@@ -499,6 +547,7 @@ static SceneView sceneView(const RptScene* s) {
 #define PASS_PROLOGUE(name) \
 	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, name ": NULL argument"); \
 	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, name ": frame and scene belong to different contexts"); \
+	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, name ": a multi-GPU hand-over of an earlier pass timed out on the device (a neighbouring strip died or was not driven in lock step); disconnect the peers to recover"); \
 	CU(f->ctx, cudaSetDevice(f->ctx->device)); \
 	joinTail(f);
 #define PASS_EPILOGUE(name) \
@@ -515,52 +564,67 @@ SIMPLE_PASS(rpt_gbuffer, RPT_PASS_GBUFFER, launchGBuffer)
 SIMPLE_PASS(rpt_di_naive, RPT_PASS_DI_NAIVE, launchDINaive)
 SIMPLE_PASS(rpt_di_naive_rt, RPT_PASS_DI_NAIVE, launchDINaiveRT)
 SIMPLE_PASS(rpt_gi_naive, RPT_PASS_GI_NAIVE, launchGINaive)
+static void peerBefore(RptFrame* f, int h);
+static void peerAfter(RptFrame* f, int h);
+enum PeerHook { HookNone, HookGrisTemporal, HookGrisSpatial, HookDiTemporal, HookDiSpatial, HookGi };
 RPT_API int rpt_gi_restir(RptFrame* f, const RptScene* s) {
 	PASS_PROLOGUE("rpt_gi_restir")
+	peerBefore(f, HookGi);
 	{
 		PassTimer timer(f, RPT_PASS_GI_RESTIR);
-		const bool overlap = getenv("RPT_TRACE_ONE_STREAM") == nullptr;   // A/B switch
+		const bool overlap = !f->ctx->traceOneStream;   // A/B switch
 		launchGIReSTIR(makeView(f), sceneView(s), f->stream, overlap ? f->tailStream : nullptr, f->tailFork, f->tailDone);
 	}
+	peerAfter(f, HookGi);
 	PASS_EPILOGUE("rpt_gi_restir")
 }
 SIMPLE_PASS(rpt_visualize_as, RPT_PASS_VISUALIZE_AS, launchVisualizeAS)
 
 // hand-over hooks around the temporal / spatial passes of a striped frame (no-ops without connected peers)
-enum PeerHook { HookNone, HookGrisTemporal, HookGrisSpatial, HookDiTemporal, HookDiSpatial };
-static void peerBefore(RptFrame* f, PeerHook h) {
+static void peerBefore(RptFrame* f, int h) {
 	if (!f->up.connected && !f->down.connected) return;
 	uint32_t* err = f->flags + PeerError;
 	const uint32_t* fromUp = f->up.connected ? f->flags : nullptr;
 	const uint32_t* fromDown = f->down.connected ? f->flags : nullptr;
+	auto wait = [&](int upSlot, int downSlot, uint32_t epoch) {
+		launchPeerWait(fromUp ? fromUp + upSlot : nullptr, fromDown ? fromDown + downSlot : nullptr, epoch, err, f->hostErrorDev, f->stream);
+	};
 	switch (h) {
-	case HookGrisTemporal:   // neighbours must have finished reading the halo rows written last frame
-		f->grisEpoch++;
-		launchPeerWait(fromUp ? fromUp + GrisSpatialFromUp : nullptr, fromDown ? fromDown + GrisSpatialFromDown : nullptr, f->grisEpoch - 1, err, f->stream);
+	case HookGrisTemporal:   // neighbours must have finished last frame's spatial pass: they no longer read the halo rows the temporal
+		f->grisEpoch++;      // pass is about to overwrite, and the mirrored rows of their final reservoirs have landed in ours
+		wait(GrisSpatialFromUp, GrisSpatialFromDown, f->grisEpoch - 1);
 		break;
 	case HookGrisSpatial:    // neighbours' boundary rows of this frame must have landed in our halo rows
-		launchPeerWait(fromUp ? fromUp + GrisTemporalFromUp : nullptr, fromDown ? fromDown + GrisTemporalFromDown : nullptr, f->grisEpoch, err, f->stream);
+		wait(GrisTemporalFromUp, GrisTemporalFromDown, f->grisEpoch);
 		break;
 	case HookDiTemporal:
 		f->diEpoch++;
-		launchPeerWait(fromUp ? fromUp + DiSpatialFromUp : nullptr, fromDown ? fromDown + DiSpatialFromDown : nullptr, f->diEpoch - 1, err, f->stream);
+		wait(DiSpatialFromUp, DiSpatialFromDown, f->diEpoch - 1);
 		break;
 	case HookDiSpatial:
-		launchPeerWait(fromUp ? fromUp + DiTemporalFromUp : nullptr, fromDown ? fromDown + DiTemporalFromDown : nullptr, f->diEpoch, err, f->stream);
+		wait(DiTemporalFromUp, DiTemporalFromDown, f->diEpoch);
+		break;
+	case HookGi:             // one pass per frame: the neighbours' previous frame must be complete — its mirrored rows are what this
+		f->giEpoch++;        // pass reads as history, and this pass mirrors into rows the neighbours read as history last frame
+		wait(GiFromUp, GiFromDown, f->giEpoch - 1);
 		break;
 	default: break;
 	}
 }
-static void peerAfter(RptFrame* f, PeerHook h) {
+static void peerAfter(RptFrame* f, int h) {
 	if (!f->up.connected && !f->down.connected) return;
 	// we are the "down" neighbour of the strip above and the "up" neighbour of the strip below
 	uint32_t* toUp = f->up.connected ? f->up.flags : nullptr;
 	uint32_t* toDown = f->down.connected ? f->down.flags : nullptr;
+	auto signal = [&](int slotInUp, int slotInDown, uint32_t epoch) {
+		launchPeerSignal(toUp ? toUp + slotInUp : nullptr, toDown ? toDown + slotInDown : nullptr, epoch, f->stream);
+	};
 	switch (h) {
-	case HookGrisTemporal: launchPeerSignal(toUp ? toUp + GrisTemporalFromDown : nullptr, toDown ? toDown + GrisTemporalFromUp : nullptr, f->grisEpoch, f->stream); break;
-	case HookGrisSpatial: launchPeerSignal(toUp ? toUp + GrisSpatialFromDown : nullptr, toDown ? toDown + GrisSpatialFromUp : nullptr, f->grisEpoch, f->stream); break;
-	case HookDiTemporal: launchPeerSignal(toUp ? toUp + DiTemporalFromDown : nullptr, toDown ? toDown + DiTemporalFromUp : nullptr, f->diEpoch, f->stream); break;
-	case HookDiSpatial: launchPeerSignal(toUp ? toUp + DiSpatialFromDown : nullptr, toDown ? toDown + DiSpatialFromUp : nullptr, f->diEpoch, f->stream); break;
+	case HookGrisTemporal: signal(GrisTemporalFromDown, GrisTemporalFromUp, f->grisEpoch); break;
+	case HookGrisSpatial: signal(GrisSpatialFromDown, GrisSpatialFromUp, f->grisEpoch); break;
+	case HookDiTemporal: signal(DiTemporalFromDown, DiTemporalFromUp, f->diEpoch); break;
+	case HookDiSpatial: signal(DiSpatialFromDown, DiSpatialFromUp, f->diEpoch); break;
+	case HookGi: signal(GiFromDown, GiFromUp, f->giEpoch); break;
 	default: break;
 	}
 }
@@ -589,7 +653,7 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_PATHTRACE);
 		FrameKernelClock clock(f);
-		const bool overlap = getenv("RPT_TRACE_ONE_STREAM") == nullptr;   // A/B switch (profiles/r1_18_*)
+		const bool overlap = !f->ctx->traceOneStream;   // A/B switch (profiles/r1_18_*)
 		launchGRISPathTraceBounces(view, scene, *st, 0, WavefrontTailStart - 1, f->stream, f->timing ? &clock : nullptr,
 		                           overlap ? f->tailStream : nullptr, f->tailFork, f->tailDone);
 	}
@@ -597,7 +661,7 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	if (f->timing) { t0 = takeEvent(f); t1 = takeEvent(f); cudaEventRecord(t0, f->tailStream); }
-	if (getenv("RPT_WAVEFRONT_TAIL")) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
+	if (f->ctx->wavefrontTail) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
 	else launchGRISPathTraceTail(view, scene, *st, f->tailStream);
 	if (f->timing) { cudaEventRecord(t1, f->tailStream); f->pending.push_back({ RPT_PASS_COUNT + RPT_KERNEL_GRIS_TAIL, t0, t1, true }); }
 	CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
@@ -611,6 +675,7 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_gris_temporal: NULL argument");
 	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: frame and scene belong to different contexts");
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: NULL settings");
+	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gris_temporal: a multi-GPU hand-over of an earlier pass timed out on the device; disconnect the peers to recover");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	peerBefore(f, HookGrisTemporal);
 	{
@@ -638,7 +703,7 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
 		FrameKernelClock clock(f);
 		joinTail(f);   // (the tail stream and its events are free again from here)
-		const bool side = getenv("RPT_SPATIAL_ONE_STREAM") == nullptr;   // A/B switch
+		const bool side = !f->ctx->spatialOneStream;   // A/B switch
 		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
 		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone);
 	}
@@ -650,7 +715,12 @@ RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgb
 	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
+	if (f->gather.connected) {   // the film image on the root must have been released by the gather of the previous frame
+		f->gather.epoch++;
+		launchPeerWait(f->gather.flags + GatherReleaseFlag, nullptr, f->gather.epoch - 1, f->flags + PeerError, f->hostErrorDev, f->stream);
+	}
 	{ PassTimer timer(f, RPT_PASS_POSTPROCESS); launchPostProcess(makeView(f), *st, f->rgba8, f->stream); }
+	if (f->gather.connected) launchPeerSignal(f->gather.flags + GatherArrivalFlag0 + f->gather.strip, nullptr, f->gather.epoch, f->stream);
 	CU(f->ctx, cudaGetLastError());
 	if (rgba8Out) {
 		CU(f->ctx, cudaMemcpyAsync(rgba8Out, f->rgba8, size_t(f->width) * (f->rowEnd - f->rowBegin) * 4, cudaMemcpyDeviceToHost, f->stream));
@@ -723,21 +793,32 @@ RPT_API int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out) {
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	std::memset(out, 0, sizeof(*out));
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->grisTempHandle), f->grisTemp));
-	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->diTempHandle), f->diTemp));
-	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->flagsHandle), f->flags));
+	auto handle = [&](uint8_t* dst, void* p) { return cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(dst), p); };
+	CU(f->ctx, handle(out->grisTempHandle, f->grisTemp));
+	CU(f->ctx, handle(out->diTempHandle, f->diTemp));
+	CU(f->ctx, handle(out->flagsHandle, f->flags));
+	for (int i = 0; i < 2; i++) {
+		CU(f->ctx, handle(out->grisHandle[i], f->gris[i]));
+		CU(f->ctx, handle(out->diHandle[i], f->di[i]));
+		CU(f->ctx, handle(out->giHandle[i], f->gi[i]));
+		out->grisPtr[i] = reinterpret_cast<uint64_t>(f->gris[i]);
+		out->diPtr[i] = reinterpret_cast<uint64_t>(f->di[i]);
+		out->giPtr[i] = reinterpret_cast<uint64_t>(f->gi[i]);
+	}
 	out->grisTempPtr = reinterpret_cast<uint64_t>(f->grisTemp);
 	out->diTempPtr = reinterpret_cast<uint64_t>(f->diTemp);
 	out->flagsPtr = reinterpret_cast<uint64_t>(f->flags);
 	out->pid = uint64_t(getpid());
 	out->device = f->ctx->device;
 	out->rowBegin = f->rowBegin; out->rowEnd = f->rowEnd; out->storeBegin = f->storeBegin; out->storeEnd = f->storeEnd;
+	out->cur = f->cur;
 	return RPT_OK;
 }
 
 static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
 	p = RptFrame::Peer{};
 	if (!info) return RPT_OK;
+	void* q[9] = {};
 	if (info->pid == uint64_t(getpid())) {
 		// same process: plain pointers, peer access enabled when the neighbour lives on another device
 		if (info->device != f->ctx->device) {
@@ -748,31 +829,54 @@ static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
 			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(f->ctx, e, "cudaDeviceEnablePeerAccess");
 			cudaGetLastError();
 		}
-		p.grisTemp = reinterpret_cast<RptGRISReservoir*>(info->grisTempPtr);
-		p.diTemp = reinterpret_cast<RptDIReservoir*>(info->diTempPtr);
-		p.flags = reinterpret_cast<uint32_t*>(info->flagsPtr);
+		const uint64_t raw[9] = { info->grisTempPtr, info->diTempPtr, info->flagsPtr, info->grisPtr[0], info->grisPtr[1],
+		                          info->diPtr[0], info->diPtr[1], info->giPtr[0], info->giPtr[1] };
+		for (int i = 0; i < 9; i++) q[i] = reinterpret_cast<void*>(raw[i]);
 	}
 	else {
-		void *a = nullptr, *b = nullptr, *c = nullptr;
-		CU(f->ctx, cudaIpcOpenMemHandle(&a, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->grisTempHandle), cudaIpcMemLazyEnablePeerAccess));
-		CU(f->ctx, cudaIpcOpenMemHandle(&b, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->diTempHandle), cudaIpcMemLazyEnablePeerAccess));
-		CU(f->ctx, cudaIpcOpenMemHandle(&c, *reinterpret_cast<const cudaIpcMemHandle_t*>(info->flagsHandle), cudaIpcMemLazyEnablePeerAccess));
-		p.grisTemp = static_cast<RptGRISReservoir*>(a); p.diTemp = static_cast<RptDIReservoir*>(b); p.flags = static_cast<uint32_t*>(c);
+		const uint8_t* h[9] = { info->grisTempHandle, info->diTempHandle, info->flagsHandle, info->grisHandle[0], info->grisHandle[1],
+		                        info->diHandle[0], info->diHandle[1], info->giHandle[0], info->giHandle[1] };
+		for (int i = 0; i < 9; i++) {
+			cudaError_t e = cudaIpcOpenMemHandle(&q[i], *reinterpret_cast<const cudaIpcMemHandle_t*>(h[i]), cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) {
+				for (int k = 0; k < i; k++) cudaIpcCloseMemHandle(q[k]);
+				return cudaFail(f->ctx, e, "cudaIpcOpenMemHandle");
+			}
+		}
 		p.ipc = true;
+	}
+	p.grisTemp = static_cast<RptGRISReservoir*>(q[0]); p.diTemp = static_cast<RptDIReservoir*>(q[1]); p.flags = static_cast<uint32_t*>(q[2]);
+	// index the neighbour's ping-pong buffers by OUR phase: both frames flip once per frame from here on
+	const uint32_t phase = (info->cur ^ f->cur) & 1u;
+	for (uint32_t i = 0; i < 2; i++) {
+		p.gris[i] = static_cast<RptGRISReservoir*>(q[3 + (i ^ phase)]);
+		p.di[i] = static_cast<RptDIReservoir*>(q[5 + (i ^ phase)]);
+		p.gi[i] = static_cast<RptGIReservoir*>(q[7 + (i ^ phase)]);
 	}
 	p.storeBegin = info->storeBegin;
 	p.connected = true;
 	return RPT_OK;
 }
 
+// All strips of a film connect between the same two frames, and a barrier (or, in one process, program order) separates the
+// connection from the first pass: the epoch counters and flag words of the hand-over restart at zero here on every strip, so
+// frames that rendered different numbers of frames before (re-partitioning, a replaced GPU) start in step again.
 RPT_API int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const RptPeerInfo* down) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_connect_peers: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	if (up && (up->rowEnd != f->rowBegin || up->storeEnd < f->rowBegin + f->halo)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: `up` is not the strip directly above with a matching halo");
 	if (down && (down->rowBegin != f->rowEnd || down->storeBegin + f->halo > f->rowEnd)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: `down` is not the strip directly below with a matching halo");
+	// a neighbour fills our halo rows with ITS rows only: it must own all of them (or reach the film edge)
+	if (up && up->rowBegin != 0 && up->rowEnd - up->rowBegin < f->halo) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: the strip above is shorter than the halo");
+	if (down && down->rowEnd != f->height && down->rowEnd - down->rowBegin < f->halo) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: the strip below is shorter than the halo");
+	joinTail(f);
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	disconnectPeers(f);   // also: epochs, flag words and the sticky error back to zero
 	int r = connectOne(f, f->up, up);
 	if (r != RPT_OK) return r;
-	return connectOne(f, f->down, down);
+	r = connectOne(f, f->down, down);
+	if (r != RPT_OK) disconnectPeers(f);
+	return r;
 }
 
 RPT_API int rpt_frame_disconnect_peers(RptFrame* f) {
@@ -781,6 +885,92 @@ RPT_API int rpt_frame_disconnect_peers(RptFrame* f) {
 	joinTail(f);
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	disconnectPeers(f);
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_peers_in_process(const RptFrame* f) {
+	if (!f) return 0;
+	return ((f->up.connected && !f->up.ipc) || (f->down.connected && !f->down.ipc)) ? 1 : 0;
+}
+
+// ---- final image gather ------------------------------------------------------------------------------------------
+RPT_API int rpt_frame_gather_create(RptFrame* f, uint32_t numStrips, RptGatherInfo* out) {
+	if (!f || !out || numStrips == 0 || numStrips > uint32_t(GatherMaxStrips)) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_gather_create: bad argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	if (f->gatherImageOwned) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_gather_create: this frame already is a gather root");
+	const size_t bytes = size_t(f->width) * f->height * 4;
+	CU(f->ctx, cudaMalloc(&f->gatherImageOwned, bytes));
+	CU(f->ctx, cudaMemset(f->gatherImageOwned, 0, bytes));
+	CU(f->ctx, cudaMalloc(&f->gatherFlagsOwned, 64 * sizeof(uint32_t)));
+	CU(f->ctx, cudaMemset(f->gatherFlagsOwned, 0, 64 * sizeof(uint32_t)));
+	std::memset(out, 0, sizeof(*out));
+	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->imageHandle), f->gatherImageOwned));
+	CU(f->ctx, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out->flagsHandle), f->gatherFlagsOwned));
+	out->imagePtr = reinterpret_cast<uint64_t>(f->gatherImageOwned);
+	out->flagsPtr = reinterpret_cast<uint64_t>(f->gatherFlagsOwned);
+	out->pid = uint64_t(getpid());
+	out->device = f->ctx->device;
+	out->width = f->width; out->height = f->height; out->numStrips = numStrips;
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_gather_connect(RptFrame* f, const RptGatherInfo* root, uint32_t stripIndex) {
+	if (!f || !root) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_gather_connect: NULL argument");
+	if (root->width != f->width || root->height != f->height || stripIndex >= root->numStrips) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_gather_connect: film size or strip index does not match the root");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	disconnectGather(f);
+	RptFrame::Gather g;
+	if (root->pid == uint64_t(getpid())) {
+		if (root->device != f->ctx->device) {
+			int can = 0;
+			CU(f->ctx, cudaDeviceCanAccessPeer(&can, f->ctx->device, root->device));
+			if (!can) return fail(f->ctx, RPT_ERR_UNSUPPORTED, "rpt_frame_gather_connect: no peer access to the root's device");
+			cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(f->ctx, e, "cudaDeviceEnablePeerAccess");
+			cudaGetLastError();
+		}
+		g.image = reinterpret_cast<uchar4*>(root->imagePtr);
+		g.flags = reinterpret_cast<uint32_t*>(root->flagsPtr);
+	}
+	else {
+		void *a = nullptr, *b = nullptr;
+		CU(f->ctx, cudaIpcOpenMemHandle(&a, *reinterpret_cast<const cudaIpcMemHandle_t*>(root->imageHandle), cudaIpcMemLazyEnablePeerAccess));
+		cudaError_t e = cudaIpcOpenMemHandle(&b, *reinterpret_cast<const cudaIpcMemHandle_t*>(root->flagsHandle), cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { cudaIpcCloseMemHandle(a); return cudaFail(f->ctx, e, "cudaIpcOpenMemHandle"); }
+		g.image = static_cast<uchar4*>(a); g.flags = static_cast<uint32_t*>(b);
+		g.ipc = true;
+	}
+	g.connected = true;
+	g.root = f->gatherImageOwned != nullptr && reinterpret_cast<uint64_t>(f->gatherImageOwned) == root->imagePtr && root->pid == uint64_t(getpid());
+	g.strip = stripIndex; g.numStrips = root->numStrips;
+	f->gather = g;
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_gather_disconnect(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_gather_disconnect: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	disconnectGather(f);
+	return RPT_OK;
+}
+
+// The root's side of the gather: wait (on the device) until every strip's rows of gather epoch k have arrived, copy the film to
+// the host, then release the image: the strips' next post-process passes wait for that release before they overwrite it.
+RPT_API int rpt_gather_output(RptFrame* f, uint8_t* rgba8FullFilm) {
+	if (!f || !rgba8FullFilm) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_gather_output: NULL argument");
+	if (!f->gatherImageOwned || !f->gather.connected) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gather_output: this frame is not a connected gather root");
+	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gather_output: a multi-GPU hand-over timed out on the device");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
+	const uint32_t epoch = ++f->gather.gathered;
+	launchPeerWaitMany(f->gatherFlagsOwned + GatherArrivalFlag0, f->gather.numStrips, epoch, f->flags + PeerError, f->hostErrorDev, f->stream);
+	CU(f->ctx, cudaMemcpyAsync(rgba8FullFilm, f->gatherImageOwned, size_t(f->width) * f->height * 4, cudaMemcpyDeviceToHost, f->stream));
+	launchPeerSignal(f->gatherFlagsOwned + GatherReleaseFlag, nullptr, epoch, f->stream);
+	CU(f->ctx, cudaGetLastError());
+	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	if (*reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gather_output: a strip's rows did not arrive within the time limit");
 	return RPT_OK;
 }
 
@@ -859,6 +1049,13 @@ RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
 	joinTail(f);
 	CU(f->ctx, cudaStreamSynchronize(f->stream));
 	CU(f->ctx, cudaMemcpy(out64, f->wf.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return RPT_OK;
+}
+
+RPT_API int rpt_membench(RptCtx* ctx, size_t bytes, int iterations, float* streamGBs, float* chaseNs) {
+	if (!ctx || iterations < 1 || (!streamGBs && !chaseNs)) return fail(ctx, RPT_ERR_INVALID, "rpt_membench: bad argument");
+	CU(ctx, cudaSetDevice(ctx->device));
+	CU(ctx, runMemBench(bytes, iterations, streamGBs, chaseNs, ctx->stream));
 	return RPT_OK;
 }
 

@@ -42,6 +42,10 @@ inline dim3 passGrid(uint32_t width, uint32_t rows) {
 	return dim3((width + PassBlockX - 1) / PassBlockX, (rows + PassBlockY - 1) / PassBlockY, 1);
 }
 
+// memory-system microbenchmarks (microbench.cu): bandwidth of `iterations` full reads of a `bytes` buffer by all SMs, and the
+// dependent-load latency of a pointer chase through it
+cudaError_t runMemBench(size_t bytes, int iterations, float* streamGBs, float* chaseNs, cudaStream_t st);
+
 // grid of a persistent kernel: every SM filled to the kernel's occupancy limit (148 SMs on B200)
 inline int persistentBlocks(const void* kernel, int blockSize) {
 	int dev = 0, sms = 0, perSm = 0;

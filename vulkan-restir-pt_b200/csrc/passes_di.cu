@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) diTemporalKernel(const
 	resv.resetIfInvalid();
 	storeDI(f.diTemp + idx, resv);
 	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
-	if (f.peerDiUp != nullptr && y < f.rowBegin + f.halo) storeDI(f.peerDiUp + (size_t(y - f.peerUpStoreBegin) * f.width + x), resv);
-	if (f.peerDiDown != nullptr && y + f.halo >= f.rowEnd) storeDI(f.peerDiDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
+	if (f.peerDiUp != nullptr && rowInUpHalo(f, y)) storeDI(f.peerDiUp + peerUpIndex(f, x, y), resv);
+	if (f.peerDiDown != nullptr && rowInDownHalo(f, y)) storeDI(f.peerDiDown + peerDownIndex(f, x, y), resv);
 }
 
 __global__ void __launch_bounds__(PassBlockX* PassBlockY) diSpatialKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptDISettings st) {
@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) diSpatialKernel(const 
 		diCap(resv, 40);
 		resv.resetIfInvalid();
 		storeDI(f.diThis + idx, resv);
+		// multi-GPU strips: the final reservoirs of the boundary rows are mirrored into the neighbours' halo rows (next frame's
+		// previous-frame lookups across a cut, as in passes_gris.cu spatialStore)
+		if (f.peerDiThisUp != nullptr && rowInUpHalo(f, y)) storeDI(f.peerDiThisUp + peerUpIndex(f, x, y), resv);
+		if (f.peerDiThisDown != nullptr && rowInDownHalo(f, y)) storeDI(f.peerDiThisDown + peerDownIndex(f, x, y), resv);
 
 		if (resv.valid() && resv.sampleValid()) {
 			Surface surf;

@@ -110,7 +110,11 @@ __global__ void __launch_bounds__(256) postProcessKernel(const __grid_constant__
 		v = v != v ? 0.0f : clamp_(v, 0.0f, 1.0f);
 		q[k] = uint32_t(floorf(v * 255.0f + 0.5f));
 	}
-	out[size_t(y - f.rowBegin) * f.width + x] = make_uchar4(uint8_t(q[0]), uint8_t(q[1]), uint8_t(q[2]), 255);
+	const uchar4 px = make_uchar4(uint8_t(q[0]), uint8_t(q[1]), uint8_t(q[2]), 255);
+	out[size_t(y - f.rowBegin) * f.width + x] = px;
+	// multi-GPU strips with a connected gather: the row also goes straight into the full-film image on the root strip's GPU
+	// (NVLink peer store, coalesced 128 B per warp) — the final gather of SURVEY.md §8(e) fused into the pass that makes the pixels
+	if (f.gatherImage != nullptr) f.gatherImage[size_t(y) * f.width + x] = px;
 }
 
 // raw ray queries for the parity tests / traversal microbenchmarks: rays[2i] = {o, tmin}, rays[2i+1] = {d, tmax}

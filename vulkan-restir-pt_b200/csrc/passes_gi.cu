@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(GIBlock) giBeginKernel(const __grid_constant__
 		float4 q2 = outResv[2];
 		q2.x = __uint_as_float(0u); q2.y = 0.0f; q2.z = 0.0f;
 		outResv[2] = q2;
+		if (f.peerGiThisUp != nullptr && rowInUpHalo(f, y)) reinterpret_cast<float4*>(f.peerGiThisUp + peerUpIndex(f, x, y))[2] = q2;
+		if (f.peerGiThisDown != nullptr && rowInDownHalo(f, y)) reinterpret_cast<float4*>(f.peerGiThisDown + peerDownIndex(f, x, y))[2] = q2;
 		accumulate(f.indirectOutput, f, x, y, f3(0.0f));
 		return;
 	}
@@ -297,6 +299,15 @@ __global__ void __launch_bounds__(GIBlock) giResolveKernel(const __grid_constant
 	}
 	float4* outResv = reinterpret_cast<float4*>(f.giThis + idx);
 	outResv[0] = resv.q0; outResv[1] = resv.q1; outResv[2] = resv.q2;
+	// multi-GPU strips: boundary rows mirrored into the neighbours' halo rows (next frame's previous-frame lookups across a cut)
+	if (f.peerGiThisUp != nullptr && rowInUpHalo(f, y)) {
+		float4* q = reinterpret_cast<float4*>(f.peerGiThisUp + peerUpIndex(f, x, y));
+		q[0] = resv.q0; q[1] = resv.q1; q[2] = resv.q2;
+	}
+	if (f.peerGiThisDown != nullptr && rowInDownHalo(f, y)) {
+		float4* q = reinterpret_cast<float4*>(f.peerGiThisDown + peerDownIndex(f, x, y));
+		q[0] = resv.q0; q[1] = resv.q1; q[2] = resv.q2;
+	}
 	recordPlane(f, 3)[o] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(needRay));
 	if (needRay) recordPlane(f, 4)[o] = make_float4(visibleRadiance.x, visibleRadiance.y, visibleRadiance.z, 0.f);
 }

@@ -858,8 +858,16 @@ RT_DEV void temporalStore(const FrameView& f, uint32_t x, uint32_t y, size_t idx
 	if (!resv.valid()) resv.reset();
 	storeGRIS(f.grisTemp + idx, resv);
 	// multi-GPU strips: boundary rows go straight into the neighbours' halo rows over NVLink peer memory
-	if (f.peerGrisUp != nullptr && y < f.rowBegin + f.halo) storeGRIS(f.peerGrisUp + (size_t(y - f.peerUpStoreBegin) * f.width + x), resv);
-	if (f.peerGrisDown != nullptr && y + f.halo >= f.rowEnd) storeGRIS(f.peerGrisDown + (size_t(y - f.peerDownStoreBegin) * f.width + x), resv);
+	if (f.peerGrisUp != nullptr && rowInUpHalo(f, y)) storeGRIS(f.peerGrisUp + peerUpIndex(f, x, y), resv);
+	if (f.peerGrisDown != nullptr && rowInDownHalo(f, y)) storeGRIS(f.peerGrisDown + peerDownIndex(f, x, y), resv);
+}
+
+// the spatial pass's output = next frame's "previous" reservoirs.  Boundary rows are mirrored into the neighbours' halo rows
+// of the same ping-pong buffer, so a reprojection that crosses a cut (camera motion) finds its history on this GPU
+RT_DEV void spatialStore(const FrameView& f, uint32_t x, uint32_t y, size_t idx, const GRISResv& resv) {
+	storeGRIS(f.grisThis + idx, resv);
+	if (f.peerGrisThisUp != nullptr && rowInUpHalo(f, y)) storeGRIS(f.peerGrisThisUp + peerUpIndex(f, x, y), resv);
+	if (f.peerGrisThisDown != nullptr && rowInDownHalo(f, y)) storeGRIS(f.peerGrisThisDown + peerDownIndex(f, x, y), resv);
 }
 
 // the sequential per-pixel form (gris_resample_temporal.glsl:11-83), used for the pixels of the path-tracing tail
@@ -981,7 +989,7 @@ RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGR
 			}
 		}
 		if (!resv.valid()) resv.reset();
-		storeGRIS(f.grisThis + idx, resv);
+		spatialStore(f, x, y, idx, resv);
 		radiance = spatialShade(s, st, p, dstPrimarySurf, resv);
 	}
 	accumulate(f.indirectOutput, f, x, y, radiance);
@@ -1084,7 +1092,7 @@ __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialMer
 			}
 		}
 		if (!resv.valid()) resv.reset();
-		storeGRIS(f.grisThis + idx, resv);
+		spatialStore(f, x, y, idx, resv);
 		if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid() && flagsRcVertexId(resv.flags()) != 1u) {
 			f.ru.shadeList[atomicAdd(f.ru.counters + 0, 1u)] = o;   // shading needs replay rays: grisSpatialShadeListKernel
 			return;

@@ -115,6 +115,13 @@ struct FrameView {
 	uint32_t peerUpStoreBegin, peerDownStoreBegin;
 	RptGRISReservoir* peerGrisUp;  RptGRISReservoir* peerGrisDown;
 	RptDIReservoir* peerDiUp;      RptDIReservoir* peerDiDown;
+	// ... and their final ("this") reservoir buffers of the current frame: the boundary rows of the spatial / GI pass output are
+	// mirrored into the neighbours' halo rows, so that next frame's previous-frame lookups near a cut find what a single GPU finds
+	RptGRISReservoir* peerGrisThisUp;  RptGRISReservoir* peerGrisThisDown;
+	RptDIReservoir* peerDiThisUp;      RptDIReservoir* peerDiThisDown;
+	RptGIReservoir* peerGiThisUp;      RptGIReservoir* peerGiThisDown;
+	uint32_t prevRowBegin, prevRowEnd;   // rows whose previous-frame reservoirs (and bilinear G-buffer taps) are valid on this GPU
+	uchar4* gatherImage;                 // full-film RGBA8 image on the root strip's GPU (peer memory), or nullptr
 	bool striped;                 // true when this frame is one strip of a larger film
 	uint32_t* work;               // work-queue heads of the persistent kernels (WorkCounterCount words)
 	WavefrontView wf;

@@ -418,9 +418,11 @@ RT_DEV Neighbor lookupSurface(const FrameView& f, bool previousFrame, float2 uv)
 	int px = int(uv.x * float(f.width)), py = int(uv.y * float(f.height));
 	if (px > int(f.width) - 1) px = int(f.width) - 1;
 	if (py > int(f.height) - 1) py = int(f.height) - 1;
-	// multi-GPU strips: previous-frame reservoirs exist for the owned rows only (temporal
-	// reuse stays GPU-local), current-frame ones for owned + halo rows; a lookup outside fails
-	if (previousFrame ? (py < int(f.rowBegin) || py >= int(f.rowEnd)) : (py < int(f.storeBegin) || py >= int(f.storeEnd))) return nb;
+	// multi-GPU strips: every lookup is GPU-local.  Current-frame reservoirs exist for owned + halo rows.
+	// Previous-frame ones exist for the owned rows, plus — when the neighbour is connected and mirrors the boundary rows of its
+	// final reservoirs into this GPU's halo rows — the halo rows whose bilinear taps stay inside the stored rows
+	// (prevRowBegin / prevRowEnd, set by the host).  A lookup outside fails.
+	if (previousFrame ? (py < int(f.prevRowBegin) || py >= int(f.prevRowEnd)) : (py < int(f.storeBegin) || py >= int(f.storeEnd))) return nb;
 	const float4 dn = fetchDepthNormalBilinear(f, previousFrame ? f.depthNormalPrev : f.depthNormal, uv);
 	nb.depth = dn.x;
 	if (nb.depth == 0.0f) return nb;
@@ -434,6 +436,13 @@ RT_DEV Neighbor lookupSurface(const FrameView& f, bool previousFrame, float2 uv)
 	nb.found = true;
 	return nb;
 }
+
+// multi-GPU strips: film rows of this strip that are halo rows of the strip above / below, and where they live in the
+// neighbour's storage (peer memory over NVLink; the neighbour's buffers have the same row-major layout from its storeBegin)
+RT_DEV bool rowInUpHalo(const FrameView& f, uint32_t y) { return y < f.rowBegin + f.halo; }
+RT_DEV bool rowInDownHalo(const FrameView& f, uint32_t y) { return y + f.halo >= f.rowEnd; }
+RT_DEV size_t peerUpIndex(const FrameView& f, uint32_t x, uint32_t y) { return size_t(y - f.peerUpStoreBegin) * f.width + x; }
+RT_DEV size_t peerDownIndex(const FrameView& f, uint32_t x, uint32_t y) { return size_t(y - f.peerDownStoreBegin) * f.width + x; }
 
 RT_DEV void accumulate(float4* __restrict__ img, const FrameView& f, uint32_t x, uint32_t y, float3 c) {
 	const float n = float(f.camera.frameIndex & 0x7fffffffu);

@@ -37,52 +37,84 @@ void Renderer::updateInstances(const Scene& scene) {
 }
 
 void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
-	// processGUI tail (src/Renderer.cpp:654-660): without accumulation the camera is re-updated every
-	// frame, which zeroes frameIndex so every frame is shown un-accumulated
-	if (!settings.accumulate) {
-		mCamera.update();
+	// Strips of one film that live in this process are enqueued by one host thread: a strip's spatial pass waits (on the device)
+	// for the neighbours' temporal passes, which must therefore be enqueued first — Renderer::drawStrips does that.
+	if (rpt_frame_peers_in_process(mFrame)) {
+		throw std::runtime_error("Renderer::drawFrame: this strip is connected to a neighbouring strip of the same process; "
+		                         "draw all strips of the film together with Renderer::drawStrips (rh_draw_strips)");
 	}
-	if (mClearNext) {
-		mCamera.setClearFlag();
-		mClearNext = false;
-	}
-	// memorySyncHostAndDevice (src/Renderer.cpp:358-368)
-	mCamera.data().seed = seed;
-	check(rpt_set_camera(mFrame, &mCamera.data(), &mPrevCamera.data()), "rpt_set_camera");
-	mPrevCamera = mCamera;
-	mCamera.nextFrame(seed);
+	drawStage(0, seed, nullptr);
+	drawStage(1, seed, rgba8Out);
+}
 
-	// recordRenderCommand (src/Renderer.cpp:400-503)
-	check(rpt_gbuffer(mFrame, mDeviceScene), "rpt_gbuffer");
+void Renderer::drawStrips(Renderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs) {
+	for (uint32_t i = 0; i < count; i++) strips[i]->drawStage(0, seed, nullptr);
+	for (uint32_t i = 0; i < count; i++) strips[i]->drawStage(1, seed, rgba8Outs ? rgba8Outs[i] : nullptr);
+}
+
+// stage 0: camera upload, G-buffer and everything up to and including the temporal passes (candidate generation, path tracing,
+//          temporal reuse, ReSTIR GI); stage 1: the spatial passes (they read the neighbours' temporal output), post-process, flip.
+// The direct and the indirect method write disjoint buffers, so running di_spatial after gris_temporal changes no result.
+void Renderer::drawStage(int stage, uint32_t seed, uint8_t* rgba8Out) {
+	if (stage == 0) {
+		// processGUI tail (src/Renderer.cpp:654-660): without accumulation the camera is re-updated every
+		// frame, which zeroes frameIndex so every frame is shown un-accumulated
+		if (!settings.accumulate) {
+			mCamera.update();
+		}
+		if (mClearNext) {
+			mCamera.setClearFlag();
+			mClearNext = false;
+		}
+		// memorySyncHostAndDevice (src/Renderer.cpp:358-368)
+		mCamera.data().seed = seed;
+		check(rpt_set_camera(mFrame, &mCamera.data(), &mPrevCamera.data()), "rpt_set_camera");
+		mPrevCamera = mCamera;
+		mCamera.nextFrame(seed);
+
+		// recordRenderCommand (src/Renderer.cpp:400-503)
+		check(rpt_gbuffer(mFrame, mDeviceScene), "rpt_gbuffer");
+	}
 
 	if (settings.directMethod == RayTracingMethod::Naive) {
-		if (settings.pipelineMode == 1) check(rpt_di_naive_rt(mFrame, mDeviceScene), "rpt_di_naive_rt");
-		else check(rpt_di_naive(mFrame, mDeviceScene), "rpt_di_naive");
+		if (stage == 0) {
+			if (settings.pipelineMode == 1) check(rpt_di_naive_rt(mFrame, mDeviceScene), "rpt_di_naive_rt");
+			else check(rpt_di_naive(mFrame, mDeviceScene), "rpt_di_naive");
+		}
 	}
 	else if (settings.directMethod == RayTracingMethod::ResampledDI) {
 		// TestReSTIR::render (src/TestReSTIR.cpp:9-36)
-		check(rpt_di_pathgen(mFrame, mDeviceScene, &diSettings), "rpt_di_pathgen");
-		check(rpt_di_temporal(mFrame, mDeviceScene, &diSettings), "rpt_di_temporal");
-		if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_DI_TEMP);
-		check(rpt_di_spatial(mFrame, mDeviceScene, &diSettings), "rpt_di_spatial");
+		if (stage == 0) {
+			check(rpt_di_pathgen(mFrame, mDeviceScene, &diSettings), "rpt_di_pathgen");
+			check(rpt_di_temporal(mFrame, mDeviceScene, &diSettings), "rpt_di_temporal");
+		}
+		else {
+			if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_DI_TEMP);
+			check(rpt_di_spatial(mFrame, mDeviceScene, &diSettings), "rpt_di_spatial");
+		}
 	}
 	else if (settings.directMethod == RayTracingMethod::VisualizeAS) {
-		check(rpt_visualize_as(mFrame, mDeviceScene), "rpt_visualize_as");
+		if (stage == 0) check(rpt_visualize_as(mFrame, mDeviceScene), "rpt_visualize_as");
 	}
 
 	if (settings.indirectMethod == RayTracingMethod::Naive) {
-		check(rpt_gi_naive(mFrame, mDeviceScene), "rpt_gi_naive");
+		if (stage == 0) check(rpt_gi_naive(mFrame, mDeviceScene), "rpt_gi_naive");
 	}
 	else if (settings.indirectMethod == RayTracingMethod::ResampledGI) {
-		check(rpt_gi_restir(mFrame, mDeviceScene), "rpt_gi_restir");
+		if (stage == 0) check(rpt_gi_restir(mFrame, mDeviceScene), "rpt_gi_restir");
 	}
 	else if (settings.indirectMethod == RayTracingMethod::ResampledPT) {
 		// GRISReSTIR::render (src/GRISReSTIR.cpp:9-53)
-		check(rpt_gris_pathtrace(mFrame, mDeviceScene, &grisSettings), "rpt_gris_pathtrace");
-		check(rpt_gris_temporal(mFrame, mDeviceScene, &grisSettings), "rpt_gris_temporal");
-		if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_GRIS_TEMP);
-		check(rpt_gris_spatial(mFrame, mDeviceScene, &grisSettings), "rpt_gris_spatial");
+		if (stage == 0) {
+			check(rpt_gris_pathtrace(mFrame, mDeviceScene, &grisSettings), "rpt_gris_pathtrace");
+			check(rpt_gris_temporal(mFrame, mDeviceScene, &grisSettings), "rpt_gris_temporal");
+		}
+		else {
+			if (mHaloFn) mHaloFn(mHaloUser, mFrame, RPT_BUF_GRIS_TEMP);
+			check(rpt_gris_spatial(mFrame, mDeviceScene, &grisSettings), "rpt_gris_spatial");
+		}
 	}
+	if (stage == 0) return;
 
 	RptPostSettings post;
 	post.toneMapping = uint32_t(settings.toneMapping);

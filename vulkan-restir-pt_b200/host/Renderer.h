@@ -39,6 +39,9 @@ public:
 
 	// one frame; rgba8Out may be null (no read-back).  seed = this frame's Camera::seed
 	void drawFrame(uint32_t seed, uint8_t* rgba8Out);
+	// all strips of one film that live in this process (multi-GPU from one host thread, or several strips on one device): the
+	// same frame on every strip, stage by stage, so that every device-side hand-over wait finds its signal already enqueued
+	static void drawStrips(Renderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs);
 	// dynamic scenes: push the scene's current object instances to the device and rebuild the acceleration structure
 	void updateInstances(const Scene& scene);
 	void clearReservoirs() { mClearNext = true; }   // GUI "clear" → Camera::setClearFlag
@@ -56,6 +59,7 @@ public:
 
 private:
 	void check(int status, const char* what);
+	void drawStage(int stage, uint32_t seed, uint8_t* rgba8Out);
 
 	RptCtx* mCtx = nullptr;
 	RptScene* mDeviceScene = nullptr;

@@ -5,7 +5,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <fstream>
+#include <sstream>
+#include "XmlLite.h"
 #include <string>
+#include <vector>
 
 using namespace rpt;
 
@@ -108,9 +112,45 @@ int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out) {
 		return -1;
 	}
 }
+int rh_draw_strips(RhRenderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs) {
+	try {
+		std::vector<Renderer*> rs(count);
+		for (uint32_t i = 0; i < count; i++) rs[i] = strips[i]->r;
+		Renderer::drawStrips(rs.data(), count, seed, rgba8Outs);
+		return 0;
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		return -1;
+	}
+}
 RptFrame* rh_renderer_frame(RhRenderer* r) { return r->r->frame(); }
 RptScene* rh_renderer_scene(RhRenderer* r) { return r->r->deviceScene(); }
 RptCtx* rh_renderer_ctx(RhRenderer* r) { return r->r->ctx(); }
+
+// canonical dump of a scene file's element tree as host/XmlLite.h reads it ("<depth> <name> <attr>=<value> ...\n", document order):
+// compared in the tests with the same dump made by the reference's parser (pugixml, oracle/ref/ref_pugi.cpp)
+static void dumpXml(const XmlNode& n, int depth, std::string& out) {
+	out += std::to_string(depth) + " " + n.name;
+	for (auto& a : n.attrs) out += " " + a.first + "=" + a.second;
+	out += "\n";
+	for (auto& c : n.children) dumpXml(*c, depth + 1, out);
+}
+size_t rh_xml_dump(const char* path, char* out, size_t capacity) {
+	try {
+		std::ifstream f(path, std::ios::binary);
+		if (!f) { gLastError = std::string("rh_xml_dump: cannot open ") + path; return 0; }
+		std::stringstream ss;
+		ss << f.rdbuf();
+		const std::string text = ss.str();
+		auto root = XmlParser(text).parseDocument();
+		std::string s;
+		dumpXml(*root, 0, s);
+		if (out && capacity) { std::strncpy(out, s.c_str(), capacity - 1); out[capacity - 1] = 0; }
+		return s.size() + 1;
+	}
+	catch (const std::exception& e) { gLastError = e.what(); return 0; }
+}
 
 int rh_write_png(const char* path, const uint8_t* rgba8, uint32_t w, uint32_t h) { return writePNG(path, rgba8, w, h) ? 0 : -1; }
 uint8_t* rh_read_image(const char* path, uint32_t* width, uint32_t* height) {

@@ -98,9 +98,17 @@ class Counters(C.Structure):
 
 class PeerInfo(C.Structure):
     _fields_ = [("grisTempHandle", C.c_uint8 * 64), ("diTempHandle", C.c_uint8 * 64), ("flagsHandle", C.c_uint8 * 64),
-                ("grisTempPtr", C.c_uint64), ("diTempPtr", C.c_uint64), ("flagsPtr", C.c_uint64), ("pid", C.c_uint64),
+                ("grisHandle", C.c_uint8 * 64 * 2), ("diHandle", C.c_uint8 * 64 * 2), ("giHandle", C.c_uint8 * 64 * 2),
+                ("grisTempPtr", C.c_uint64), ("diTempPtr", C.c_uint64), ("flagsPtr", C.c_uint64),
+                ("grisPtr", C.c_uint64 * 2), ("diPtr", C.c_uint64 * 2), ("giPtr", C.c_uint64 * 2), ("pid", C.c_uint64),
                 ("device", C.c_int32), ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32), ("storeBegin", C.c_uint32),
-                ("storeEnd", C.c_uint32), ("pad", C.c_uint32 * 3)]
+                ("storeEnd", C.c_uint32), ("cur", C.c_uint32), ("pad", C.c_uint32 * 2)]
+
+
+class GatherInfo(C.Structure):
+    _fields_ = [("imageHandle", C.c_uint8 * 64), ("flagsHandle", C.c_uint8 * 64), ("imagePtr", C.c_uint64),
+                ("flagsPtr", C.c_uint64), ("pid", C.c_uint64), ("device", C.c_int32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("numStrips", C.c_uint32)]
 
 
 class PassStats(C.Structure):
@@ -194,6 +202,11 @@ DEVICE_API = {
     "rpt_frame_connect_peers": (C.c_int, [P, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
     "rpt_frame_disconnect_peers": (C.c_int, [P]),
     "rpt_frame_peer_error": (C.c_int, [P]),
+    "rpt_frame_peers_in_process": (C.c_int, [P]),
+    "rpt_frame_gather_create": (C.c_int, [P, C.c_uint32, C.POINTER(GatherInfo)]),
+    "rpt_frame_gather_connect": (C.c_int, [P, C.POINTER(GatherInfo), C.c_uint32]),
+    "rpt_frame_gather_disconnect": (C.c_int, [P]),
+    "rpt_gather_output": (C.c_int, [P, P]),
     "rpt_frame_timing": (C.c_int, [P, C.c_int]),
     "rpt_frame_pass_stats": (C.c_int, [P, C.POINTER(PassStats)]),
     "rpt_buffer_stride": (C.c_size_t, [C.c_int]),
@@ -205,6 +218,7 @@ DEVICE_API = {
     "rpt_trace_shadow": (C.c_int, [P, P, P, C.c_uint32, P]),
     "rpt_trace_bench": (C.c_int, [P, P, P, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), P, P]),
     "rpt_wavefront_counters": (C.c_int, [P, C.POINTER(C.c_uint32)]),
+    "rpt_membench": (C.c_int, [P, C.c_size_t, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rpt_counters_enable": (C.c_int, [P, C.c_int]),
     "rpt_counters_reset": (C.c_int, [P]),
     "rpt_counters_read": (C.c_int, [P, C.POINTER(Counters)]),
@@ -243,9 +257,11 @@ HOST_API = {
     "rh_renderer_camera": (None, [P, C.POINTER(Camera)]),
     "rh_renderer_set_halo_exchange": (None, [P, HALO_FN, P]),
     "rh_renderer_draw_frame": (C.c_int, [P, C.c_uint32, P]),
+    "rh_draw_strips": (C.c_int, [C.POINTER(P), C.c_uint32, C.c_uint32, C.POINTER(P)]),
     "rh_renderer_frame": (P, [P]),
     "rh_renderer_scene": (P, [P]),
     "rh_renderer_ctx": (P, [P]),
+    "rh_xml_dump": (C.c_size_t, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "rh_write_png": (C.c_int, [C.c_char_p, P, C.c_uint32, C.c_uint32]),
     "rh_read_image": (P, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rh_free_image": (None, [P]),
