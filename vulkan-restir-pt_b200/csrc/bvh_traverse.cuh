@@ -174,11 +174,16 @@ struct TriHit {
 };
 
 // Möller–Trumbore in the fixed operation order of the numeric contract; accepted iff tmin < t < tmax.
-// (o, d, tmin) given directly: the warp-cooperative triangle rounds of trace_queue.cu test OTHER lanes' rays.
-RT_DEV bool triTestRay(const SceneView& s, float3 o, float3 d, float tmin, uint32_t triIndex, float tmax, TriHit& h) {
+// The 48-byte record is loaded apart from the test so that a loop can have the next record in flight (triLoop).
+struct TriData { float4 t0, t1, t2; };
+RT_DEV TriData loadTri(const SceneView& s, uint32_t triIndex) {
 	const float4* tp = reinterpret_cast<const float4*>(s.tris + triIndex);
-	const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-	const float3 v0 = f3(t0), e1 = f3(t1), e2 = f3(t2);
+	TriData d;
+	d.t0 = __ldg(tp + 0); d.t1 = __ldg(tp + 1); d.t2 = __ldg(tp + 2);
+	return d;
+}
+RT_DEV bool triTestData(const TriData& td, float3 o, float3 d, float tmin, float tmax, TriHit& h) {
+	const float3 v0 = f3(td.t0), e1 = f3(td.t1), e2 = f3(td.t2);
 	const float3 p = cross(d, e2);
 	const float det = dot(e1, p);
 	const float inv = 1.0f / det;
@@ -188,8 +193,11 @@ RT_DEV bool triTestRay(const SceneView& s, float3 o, float3 d, float tmin, uint3
 	const float v = dot(d, q) * inv;
 	const float t = dot(e2, q) * inv;
 	h.t = t; h.u = u; h.v = v;
-	h.instanceIdx = __float_as_uint(t0.w); h.triangleIdx = __float_as_uint(t1.w); h.flat = __float_as_uint(t2.w);
+	h.instanceIdx = __float_as_uint(td.t0.w); h.triangleIdx = __float_as_uint(td.t1.w); h.flat = __float_as_uint(td.t2.w);
 	return u >= -BaryEps && v >= -BaryEps && (u + v) <= 1.0f + BaryEps && t > tmin && t < tmax;
+}
+RT_DEV bool triTestRay(const SceneView& s, float3 o, float3 d, float tmin, uint32_t triIndex, float tmax, TriHit& h) {
+	return triTestData(loadTri(s, triIndex), o, d, tmin, tmax, h);
 }
 RT_DEV bool triTest(const SceneView& s, const TravRay& r, uint32_t triIndex, float tmax, TriHit& h) {
 	return triTestRay(s, r.o, r.d, r.tmin, triIndex, tmax, h);
@@ -221,6 +229,45 @@ struct TravResult {
 		return false;
 	}
 };
+
+// The triangles of one node's leaf children (bits of triHits, relative to triBase) against the ray; returns true when the
+// traversal may stop (any hit accepted).  RT_TRI_PIPE: the next triangle's record is requested before the current one is
+// tested, so its L1 / L2 latency overlaps the test instead of following it (the loop runs at ~8 of 32 lanes and a third of the
+// traversal kernels' stall samples sit on these loads, profiles/r2_03_*).
+template <int MODE>
+RT_DEV bool triLoop(const SceneView& s, const TravRay& r, uint32_t triBase, uint32_t triHits, float tmaxOrig, TravResult& res, uint32_t& triTests) {
+#ifdef RT_TRI_PIPE
+	if (!triHits) return false;
+	TriData cur = loadTri(s, triBase + uint32_t(__ffs(int(triHits))) - 1u);
+	triHits &= triHits - 1u;
+	for (;;) {
+		const bool more = triHits != 0u;
+		TriData nxt = cur;
+		if (more) {
+			nxt = loadTri(s, triBase + uint32_t(__ffs(int(triHits))) - 1u);
+			triHits &= triHits - 1u;
+		}
+		triTests++;
+		TriHit h;
+		if (triTestData(cur, r.o, r.d, r.tmin, tmaxOrig, h)) {
+			if (res.accept<MODE>(h)) return true;
+		}
+		if (!more) return false;
+		cur = nxt;
+	}
+#else
+	while (triHits) {
+		const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
+		triHits &= triHits - 1u;
+		triTests++;
+		TriHit h;
+		if (triTest(s, r, triBase + i, tmaxOrig, h)) {
+			if (res.accept<MODE>(h)) return true;
+		}
+	}
+	return false;
+#endif
+}
 
 // One ray per thread, run to completion (the per-pixel passes call this in line).
 template <int MODE>

@@ -95,15 +95,7 @@ __global__ void RT_TRACE_BOUNDS traceQueueKernel(const __grid_constant__ SceneVi
 				nodeStep(s, r, res.bestT, ngroup, stack, sp, triBase, triHits);
 				nodeVisits++;
 			}
-			while (triHits) {
-				const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
-				triHits &= triHits - 1u;
-				triTests++;
-				TriHit h;
-				if (triTest(s, r, triBase + i, tmaxOrig, h)) {
-					if (res.accept<MODE>(h)) { finished = true; break; }
-				}
-			}
+			finished = triLoop<MODE>(s, r, triBase, triHits, tmaxOrig, res, triTests);
 			if (!finished && ngroup.y <= 0x00ffffffu) {
 				if (sp == 0) finished = true;
 				else ngroup = stack[--sp];
@@ -129,186 +121,145 @@ __global__ void RT_TRACE_BOUNDS traceQueueKernel(const __grid_constant__ SceneVi
 }
 
 
-// ---- variant: warp-cooperative triangle rounds (RT_TRI_COMPACT) ---------------------------------------------------
-// The node step above runs at ~28 of 32 lanes, the per-lane triangle loop at ~8 (profiles/r1_14_*: most node steps yield no
-// triangle, a few yield several, so the loop runs as long as the fullest lane).  Here every round's (ray, triangle) pairs are
-// listed in shared memory and tested by full warps: lane j tests pair j with the OWNER lane's ray (origin / direction staged
-// in shared memory at fetch time).  Results return through native 32-bit shared atomics only (a 64-bit shared atomicMin is
-// a CAS loop, which is what sank the r1_16 attempt): pass 1 atomicMin on the order-mapped bits of t, pass 2 atomicMin on the
-// flattened index among the lanes that hold the minimum t, pass 3 the unique winner publishes {u, v, ids}; the owner merges
-// it with the order-independent closest-hit rule.  Same triangle arithmetic, same rule => same bits as traceRay<>.
-constexpr uint32_t NoCand = 0xffffffffu;
-struct __align__(16) WarpScratch {
-	float4 rayA[32];        // origin, tmin      of the lane's current ray
-	float4 rayB[32];        // direction, tmax
-	uint4 win[32];          // closest hit: {u, v, instanceIdx, triangleIdx} of the round's winner for this owner
-	uint32_t keyT[32];      // closest hit: order-mapped bits of the best t so far; any hit: 1 = occluded
-	uint32_t candFlat[32];  // lowest flattened index among this chunk's candidates at t == keyT (NoCand: none)
-	uint32_t triBase[32];   // first triangle of the owner's current node
-	uint32_t count;         // pairs listed this round
-	uint32_t pad[3];
-	uint16_t list[32 * 24]; // owner lane << 5 | triangle bit of the owner's hit mask
+// ---- variant: warp-local ray pool in shared memory (RT_RAY_POOL) ----------------------------------------------------
+// In the kernel above a fetch is a dependent chain — queue atomic (L2 round trip) -> ray record (HBM, read once) -> three IEEE
+// reciprocals — that the whole warp sits through whenever 8 lanes are idle: 30 % of the kernel's stall samples
+// (profiles/r2_03_*), and the node step runs at 28 of 32 lanes while lanes wait for the threshold.  Here each warp owns a
+// two-deep pool of 32-ray batches in shared memory: the queue atomic for batch k+2 is issued one loop iteration before its
+// result is used, the batch's records travel HBM -> shared memory as asynchronous copies (cp.async, bypassing L1: they are
+// read once) while the warp traverses, and when a batch lands all 32 lanes prepare one ray each (degenerate test, reciprocal
+// direction, octant) at full width.  A lane whose ray ends takes the next prepared ray from shared memory in the same
+// iteration (three 16-byte shared loads), so lanes are never parked waiting for a threshold.
+// Per-ray arithmetic and results are those of traceQueueKernel.
+constexpr uint32_t PoolBatch = 32;
+#ifndef RT_POOL_THRESHOLD
+#define RT_POOL_THRESHOLD 1   // idle lanes per warp that trigger a refill from the pool
+#endif
+struct __align__(16) RayPool {
+	float4 a[2][PoolBatch];   // origin, tmin
+	float4 b[2][PoolBatch];   // direction, tmax
+	float4 c[PoolBatch];      // prepared: reciprocal direction, w = octinv (bits) or 0xffffffff for a degenerate ray (already answered)
 };
 
-RT_DEV uint32_t orderKey(float t) {   // monotone map float -> uint32
-	const uint32_t b = __float_as_uint(t);
-	return b ^ (uint32_t(int32_t(b) >> 31) | 0x80000000u);
+RT_DEV void cpAsync16(void* sharedDst, const void* globalSrc) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(uint32_t(__cvta_generic_to_shared(sharedDst))), "l"(globalSrc) : "memory");
 }
-RT_DEV float orderKeyInv(uint32_t k) {
-	return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
-}
+RT_DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+RT_DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int MODE>
-__global__ void RT_TRACE_BOUNDS traceQueueCompactKernel(const __grid_constant__ SceneView s, const float4* __restrict__ rays,
-                                                        const uint32_t* __restrict__ countPtr, uint32_t countHost, uint32_t* __restrict__ head,
-                                                        RptIntersection* __restrict__ hits, uint8_t* __restrict__ occluded) {
-	__shared__ WarpScratch scratch[TraceBlock / 32];
-	WarpScratch& ws = scratch[threadIdx.x >> 5];
+__global__ void RT_TRACE_BOUNDS traceQueuePoolKernel(const __grid_constant__ SceneView s, const float4* __restrict__ rays,
+                                                     const uint32_t* __restrict__ countPtr, uint32_t countHost, uint32_t* __restrict__ head,
+                                                     RptIntersection* __restrict__ hits, uint8_t* __restrict__ occluded) {
+	__shared__ RayPool pools[TraceBlock / 32];
+	RayPool& pool = pools[threadIdx.x >> 5];
 	const uint32_t n = countPtr ? *countPtr : countHost;
 	const uint32_t lane = threadIdx.x & 31u;
 	uint32_t rayIdx = NoRay;
-	bool dry = false;
 	TravRay r = makeTravRay(f3(0.0f), 0.0f, f3(1.0f));
-	float bestT = 0.0f, bestU = 0.0f, bestV = 0.0f;
-	uint32_t bestKey = 0, bestFlat = NoCand, bestInst = InvalidHitIndex, bestTri = 0;
-#ifdef RT_SMEM_STACK
-	__shared__ uint2 stackShared[RT_SMEM_STACK][TraceBlock];
-	struct HybridStack {
-		uint2 (*sh)[TraceBlock];
-		uint2 spill[TraversalStackSize - RT_SMEM_STACK];
-		struct Ref {
-			HybridStack& st; int i;
-			RT_DEV void operator=(uint2 v) { if (i < RT_SMEM_STACK) st.sh[i][threadIdx.x] = v; else st.spill[i - RT_SMEM_STACK] = v; }
-			RT_DEV operator uint2() const { return i < RT_SMEM_STACK ? st.sh[i][threadIdx.x] : st.spill[i - RT_SMEM_STACK]; }
-		};
-		RT_DEV Ref operator[](int i) { return Ref{ *this, i }; }
-	} stack;
-	stack.sh = stackShared;
-#else
+	TravResult res;
+	res.init(0.0f);
+	float tmaxOrig = 0.0f;
 	uint2 stack[TraversalStackSize];
-#endif
 	int sp = 0;
 	uint2 ngroup = make_uint2(0u, 0u);
 	uint32_t nodeVisits = 0, triTests = 0, visitsAtFetch = 0;
-	if (lane == 0) ws.count = 0;
-	__syncwarp();
+
+	// warp-uniform pool state
+	uint32_t curBase = 0, curCount = 0, curPos = 0, buf = 0;   // batch being handed out: rays curBase + [curPos, curCount) of pool.a/b[buf]
+	uint32_t nxtBase = 0, nxtCount = 0;
+	int nxtState = 0;          // 0: nothing in flight, 1: queue atomic issued (result in lane 0's ticket), 2: copies issued into pool.a/b[buf ^ 1]
+	uint32_t ticket = 0;       // lane 0: result of the queue atomic
+	bool dry = false;          // the queue has been handed out completely (no further atomics)
 
 	for (;;) {
-		// ---- dynamic fetch (as in traceQueueKernel) ---------------------------------------------------------------
 		const unsigned idleMask = __ballot_sync(FullWarp, rayIdx == NoRay);
-		if (!dry && __popc(idleMask) >= FetchThreshold) {
-			const int leader = __ffs(int(idleMask)) - 1;
-			const uint32_t want = uint32_t(__popc(idleMask));
-			uint32_t base = 0;
-			if (int(lane) == leader) base = atomicAdd(head, want);
-			base = __shfl_sync(FullWarp, base, leader);
-			if (base + want >= n) dry = true;
-			if (rayIdx == NoRay) {
-				const uint32_t idx = base + uint32_t(__popc(idleMask & ((1u << lane) - 1u)));
-				if (idx < n) {
-					const float4 a = __ldcs(rays + 2 * size_t(idx)), b = __ldcs(rays + 2 * size_t(idx) + 1);
-					if (rayIsDegenerate(f3(a), a.w, f3(b), b.w)) {
-						if (MODE == TraceAny) occluded[idx] = 0;
-						else { RptIntersection o; o.bary[0] = 0.f; o.bary[1] = 0.f; o.instanceIdx = InvalidHitIndex; o.triangleIdx = 0; hits[idx] = o; }
-					}
-					else {
-						if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
-						rayIdx = idx;
-						r = makeTravRay(f3(a), a.w, f3(b));
-						ws.rayA[lane] = a; ws.rayB[lane] = b;
-						bestT = b.w; bestU = 0.0f; bestV = 0.0f; bestFlat = NoCand; bestInst = InvalidHitIndex; bestTri = 0;
-						bestKey = MODE == TraceAny ? 0u : orderKey(b.w);
-						ws.keyT[lane] = bestKey;
-						ws.candFlat[lane] = NoCand;
-						sp = 0;
-						ngroup = make_uint2(0u, 0x80000000u);
-						visitsAtFetch = nodeVisits;
-					}
+		// ---- the next batch: keep the pipeline one step ahead of its use ----------------------------------------------------
+		if (nxtState == 1) {
+			const uint32_t base = __shfl_sync(FullWarp, ticket, 0);
+			nxtBase = base;
+			nxtCount = base < n ? min(PoolBatch, n - base) : 0u;
+			if (base + PoolBatch >= n) dry = true;
+			if (lane < nxtCount) {
+				cpAsync16(&pool.a[buf ^ 1u][lane], rays + 2 * size_t(base + lane));
+				cpAsync16(&pool.b[buf ^ 1u][lane], rays + 2 * size_t(base + lane) + 1);
+			}
+			cpAsyncCommit();
+			nxtState = 2;
+		}
+		else if (nxtState == 0 && !dry) {
+			if (lane == 0) ticket = atomicAdd(head, PoolBatch);
+			nxtState = 1;
+		}
+		// ---- the current batch is used up: take over the next one and prepare its rays with all 32 lanes ----------------------
+		if (curPos == curCount && nxtState == 2 && idleMask != 0u) {
+			cpAsyncWaitAll();
+			__syncwarp();
+			buf ^= 1u;
+			curBase = nxtBase; curCount = nxtCount; curPos = 0;
+			nxtState = 0;
+			if (lane < curCount) {
+				const float4 a = pool.a[buf][lane], b = pool.b[buf][lane];
+				float4 c;
+				if (rayIsDegenerate(f3(a), a.w, f3(b), b.w)) {
+					const uint32_t idx = curBase + lane;
+					if (MODE == TraceAny) occluded[idx] = 0;
+					else { RptIntersection o; o.bary[0] = 0.f; o.bary[1] = 0.f; o.instanceIdx = InvalidHitIndex; o.triangleIdx = 0; hits[idx] = o; }
+					c = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
 				}
+				else {
+					if (s.counters != nullptr) atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+					const TravRay t = makeTravRay(f3(a), a.w, f3(b));
+					c = make_float4(t.idx, t.idy, t.idz, __uint_as_float(t.octinv));
+				}
+				pool.c[lane] = c;
 			}
 			__syncwarp();
 		}
+		// ---- idle lanes take prepared rays ------------------------------------------------------------------------------------
+		if (curPos < curCount && __popc(idleMask) >= RT_POOL_THRESHOLD) {
+			const uint32_t slot = curPos + uint32_t(__popc(idleMask & ((1u << lane) - 1u)));
+			if (rayIdx == NoRay && slot < curCount) {
+				const float4 c = pool.c[slot];
+				const uint32_t oct = __float_as_uint(c.w);
+				if (oct != 0xffffffffu) {
+					const float4 a = pool.a[buf][slot], b = pool.b[buf][slot];
+					rayIdx = curBase + slot;
+					r.o = f3(a); r.d = f3(b); r.tmin = a.w;
+					r.idx = c.x; r.idy = c.y; r.idz = c.z; r.octinv = oct;
+					tmaxOrig = b.w;
+					res.init(b.w);
+					sp = 0;
+					ngroup = make_uint2(0u, 0x80000000u);
+					visitsAtFetch = nodeVisits;
+				}
+			}
+			curPos = min(curCount, curPos + uint32_t(__popc(idleMask)));
+		}
 		if (__all_sync(FullWarp, rayIdx == NoRay)) {
-			if (dry) break;
+			if (curPos == curCount && nxtState == 0 && dry) break;
 			continue;
 		}
 
-		// ---- node step of every lane that holds a ray -----------------------------------------------------------------
-		uint32_t triBase = 0, triHits = 0;
-		if (rayIdx != NoRay && ngroup.y > 0x00ffffffu) {
-			nodeStep(s, r, bestT, ngroup, stack, sp, triBase, triHits);
-			nodeVisits++;
-		}
-
-		// ---- the round's triangles, tested by full warps ---------------------------------------------------------------
-		if (__any_sync(FullWarp, triHits != 0u)) {
-			if (triHits) {
-				uint32_t p = atomicAdd(&ws.count, uint32_t(__popc(triHits)));
-				ws.triBase[lane] = triBase;
-				uint32_t m = triHits;
-				do {
-					const uint32_t i = uint32_t(__ffs(int(m))) - 1u;
-					m &= m - 1u;
-					ws.list[p++] = uint16_t((lane << 5) | i);
-				} while (m);
-			}
-			__syncwarp();
-			const uint32_t total = ws.count;
-			for (uint32_t c = 0; c < total; c += 32u) {
-				const uint32_t j = c + lane;
-				bool ok = false;
-				uint32_t owner = 0, key = 0;
-				TriHit h;
-				if (j < total) {
-					const uint32_t e = ws.list[j];
-					owner = e >> 5;
-					const float4 a = ws.rayA[owner], b = ws.rayB[owner];
-					triTests++;
-					ok = triTestRay(s, f3(a), f3(b), a.w, ws.triBase[owner] + (e & 31u), b.w, h);
-				}
-				if (MODE == TraceAny) {
-					if (ok) ws.keyT[owner] = 1u;
-					__syncwarp();
-				}
-				else {
-					if (ok) { key = orderKey(h.t); atomicMin(&ws.keyT[owner], key); }
-					__syncwarp();
-					const bool cand = ok && ws.keyT[owner] == key;
-					if (cand) atomicMin(&ws.candFlat[owner], h.flat);
-					__syncwarp();
-					if (cand && ws.candFlat[owner] == h.flat)
-						ws.win[owner] = make_uint4(__float_as_uint(h.u), __float_as_uint(h.v), h.instanceIdx, h.triangleIdx);
-					__syncwarp();
-					const uint32_t cf = ws.candFlat[lane];
-					if (rayIdx != NoRay && cf != NoCand) {
-						const uint32_t kt = ws.keyT[lane];
-						if (kt < bestKey || cf < bestFlat) {
-							const uint4 w = ws.win[lane];
-							bestKey = kt; bestFlat = cf; bestT = orderKeyInv(kt);
-							bestU = __uint_as_float(w.x); bestV = __uint_as_float(w.y); bestInst = w.z; bestTri = w.w;
-						}
-						ws.candFlat[lane] = NoCand;
-					}
-					__syncwarp();
-				}
-			}
-			if (lane == 0) ws.count = 0;
-			__syncwarp();
-		}
-
+		// ---- one traversal step of every lane that holds a ray (as in traceQueueKernel) -----------------------------------------
 		if (rayIdx != NoRay) {
 			bool finished = false;
-			if (MODE == TraceAny && ws.keyT[lane] != 0u) finished = true;
-			else if (ngroup.y <= 0x00ffffffu) {
+			uint32_t triBase = 0, triHits = 0;
+			if (ngroup.y > 0x00ffffffu) {
+				nodeStep(s, r, res.bestT, ngroup, stack, sp, triBase, triHits);
+				nodeVisits++;
+			}
+			finished = triLoop<MODE>(s, r, triBase, triHits, tmaxOrig, res, triTests);
+			if (!finished && ngroup.y <= 0x00ffffffu) {
 				if (sp == 0) finished = true;
 				else ngroup = stack[--sp];
 			}
 			if (finished) {
 				if (s.counters != nullptr) atomicMax(&s.counters[7], (unsigned long long)(nodeVisits - visitsAtFetch));
-				if (MODE == TraceAny) occluded[rayIdx] = ws.keyT[lane] != 0u ? 1 : 0;
+				if (MODE == TraceAny) occluded[rayIdx] = res.best.instanceIdx != InvalidHitIndex ? 1 : 0;
 				else {
 					RptIntersection o;
-					o.bary[0] = bestU; o.bary[1] = bestV; o.instanceIdx = bestInst; o.triangleIdx = bestTri;
+					o.bary[0] = res.best.u; o.bary[1] = res.best.v; o.instanceIdx = res.best.instanceIdx; o.triangleIdx = res.best.triangleIdx;
 					hits[rayIdx] = o;
 				}
 				rayIdx = NoRay;
@@ -325,9 +276,9 @@ __global__ void RT_TRACE_BOUNDS traceQueueCompactKernel(const __grid_constant__ 
 template <int MODE>
 void launchQueue(const SceneView& s, const float4* rays, const uint32_t* countPtr, uint32_t countHost, uint32_t* head,
                  RptIntersection* hits, uint8_t* occluded, cudaStream_t st) {
-#ifdef RT_TRI_COMPACT
-	static const int blocks = persistentBlocks(reinterpret_cast<const void*>(traceQueueCompactKernel<MODE>), TraceBlock);
-	traceQueueCompactKernel<MODE><<<blocks, TraceBlock, 0, st>>>(s, rays, countPtr, countHost, head, hits, occluded);
+#ifdef RT_RAY_POOL
+	static const int blocks = persistentBlocks(reinterpret_cast<const void*>(traceQueuePoolKernel<MODE>), TraceBlock);
+	traceQueuePoolKernel<MODE><<<blocks, TraceBlock, 0, st>>>(s, rays, countPtr, countHost, head, hits, occluded);
 #else
 	static const int blocks = persistentBlocks(reinterpret_cast<const void*>(traceQueueKernel<MODE>), TraceBlock);
 	traceQueueKernel<MODE><<<blocks, TraceBlock, 0, st>>>(s, rays, countPtr, countHost, head, hits, occluded);
