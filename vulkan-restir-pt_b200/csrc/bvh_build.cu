@@ -220,7 +220,7 @@ RT_DEV uint32_t exponentFor(float extent) {
 	float q = extent * (1.0f / 255.0f) * 1.000002f;
 	uint32_t b = __float_as_uint(q);
 	uint32_t e = (b + 0x7fffffu) >> 23;
-	return min(max(e, 1u), 254u);
+	return min(max(e, 1u), 239u);   // (+15 must fit the node's exponent byte; 2^112 is beyond any scene)
 }
 
 __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const uint2* __restrict__ tasks, uint2* __restrict__ nextTasks,
@@ -305,11 +305,10 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
 	const double isy = ey ? 1.0 / double(__uint_as_float(ey << 23)) : 0.0;
 	const double isz = ez ? 1.0 / double(__uint_as_float(ez << 23)) : 0.0;
 
-	uint32_t meta[8], qlo[3][8], qhi[3][8];
-	uint32_t innerSeen = 0;
+	uint32_t qlo[3][8], qhi[3][8];
+	uint32_t innerSeen = 0, leafTris = 0;
 	for (int sl = 0; sl < 8; sl++) {
-		meta[sl] = 0;
-		for (int a = 0; a < 3; a++) { qlo[a][sl] = 0; qhi[a][sl] = 0; }
+		for (int a = 0; a < 3; a++) { qlo[a][sl] = 255; qhi[a][sl] = 0; }   // empty slot: inverted box
 		const uint32_t c = slotChild[sl];
 		if (c == 0xffffffffu) continue;
 		const float4 lo = nodeLo[c], hi = nodeHi[c];
@@ -321,13 +320,11 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
 		qhi[1][sl] = uint32_t(fmin(fmax(ceil((double(hi.y) - double(p.y)) * isy), 0.0), 255.0));
 		qhi[2][sl] = uint32_t(fmin(fmax(ceil((double(hi.z) - double(p.z)) * isz), 0.0), 255.0));
 		if (imask & (1u << sl)) {
-			meta[sl] = (1u << 5) | (24u + uint32_t(sl));
 			nextTasks[queueBase + innerSeen] = make_uint2(c, childBase + innerSeen);
 			innerSeen++;
 		}
 		else {
-			const uint32_t n = triCount[sl];
-			meta[sl] = (((1u << n) - 1u) << 5) | triOffset[sl];
+			leafTris |= ((1u << triCount[sl]) - 1u) << (3 * sl);
 			// gather the subtree's triangles (<= 3 leaves)
 			uint32_t stack[4]; int sp = 0; uint32_t w = 0;
 			stack[sp++] = c;
@@ -345,9 +342,10 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
 		}
 	}
 	auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+	const uint32_t Ex = ex ? ex + 15u : 0u, Ey = ey ? ey + 15u : 0u, Ez = ez ? ez + 15u : 0u;
 	WideNode out;
-	out.n0 = make_float4(p.x, p.y, p.z, __uint_as_float(ex | (ey << 8) | (ez << 16) | (imask << 24)));
-	out.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(triBase), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+	out.n0 = make_float4(p.x, p.y, p.z, __uint_as_float(Ex | (Ey << 8) | (Ez << 16) | (imask << 24)));
+	out.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(triBase), __uint_as_float(leafTris), 0.0f);
 	out.n2 = make_float4(__uint_as_float(pack4(qlo[0])), __uint_as_float(pack4(qlo[0] + 4)), __uint_as_float(pack4(qlo[1])), __uint_as_float(pack4(qlo[1] + 4)));
 	out.n3 = make_float4(__uint_as_float(pack4(qlo[2])), __uint_as_float(pack4(qlo[2] + 4)), __uint_as_float(pack4(qhi[0])), __uint_as_float(pack4(qhi[0] + 4)));
 	out.n4 = make_float4(__uint_as_float(pack4(qhi[1])), __uint_as_float(pack4(qhi[1] + 4)), __uint_as_float(pack4(qhi[2])), __uint_as_float(pack4(qhi[2] + 4)));
@@ -430,7 +428,7 @@ cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* o
 	CK(cudaMemcpyAsync(cc, &cc0, sizeof(cc0), cudaMemcpyHostToDevice, stream));
 	const uint2 rootTask = make_uint2(root, 0u);
 	CK(cudaMemcpyAsync(qA, &rootTask, sizeof(rootTask), cudaMemcpyHostToDevice, stream));
-	const uint32_t leafMax = getenv("RPT_LEAF_MAX") ? uint32_t(atoi(getenv("RPT_LEAF_MAX"))) : 3u;
+	const uint32_t leafMax = getenv("RPT_LEAF_MAX") ? std::min(std::max(uint32_t(atoi(getenv("RPT_LEAF_MAX"))), 1u), 3u) : 3u;   // (build-time experiment switch)
 	uint32_t numTasks = 1;
 	while (numTasks) {
 		collapseKernel<<<(numTasks + 63) / 64, 64, 0, stream>>>(numTasks, qA, qB, N, nodeLo, nodeHi, nodeCount, trisFlat, wide, trisOut, cc, leafMax);

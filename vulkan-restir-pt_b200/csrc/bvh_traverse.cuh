@@ -28,28 +28,19 @@ constexpr int TraversalStackSize = 48;
 // busiest pipe of the traversal kernels, profiles/r1_03_wavefront_tracequeue_details.txt)
 template <int J>
 RT_DEV float byteIntoMantissa(uint32_t q, uint32_t unit) {
-#ifdef RT_SLAB_I2F   // A/B experiment build (profiles/README.md): float(b) through I2F.U8, `unit` = bits of the slope s
-	return __uint2float_rn((q >> (8 * J)) & 0xffu);
-#else
 	return __uint_as_float(__byte_perm(q, unit, 0x7604u | (uint32_t(J) << 4)));
-#endif
 }
 
-// one 4-child half of a node: accumulate hit bits for children j = 0..3 of the half.
+// one 4-child half of a node: hit bits of slots SLOT0 .. SLOT0+3.
 // Plane distances t = b * (2^e / d) + n (b = quantised byte, 2^e = the node's grid step) are evaluated as
-// fma(2^(e+15) (1 + b 2^-15), 1/d, N) with N = n - 2^(e+15) / d; the rounding of N (<= 2^-9 of one grid step in t) is
+// fma(2^(e+15) (1 + b 2^-15), 1/d, N) with N = n - 2^(e+15) / d; the rounding of N (<= 2^-8 of one grid step in t) is
 // covered by the slab padding in nodeStep.  ux/uy/uz = bits of 2^(e+15) per axis (0 for a flat axis).
-RT_DEV uint32_t slabHits4(uint32_t meta4, uint32_t octinv4,
-                          uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy, uint32_t qfz,
+template <int SLOT0>
+RT_DEV uint32_t slabHits4(uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx, uint32_t qfy, uint32_t qfz,
                           uint32_t ux, uint32_t uy, uint32_t uz, float idx, float idy, float idz,
                           float nx, float ny, float nz, float fx, float fy, float fz, float tmin, float tmax) {
-	uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-	uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-	uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-	uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 	uint32_t hits = 0;
 #define RT_SLAB_CHILD(J) { \
-		const int sh = 8 * J; \
 		float tnx = fma_(byteIntoMantissa<J>(qnx, ux), idx, nx); \
 		float tny = fma_(byteIntoMantissa<J>(qny, uy), idy, ny); \
 		float tnz = fma_(byteIntoMantissa<J>(qnz, uz), idz, nz); \
@@ -58,11 +49,22 @@ RT_DEV uint32_t slabHits4(uint32_t meta4, uint32_t octinv4,
 		float tfz = fma_(byteIntoMantissa<J>(qfz, uz), idz, fz); \
 		float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin)); \
 		float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax)); \
-		if (tn <= tf) hits |= ((childBits4 >> sh) & 0xffu) << ((bitIndex4 >> sh) & 0xffu); \
+		if (tn <= tf) hits |= 1u << (SLOT0 + J); \
 	}
 	RT_SLAB_CHILD(0) RT_SLAB_CHILD(1) RT_SLAB_CHILD(2) RT_SLAB_CHILD(3)
 #undef RT_SLAB_CHILD
 	return hits;
+}
+
+// bit (s ^ o) of the result = bit s of x, for an 8-bit mask and o in 0..7: slot order -> near-to-far order of a ray whose
+// direction octant is o (three conditional swaps: neighbours, pairs, nibbles)
+RT_DEV uint32_t permuteByOctant(uint32_t x, uint32_t o) {
+	const uint32_t x1 = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+	x = (o & 1u) ? x1 : x;
+	const uint32_t x2 = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+	x = (o & 2u) ? x2 : x;
+	const uint32_t x4 = ((x & 0x0fu) << 4) | (x >> 4);
+	return (o & 4u) ? x4 : x;
 }
 
 // Per-ray constants of a traversal: origin, direction, padded reciprocal direction, octant.
@@ -107,13 +109,26 @@ RT_DEV TravRay makeTravRay(float3 o, float tmin, float3 d) {
 	return r;
 }
 
+// Triangles of the leaf children of one node that the ray's interval entered.  Bit 3s + k stands for triangle k of the leaf in
+// slot s; `valid` = the bits that exist in this node; the triangles are stored from triBase on in bit order.
+struct LeafHits {
+	uint32_t bits, valid, triBase;
+};
+
+// bit s of an 8-bit mask -> bits 3s, 3s+1, 3s+2
+RT_DEV uint32_t expandSlotsToTriples(uint32_t x) {
+	x = (x * 0x101u) & 0x00f00fu;
+	x = (x * 0x11u) & 0x0c30c3u;
+	x = (x * 0x5u) & 0x249249u;
+	return x * 7u;
+}
+
 // Pops the nearest-octant child of the node group, tests its 8 child boxes against [tmin, tfar] and returns the
-// new node group (inner children hit) plus the triangle hits of its leaf children.  The remainder of the old
+// new node group (inner children hit, near to far) plus the hit leaf children.  The remainder of the old
 // group is pushed first.  Precondition: ngroup.y > 0x00ffffff.
 template <typename Stack>
-RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, uint32_t& triBase, uint32_t& triHits) {
+RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, LeafHits& leaves) {
 	const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
-	const uint32_t octinv4 = r.octinv * 0x01010101u;
 	const uint32_t hits = ngroup.y;
 	const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
 	ngroup.y &= ~(1u << bit);
@@ -124,27 +139,19 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 
 	const uint32_t ebits = __float_as_uint(n0.w);
-	// grid step 2^(e-127) per axis (e == 0: flat axis, step 0); s = step / d and h = (p - o) / d are the plane
-	// distances' slope and offset.  The slab interval is padded so that it can only grow:
-	//   1e-6 (255 |s| + |h|)  rounding of s, h and of the plane fma;   0.003 |s| >= 2^-9 |s|  rounding of N (slabHits4)
-	const uint32_t ebx = ebits & 0xffu, eby = (ebits >> 8) & 0xffu, ebz = (ebits >> 16) & 0xffu;
-	const float sx = __uint_as_float(ebx << 23) * r.idx, sy = __uint_as_float(eby << 23) * r.idy, sz = __uint_as_float(ebz << 23) * r.idz;
-	const uint32_t ux = ebx ? (ebx + 15u) << 23 : 0u, uy = eby ? (eby + 15u) << 23 : 0u, uz = ebz ? (ebz + 15u) << 23 : 0u;
-	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;
-	const float padx = fma_(fma_(abs_(sx), 255.0f, abs_(hx)), 1e-6f, abs_(sx) * 0.003f);
-	const float pady = fma_(fma_(abs_(sy), 255.0f, abs_(hy)), 1e-6f, abs_(sy) * 0.003f);
-	const float padz = fma_(fma_(abs_(sz), 255.0f, abs_(hz)), 1e-6f, abs_(sz) * 0.003f);
+	// U = 2^(e+15) per axis (the node stores e + 15; 0: flat axis, step 0), S = U / d, h = (p - o) / d: the plane of byte b is at
+	// t = h + b s with s = S 2^-15.  The slab interval is padded so that it can only grow:
+	//   1e-6 (255 |s| + |h|)  rounding of S, h and of the plane fma;   0.005 |s| >= 2 x 2^-9 |s|  the two roundings of N = (h - S) -+ pad
+	const uint32_t ux = (ebits & 0xffu) << 23, uy = (ebits & 0xff00u) << 15, uz = (ebits & 0xff0000u) << 7;
 	const float Sx = __uint_as_float(ux) * r.idx, Sy = __uint_as_float(uy) * r.idy, Sz = __uint_as_float(uz) * r.idz;
-#ifdef RT_SLAB_I2F
-	const float nx = hx - padx, ny = hy - pady, nz = hz - padz;
-	const float fx = hx + padx, fy = hy + pady, fz = hz + padz;
-	(void)Sx; (void)Sy; (void)Sz;
-#define RT_SLAB_ARGS ux, uy, uz, sx, sy, sz
-#else
-	const float nx = (hx - padx) - Sx, ny = (hy - pady) - Sy, nz = (hz - padz) - Sz;
-	const float fx = (hx + padx) - Sx, fy = (hy + pady) - Sy, fz = (hz + padz) - Sz;
-#define RT_SLAB_ARGS ux, uy, uz, r.idx, r.idy, r.idz
-#endif
+	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;
+	constexpr float PadPerUnit = (255.0e-6f + 0.005f) / 32768.0f;
+	const float padx = fma_(abs_(hx), 1e-6f, abs_(Sx) * PadPerUnit);
+	const float pady = fma_(abs_(hy), 1e-6f, abs_(Sy) * PadPerUnit);
+	const float padz = fma_(abs_(hz), 1e-6f, abs_(Sz) * PadPerUnit);
+	const float cx = hx - Sx, cy = hy - Sy, cz = hz - Sz;
+	const float nx = cx - padx, ny = cy - pady, nz = cz - padz;
+	const float fx = cx + padx, fy = cy + pady, fz = cz + padz;
 
 	const uint32_t qlox0 = __float_as_uint(n2.x), qlox1 = __float_as_uint(n2.y);
 	const uint32_t qloy0 = __float_as_uint(n2.z), qloy1 = __float_as_uint(n2.w);
@@ -153,19 +160,21 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	const uint32_t qhiy0 = __float_as_uint(n4.x), qhiy1 = __float_as_uint(n4.y);
 	const uint32_t qhiz0 = __float_as_uint(n4.z), qhiz1 = __float_as_uint(n4.w);
 
-	uint32_t hitmask = slabHits4(__float_as_uint(n1.z), octinv4,
+	uint32_t hitSlots = slabHits4<0>(
 		negx ? qhix0 : qlox0, negy ? qhiy0 : qloy0, negz ? qhiz0 : qloz0,
 		negx ? qlox0 : qhix0, negy ? qloy0 : qhiy0, negz ? qloz0 : qhiz0,
-		RT_SLAB_ARGS, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
-	hitmask |= slabHits4(__float_as_uint(n1.w), octinv4,
+		ux, uy, uz, r.idx, r.idy, r.idz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+	hitSlots |= slabHits4<4>(
 		negx ? qhix1 : qlox1, negy ? qhiy1 : qloy1, negz ? qhiz1 : qloz1,
 		negx ? qlox1 : qhix1, negy ? qloy1 : qhiy1, negz ? qloz1 : qhiz1,
-		RT_SLAB_ARGS, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
+		ux, uy, uz, r.idx, r.idy, r.idz, nx, ny, nz, fx, fy, fz, r.tmin, tfar);
 
+	const uint32_t imask = ebits >> 24;
 	ngroup.x = __float_as_uint(n1.x);
-	ngroup.y = (hitmask & 0xff000000u) | (ebits >> 24);
-	triBase = __float_as_uint(n1.y);
-	triHits = hitmask & 0x00ffffffu;
+	ngroup.y = (permuteByOctant(hitSlots & imask, r.octinv) << 24) | imask;
+	leaves.valid = __float_as_uint(n1.z);
+	leaves.bits = expandSlotsToTriples(hitSlots) & leaves.valid;   // (an inner or empty slot has no valid bits)
+	leaves.triBase = __float_as_uint(n1.y);
 }
 
 struct TriHit {
@@ -230,43 +239,19 @@ struct TravResult {
 	}
 };
 
-// The triangles of one node's leaf children (bits of triHits, relative to triBase) against the ray; returns true when the
-// traversal may stop (any hit accepted).  RT_TRI_PIPE: the next triangle's record is requested before the current one is
-// tested, so its L1 / L2 latency overlaps the test instead of following it (the loop runs at ~8 of 32 lanes and a third of the
-// traversal kernels' stall samples sit on these loads, profiles/r2_03_*).
+// The hit leaf triangles of one node against the ray; returns true when the traversal may stop (any hit accepted).
 template <int MODE>
-RT_DEV bool triLoop(const SceneView& s, const TravRay& r, uint32_t triBase, uint32_t triHits, float tmaxOrig, TravResult& res, uint32_t& triTests) {
-#ifdef RT_TRI_PIPE
-	if (!triHits) return false;
-	TriData cur = loadTri(s, triBase + uint32_t(__ffs(int(triHits))) - 1u);
-	triHits &= triHits - 1u;
-	for (;;) {
-		const bool more = triHits != 0u;
-		TriData nxt = cur;
-		if (more) {
-			nxt = loadTri(s, triBase + uint32_t(__ffs(int(triHits))) - 1u);
-			triHits &= triHits - 1u;
-		}
+RT_DEV bool triLoop(const SceneView& s, const TravRay& r, LeafHits leaves, float tmaxOrig, TravResult& res, uint32_t& triTests) {
+	while (leaves.bits) {
+		const uint32_t one = 1u << (31u - uint32_t(__clz(int(leaves.bits))));
+		leaves.bits ^= one;
 		triTests++;
 		TriHit h;
-		if (triTestData(cur, r.o, r.d, r.tmin, tmaxOrig, h)) {
-			if (res.accept<MODE>(h)) return true;
-		}
-		if (!more) return false;
-		cur = nxt;
-	}
-#else
-	while (triHits) {
-		const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
-		triHits &= triHits - 1u;
-		triTests++;
-		TriHit h;
-		if (triTest(s, r, triBase + i, tmaxOrig, h)) {
+		if (triTest(s, r, leaves.triBase + uint32_t(__popc(leaves.valid & (one - 1u))), tmaxOrig, h)) {
 			if (res.accept<MODE>(h)) return true;
 		}
 	}
 	return false;
-#endif
 }
 
 // One ray per thread, run to completion (the per-pixel passes call this in line).
@@ -287,26 +272,17 @@ RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tm
 	uint2 ngroup = make_uint2(0u, 0x80000000u);
 
 	for (;;) {
-		uint32_t triBase = 0, triHits = 0;
+		LeafHits leaves{ 0u, 0u, 0u };
 		if (ngroup.y > 0x00ffffffu) {
-			nodeStep(s, r, res.bestT, ngroup, stack, sp, triBase, triHits);
+			nodeStep(s, r, res.bestT, ngroup, stack, sp, leaves);
 			nodeVisits++;
 		}
-		while (triHits) {
-			const uint32_t i = uint32_t(__ffs(int(triHits))) - 1u;
-			triHits &= triHits - 1u;
-			triTests++;
-			TriHit h;
-			if (triTest(s, r, triBase + i, tmaxOrig, h)) {
-				if (res.accept<MODE>(h)) goto done;
-			}
-		}
+		if (triLoop<MODE>(s, r, leaves, tmaxOrig, res, triTests)) break;
 		if (ngroup.y <= 0x00ffffffu) {
 			if (sp == 0) break;
 			ngroup = stack[--sp];
 		}
 	}
-done:
 	if (s.counters != nullptr) {
 		atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
 		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);

@@ -649,36 +649,9 @@ __global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_const
 	shadeAndContinue(f, s, set, st, surf, mat, vo, pix, slot);
 }
 
-#ifdef RT_SURFACE_KERNEL
-// Experiment scaffold (not measured yet; build with `make EXTRA=-DRT_SURFACE_KERNEL LIBDIR=... BUILD=...`):
-// the surface fetch of every hit of the bounce (hit -> instance -> indices -> vertices -> material -> texture, a chain of
-// dependent gathers) in a light kernel of its own at high occupancy; grisBounceKernel then reads the 48-byte surface as a
-// coalesced stream.  The planes live in the reuse passes' task buffer, which is idle during path tracing.
-constexpr int SurfaceBlock = 256;
-__global__ void __launch_bounds__(SurfaceBlock) grisSurfaceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, int bounce) {
-	const uint32_t n = f.wf.counters[4 * bounce];
-	const size_t plane = size_t(f.ru.capacity) * 3;
-	for (uint32_t slotIdx = blockIdx.x * SurfaceBlock + threadIdx.x; slotIdx < n; slotIdx += gridDim.x * SurfaceBlock) {
-		const RptIntersection hit = f.wf.hits[slotIdx];
-		if (hit.instanceIdx == InvalidHitIndex) continue;
-		Surface surf;
-		loadSurfaceInfo(s, hit, surf);
-		float4* w = f.ru.task + slotIdx;
-		w[0] = make_float4(surf.pos.x, surf.pos.y, surf.pos.z, __uint_as_float(surf.matIndex));
-		w[plane] = make_float4(surf.norm.x, surf.norm.y, surf.norm.z, __uint_as_float(surf.isLight ? 1u : 0u));
-		w[2 * plane] = make_float4(surf.albedo.x, surf.albedo.y, surf.albedo.z, 0.f);
-	}
-}
-RT_DEV void loadStoredSurface(const FrameView& f, uint32_t slotIdx, Surface& surf) {
-	const size_t plane = size_t(f.ru.capacity) * 3;
-	const float4* w = f.ru.task + slotIdx;
-	const float4 a = w[0], b = w[plane], c = w[2 * plane];
-	surf.pos = f3(a); surf.matIndex = __float_as_uint(a.w);
-	surf.norm = f3(b); surf.isLight = __float_as_uint(b.w) != 0u;
-	surf.albedo = f3(c);
-}
-#endif
-
+// (Measured and rejected, profiles/r2_05_*: the surface fetch of every hit in a light kernel of its own at high occupancy, so that
+// this kernel reads a 48-byte surface as a coalesced stream: 2.07 -> 2.10 ms per frame — the extra 96 B per vertex through HBM cost
+// what the shorter gather chain saved.)
 // bounce >= 1: one thread per slot of the bounce's extension queue
 __global__ void __launch_bounds__(ShadeBlock, RT_BOUNCE_MINBLOCKS) grisBounceKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set, int bounce) {
 	const uint32_t n = f.wf.counters[4 * bounce];
@@ -699,11 +672,7 @@ __global__ void __launch_bounds__(ShadeBlock, RT_BOUNCE_MINBLOCKS) grisBounceKer
 		const RptIntersection hit = f.wf.hits[slotIdx];
 		if (hit.instanceIdx == InvalidHitIndex) { finishPath(cur, pix, st, slot); continue; }   // left the scene (:92-94)
 		Surface surf;
-#ifdef RT_SURFACE_KERNEL
-		loadStoredSurface(f, slotIdx, surf);
-#else
 		loadSurfaceInfo(s, hit, surf);
-#endif
 		const Mat mat = loadMaterial(s, surf.matIndex);
 		VertexOut vo;
 		vo.lightRandSample = make_float4(0.f, 0.f, 0.f, 0.f); vo.resvRandSample = 0.f;
@@ -1146,10 +1115,6 @@ void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const Rp
 		if (bounce < 15) launchTraceQueueClosest(s, f.wf.rays[bounce & 1], c + 0, 0, c + 2, f.wf.hits, st);
 		if (overlap) cudaStreamWaitEvent(st, join, 0);
 		if (clock) clock->tick(RPT_KERNEL_GRIS_BOUNCE);
-#ifdef RT_SURFACE_KERNEL
-		static const int surfaceBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSurfaceKernel), SurfaceBlock);
-		grisSurfaceKernel<<<surfaceBlocks, SurfaceBlock, 0, st>>>(f, s, bounce);
-#endif
 		grisBounceKernel<<<bounceBlocks, ShadeBlock, 0, st>>>(f, s, p, bounce);
 	}
 }

@@ -14,14 +14,19 @@ constexpr float MaxRayDistance = 1e7f;
 constexpr int WorkCounterCount = 16;
 constexpr float BaryEps = 1e-4f;   // tolerance of the triangle test, see bvh_traverse.cuh
 
-// 80-byte compressed 8-wide BVH node (Ylitie, Karras, Laine 2017): child boxes quantised to 8 bits relative
+// 80-byte compressed 8-wide BVH node (after Ylitie, Karras, Laine 2017): child boxes quantised to 8 bits relative
 // to the node origin p with per-axis power-of-two scale 2^(e-127).
-//   n0 = {p.x, p.y, p.z, e.x | e.y<<8 | e.z<<16 | imask<<24}
-//   n1 = {childBase, triBase, meta[0..3], meta[4..7]}
+//   n0 = {p.x, p.y, p.z, E.x | E.y<<8 | E.z<<16 | imask<<24}     E = e + 15 (0: flat axis, step 0) — the biased exponent is
+//                                                                  the traversal's mantissa-insertion unit (bvh_traverse.cuh)
+//   n1 = {childBase, triBase, leafTris, 0}
 //   n2 = {qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7]}
 //   n3 = {qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7]}
 //   n4 = {qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7]}
-// meta[i]: empty 0; inner child (001 << 5) | (24 + slot); leaf (unary tri count << 5) | first-triangle offset
+// imask bit s: slot s holds an inner child (the inner children are nodes childBase + rank of s among the imask bits);
+// leafTris bit 3s+k: the leaf in slot s has a triangle k (at most 3); the triangles are stored from triBase on in bit order;
+// an empty slot has an inverted box (qlo = 255, qhi = 0), which no ray interval can enter.
+// The box test yields one hit bit per SLOT; nothing per child is decoded unless it is hit (the 2017 layout's per-child
+// meta byte cost five ALU instructions per child and node, hit or not: profiles/r2_06_*).
 struct __align__(16) WideNode {
 	float4 n0, n1, n2, n3, n4;
 };
