@@ -59,11 +59,13 @@ RT_DEV uint32_t slabHits4(uint32_t qnx, uint32_t qny, uint32_t qnz, uint32_t qfx
 // bit (s ^ o) of the result = bit s of x, for an 8-bit mask and o in 0..7: slot order -> near-to-far order of a ray whose
 // direction octant is o (three conditional swaps: neighbours, pairs, nibbles)
 RT_DEV uint32_t permuteByOctant(uint32_t x, uint32_t o) {
-	const uint32_t x1 = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+	// (each swap is one bit-select of the two shifted copies; the bits a left shift carries past bit 7 fall on the side of the
+	// select that takes the right-shifted copy, so the result stays an 8-bit mask)
+	const uint32_t x1 = ((x << 1) & 0xaaaaaaaau) | ((x >> 1) & 0x55555555u);
 	x = (o & 1u) ? x1 : x;
-	const uint32_t x2 = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+	const uint32_t x2 = ((x << 2) & 0xccccccccu) | ((x >> 2) & 0x33333333u);
 	x = (o & 2u) ? x2 : x;
-	const uint32_t x4 = ((x & 0x0fu) << 4) | (x >> 4);
+	const uint32_t x4 = ((x << 4) & 0xf0f0f0f0u) | ((x >> 4) & 0x0f0f0f0fu);
 	return (o & 4u) ? x4 : x;
 }
 
@@ -94,17 +96,11 @@ RT_DEV TravRay makeTravRay(float3 o, float tmin, float3 d) {
 	r.o = o; r.d = d; r.tmin = tmin;
 	// reciprocal direction; components too close to zero are pushed away from it so 1/d stays finite
 	const float tiny = 1e-20f;
-#ifdef RT_FAST_RCP
 	// the reciprocal direction only feeds the conservative box tests (never the triangle test): MUFU.RCP's 1 ulp is inside the
-	// slab padding of nodeStep (1e-6 relative against ~3.6e-7 of accumulated rounding), and saves three IEEE divisions per ray
+	// slab padding of nodeStep (1e-6 relative against ~5e-7 of accumulated rounding), and saves three IEEE divisions per ray
 	r.idx = fastRcp(abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
 	r.idy = fastRcp(abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
 	r.idz = fastRcp(abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-#else
-	r.idx = 1.0f / (abs_(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-	r.idy = 1.0f / (abs_(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-	r.idz = 1.0f / (abs_(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-#endif
 	r.octinv = 7u ^ ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
 	return r;
 }
@@ -128,7 +124,7 @@ RT_DEV uint32_t expandSlotsToTriples(uint32_t x) {
 // group is pushed first.  Precondition: ngroup.y > 0x00ffffff.
 template <typename Stack>
 RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, LeafHits& leaves) {
-	const bool negx = r.idx < 0.0f, negy = r.idy < 0.0f, negz = r.idz < 0.0f;
+	const bool negx = !(r.octinv & 1u), negy = !(r.octinv & 2u), negz = !(r.octinv & 4u);   // (makeTravRay: octinv = 7 ^ sign bits of 1/d)
 	const uint32_t hits = ngroup.y;
 	const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
 	ngroup.y &= ~(1u << bit);
@@ -144,7 +140,7 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	//   1e-6 (255 |s| + |h|)  rounding of S, h and of the plane fma;   0.005 |s| >= 2 x 2^-9 |s|  the two roundings of N = (h - S) -+ pad
 	const uint32_t ux = (ebits & 0xffu) << 23, uy = (ebits & 0xff00u) << 15, uz = (ebits & 0xff0000u) << 7;
 	const float Sx = __uint_as_float(ux) * r.idx, Sy = __uint_as_float(uy) * r.idy, Sz = __uint_as_float(uz) * r.idz;
-	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;
+	const float hx = (n0.x - r.o.x) * r.idx, hy = (n0.y - r.o.y) * r.idy, hz = (n0.z - r.o.z) * r.idz;   // (not p/d - o/d: that cancels)
 	constexpr float PadPerUnit = (255.0e-6f + 0.005f) / 32768.0f;
 	const float padx = fma_(abs_(hx), 1e-6f, abs_(Sx) * PadPerUnit);
 	const float pady = fma_(abs_(hy), 1e-6f, abs_(Sy) * PadPerUnit);
