@@ -352,48 +352,53 @@ __global__ void __launch_bounds__(64) collapseKernel(uint32_t numTasks, const ui
 	wide[task.y] = out;
 }
 
-template <typename T>
-cudaError_t devAlloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
-
-} // namespace
-
-cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* out) {
-	const uint32_t N = in.numTris;
-	*out = BuildOutputs{};
-	if (N == 0) {
-		// empty scene: one node without children, so traversal terminates immediately
-		CK(devAlloc(&out->nodes, 1));
-		CK(devAlloc(&out->tris, 1));
-		CK(cudaMemsetAsync(out->nodes, 0, sizeof(WideNode), stream));
-		out->numNodes = 1;
-		return cudaStreamSynchronize(stream);
+// scratch allocations of one build: freed on every path out of it (an early return on a CUDA error — the likeliest being out of
+// memory on a large scene — must not leak gigabytes the context could never get back)
+struct Scratch {
+	std::vector<void*> ptrs;
+	~Scratch() { for (void* p : ptrs) cudaFree(p); }
+	template <typename T>
+	cudaError_t alloc(T** p, size_t n) {
+		void* q = nullptr;
+		cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+		if (e == cudaSuccess) { ptrs.push_back(q); *p = static_cast<T*>(q); }
+		return e;
 	}
-	cudaEvent_t ev0, ev1;
-	CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
-	CK(cudaEventRecord(ev0, stream));
+	template <typename T>
+	T* keep(T* p) {   // ownership passes to the caller
+		ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), static_cast<void*>(p)), ptrs.end());
+		return p;
+	}
+};
 
-	TriRecord* trisFlat = nullptr; float4 *leafLo = nullptr, *leafHi = nullptr, *nodeLo = nullptr, *nodeHi = nullptr;
-	uint32_t *bounds = nullptr, *valsIn = nullptr, *valsOut = nullptr, *nodeCount = nullptr, *clA = nullptr, *clB = nullptr, *nearest = nullptr;
+struct Events {
+	cudaEvent_t a = nullptr, b = nullptr;
+	~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+// Steps 2-4 for N primitives given as boxes (leafLo / leafHi, w lanes as flattenKernel writes them), their 48-byte records
+// in the same order and the bounds of all of them: Morton sort, PLOC, collapse.  The records come out in leaf order.
+cudaError_t buildFromLeaves(uint32_t N, const TriRecord* prims, const float4* leafLo, const float4* leafHi, const uint32_t* bounds,
+                            cudaStream_t stream, BuildOutputs* out) {
+	Scratch sc;
+	float4 *nodeLo = nullptr, *nodeHi = nullptr;
+	uint32_t *valsIn = nullptr, *valsOut = nullptr, *nodeCount = nullptr, *clA = nullptr, *clB = nullptr, *nearest = nullptr;
 	uint64_t *keysIn = nullptr, *keysOut = nullptr, *flags = nullptr, *prefix = nullptr;
 	void* cubTemp = nullptr;
-	CK(devAlloc(&trisFlat, N)); CK(devAlloc(&leafLo, N)); CK(devAlloc(&leafHi, N));
-	CK(devAlloc(&nodeLo, 2 * size_t(N))); CK(devAlloc(&nodeHi, 2 * size_t(N))); CK(devAlloc(&nodeCount, 2 * size_t(N)));
-	CK(devAlloc(&bounds, 8)); CK(devAlloc(&valsIn, N)); CK(devAlloc(&valsOut, N));
-	CK(devAlloc(&keysIn, N)); CK(devAlloc(&keysOut, N));
-	CK(devAlloc(&clA, N)); CK(devAlloc(&clB, N)); CK(devAlloc(&nearest, N));
-	CK(devAlloc(&flags, size_t(N) + 1)); CK(devAlloc(&prefix, size_t(N) + 1));
+	CK(sc.alloc(&nodeLo, 2 * size_t(N))); CK(sc.alloc(&nodeHi, 2 * size_t(N))); CK(sc.alloc(&nodeCount, 2 * size_t(N)));
+	CK(sc.alloc(&valsIn, N)); CK(sc.alloc(&valsOut, N));
+	CK(sc.alloc(&keysIn, N)); CK(sc.alloc(&keysOut, N));
+	CK(sc.alloc(&clA, N)); CK(sc.alloc(&clB, N)); CK(sc.alloc(&nearest, N));
+	CK(sc.alloc(&flags, size_t(N) + 1)); CK(sc.alloc(&prefix, size_t(N) + 1));
 
-	const uint32_t initBounds[8] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u };
-	CK(cudaMemcpyAsync(bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, stream));
 	const uint32_t B = 256, G = (N + B - 1) / B;
-	flattenKernel<<<G, B, 0, stream>>>(in, trisFlat, leafLo, leafHi, bounds);
 	mortonKernel<<<G, B, 0, stream>>>(N, leafLo, leafHi, bounds, keysIn, valsIn);
 
 	size_t sortBytes = 0, scanBytes = 0;
 	CK(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keysIn, keysOut, valsIn, valsOut, int(N), 0, 63, stream));
 	CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, flags, prefix, int(N) + 1, stream));
 	const size_t tempBytes = std::max(sortBytes, scanBytes);
-	CK(cudaMalloc(&cubTemp, tempBytes));
+	CK(sc.alloc(reinterpret_cast<char**>(&cubTemp), tempBytes));
 	size_t tb = tempBytes;
 	CK(cub::DeviceRadixSort::SortPairs(cubTemp, tb, keysIn, keysOut, valsIn, valsOut, int(N), 0, 63, stream));
 	initLeavesKernel<<<G, B, 0, stream>>>(N, valsOut, leafLo, leafHi, nodeLo, nodeHi, nodeCount, clA);
@@ -419,19 +424,22 @@ cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* o
 		std::swap(cur, nxt);
 	}
 	const uint32_t root = (N == 1) ? 0u : (N + nodesCreated - 1);
+	float4 rootBox[2];
+	CK(cudaMemcpyAsync(&rootBox[0], nodeLo + root, sizeof(float4), cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(&rootBox[1], nodeHi + root, sizeof(float4), cudaMemcpyDeviceToHost, stream));
 
 	// collapse, level by level
 	WideNode* wide = nullptr; TriRecord* trisOut = nullptr; uint2 *qA = nullptr, *qB = nullptr; CollapseCounters* cc = nullptr;
-	CK(devAlloc(&wide, size_t(N) + 1)); CK(devAlloc(&trisOut, N)); CK(devAlloc(&qA, size_t(N) + 1)); CK(devAlloc(&qB, size_t(N) + 1));
-	CK(devAlloc(&cc, 1));
+	CK(sc.alloc(&wide, size_t(N) + 1)); CK(sc.alloc(&trisOut, N)); CK(sc.alloc(&qA, size_t(N) + 1)); CK(sc.alloc(&qB, size_t(N) + 1));
+	CK(sc.alloc(&cc, 1));
 	const CollapseCounters cc0 = { 1u, 0u, 0u, 0u };
 	CK(cudaMemcpyAsync(cc, &cc0, sizeof(cc0), cudaMemcpyHostToDevice, stream));
 	const uint2 rootTask = make_uint2(root, 0u);
 	CK(cudaMemcpyAsync(qA, &rootTask, sizeof(rootTask), cudaMemcpyHostToDevice, stream));
 	const uint32_t leafMax = getenv("RPT_LEAF_MAX") ? std::min(std::max(uint32_t(atoi(getenv("RPT_LEAF_MAX"))), 1u), 3u) : 3u;   // (build-time experiment switch)
-	uint32_t numTasks = 1;
+	uint32_t numTasks = 1, depth = 0;
 	while (numTasks) {
-		collapseKernel<<<(numTasks + 63) / 64, 64, 0, stream>>>(numTasks, qA, qB, N, nodeLo, nodeHi, nodeCount, trisFlat, wide, trisOut, cc, leafMax);
+		collapseKernel<<<(numTasks + 63) / 64, 64, 0, stream>>>(numTasks, qA, qB, N, nodeLo, nodeHi, nodeCount, prims, wide, trisOut, cc, leafMax);
 		CollapseCounters h;
 		CK(cudaMemcpyAsync(&h, cc, sizeof(h), cudaMemcpyDeviceToHost, stream));
 		CK(cudaStreamSynchronize(stream));
@@ -439,23 +447,217 @@ cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* o
 		out->numNodes = h.numNodes;
 		CK(cudaMemsetAsync(&cc->nextCount, 0, sizeof(uint32_t), stream));
 		std::swap(qA, qB);
+		depth++;
 	}
 	CK(cudaGetLastError());
+	// The traversal pushes at most one deferred node group per level of the wide tree (the rest of the group a child was popped
+	// from), so the depth bounds the stack.  A tree deeper than the stack (PLOC puts no bound on pathological input) would
+	// silently drop subtrees, so it is an error here instead.
+	if (depth > uint32_t(MaxWideTreeDepth)) return cudaErrorInvalidValue;
+	out->depth = depth;
+	out->rootLo = make_float3(rootBox[0].x, rootBox[0].y, rootBox[0].z);
+	out->rootHi = make_float3(rootBox[1].x, rootBox[1].y, rootBox[1].z);
 
 	// shrink the node array to its final size
-	CK(devAlloc(&out->nodes, out->numNodes));
-	CK(cudaMemcpyAsync(out->nodes, wide, size_t(out->numNodes) * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream));
-	out->tris = trisOut;
-	out->numTris = N;
-	CK(cudaEventRecord(ev1, stream));
+	WideNode* nodes = nullptr;
+	CK(sc.alloc(&nodes, out->numNodes));
+	CK(cudaMemcpyAsync(nodes, wide, size_t(out->numNodes) * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream));
 	CK(cudaStreamSynchronize(stream));
-	CK(cudaEventElapsedTime(&out->buildMs, ev0, ev1));
-	cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+	out->nodes = sc.keep(nodes);
+	out->tris = sc.keep(trisOut);
+	out->numTris = N;
+	return cudaSuccess;
+}
 
-	cudaFree(trisFlat); cudaFree(leafLo); cudaFree(leafHi); cudaFree(nodeLo); cudaFree(nodeHi); cudaFree(nodeCount);
-	cudaFree(bounds); cudaFree(valsIn); cudaFree(valsOut); cudaFree(keysIn); cudaFree(keysOut);
-	cudaFree(clA); cudaFree(clB); cudaFree(nearest); cudaFree(flags); cudaFree(prefix); cudaFree(cubTemp);
-	cudaFree(wide); cudaFree(qA); cudaFree(qB); cudaFree(cc);
+
+// ---- two-level: instance records, TLAS leaf boxes ---------------------------------------------------------------------------
+__global__ void rebaseKernel(WideNode* __restrict__ nodes, uint32_t n, uint32_t nodeOffset, uint32_t triOffset) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 n1 = nodes[i].n1;
+	n1.x = __uint_as_float(__float_as_uint(n1.x) + nodeOffset);
+	n1.y = __uint_as_float(__float_as_uint(n1.y) + triOffset);
+	nodes[i].n1 = n1;
+}
+
+// record k: k == 0 the light triangles (world space), k >= 1 object instance k - 1
+__global__ void instanceRecordKernel(uint32_t count, const RptObjectInstance* __restrict__ instances, const uint32_t* __restrict__ meshOfRecord,
+                                     const BlasInfo* __restrict__ blas, const uint32_t* __restrict__ triOffsets,
+                                     InstanceRecord* __restrict__ records, TriRecord* __restrict__ prims,
+                                     float4* __restrict__ leafLo, float4* __restrict__ leafHi, uint32_t* __restrict__ bounds) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= count) return;
+	const BlasInfo b = blas[meshOfRecord[k]];
+	InstanceRecord r;
+	r.r0 = make_float4(1.f, 0.f, 0.f, 0.f); r.r1 = make_float4(0.f, 1.f, 0.f, 0.f); r.r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+	r.rootNode = b.numTris ? b.rootNode : 0xffffffffu;
+	r.customIndex = k; r.flatBase = 0; r.pad = 0;
+	float3 lo = b.lo, hi = b.hi;
+	if (k > 0) {
+		const RptObjectInstance& I = instances[k - 1];
+		const float* m = I.transformInv;   // column-major
+		r.r0 = make_float4(m[0], m[4], m[8], m[12]);
+		r.r1 = make_float4(m[1], m[5], m[9], m[13]);
+		r.r2 = make_float4(m[2], m[6], m[10], m[14]);
+		r.flatBase = triOffsets[k - 1];
+		lo = f3(FLT_MAX); hi = f3(-FLT_MAX);
+		for (int c = 0; c < 8; c++) {
+			const float3 p = xformPoint(I.transform, make_float3((c & 1) ? b.hi.x : b.lo.x, (c & 2) ? b.hi.y : b.lo.y, (c & 4) ? b.hi.z : b.lo.z));
+			lo = make_float3(fminf(lo.x, p.x), fminf(lo.y, p.y), fminf(lo.z, p.z));
+			hi = make_float3(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y), fmaxf(hi.z, p.z));
+		}
+		// the world-space box only has to contain what the object-space traversal can hit: padded for the rounding of the two
+		// transforms (the ray goes through transformInv, the box through transform; the two need not be exact inverses)
+		const float ext = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+		const float3 pad = make_float3(1e-4f * ext + 1e-5f * (fmaxf(fabsf(lo.x), fabsf(hi.x)) + 1.0f),
+		                               1e-4f * ext + 1e-5f * (fmaxf(fabsf(lo.y), fabsf(hi.y)) + 1.0f),
+		                               1e-4f * ext + 1e-5f * (fmaxf(fabsf(lo.z), fabsf(hi.z)) + 1.0f));
+		lo = lo - pad; hi = hi + pad;
+	}
+	if (!(lo.x <= hi.x) || !isfinite(lo.x + lo.y + lo.z + hi.x + hi.y + hi.z)) {   // empty mesh / NaN transform: never entered
+		lo = f3(0.0f); hi = f3(0.0f);
+		r.rootNode = 0xffffffffu;
+	}
+	records[k] = r;
+	TriRecord t;
+	t.t0 = make_float4(0.f, 0.f, 0.f, __uint_as_float(k)); t.t1 = make_float4(0.f, 0.f, 0.f, 0.f); t.t2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(k));
+	prims[k] = t;
+	leafLo[k] = make_float4(lo.x, lo.y, lo.z, __uint_as_float(k));
+	leafHi[k] = make_float4(hi.x, hi.y, hi.z, __uint_as_float(0xffffffffu));
+	atomicMin(&bounds[0], floatFlip(lo.x)); atomicMin(&bounds[1], floatFlip(lo.y)); atomicMin(&bounds[2], floatFlip(lo.z));
+	atomicMax(&bounds[3], floatFlip(hi.x)); atomicMax(&bounds[4], floatFlip(hi.y)); atomicMax(&bounds[5], floatFlip(hi.z));
+}
+
+} // namespace
+
+cudaError_t buildBvh(const BuildInputs& in, cudaStream_t stream, BuildOutputs* out) {
+	const uint32_t N = in.numTris;
+	*out = BuildOutputs{};
+	Scratch sc;
+	if (N == 0) {
+		// empty scene: one node without children, so traversal terminates immediately
+		WideNode* nodes = nullptr; TriRecord* tris = nullptr;
+		CK(sc.alloc(&nodes, 1));
+		CK(sc.alloc(&tris, 1));
+		CK(cudaMemsetAsync(nodes, 0, sizeof(WideNode), stream));
+		CK(cudaStreamSynchronize(stream));
+		out->nodes = sc.keep(nodes); out->tris = sc.keep(tris);
+		out->numNodes = 1;
+		return cudaSuccess;
+	}
+	Events ev;
+	CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+	CK(cudaEventRecord(ev.a, stream));
+
+	TriRecord* trisFlat = nullptr; float4 *leafLo = nullptr, *leafHi = nullptr; uint32_t* bounds = nullptr;
+	CK(sc.alloc(&trisFlat, N)); CK(sc.alloc(&leafLo, N)); CK(sc.alloc(&leafHi, N)); CK(sc.alloc(&bounds, 8));
+	const uint32_t initBounds[8] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u };
+	CK(cudaMemcpyAsync(bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, stream));
+	flattenKernel<<<(N + 255) / 256, 256, 0, stream>>>(in, trisFlat, leafLo, leafHi, bounds);
+	CK(buildFromLeaves(N, trisFlat, leafLo, leafHi, bounds, stream, out));
+	CK(cudaEventRecord(ev.b, stream));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaEventElapsedTime(&out->buildMs, ev.a, ev.b));
+	return cudaSuccess;
+}
+
+void TwoLevelState::release() {
+	cudaFree(blasNodes); cudaFree(blasTris); cudaFree(tlasNodes); cudaFree(tlasLeaves); cudaFree(records); cudaFree(blasInfo); cudaFree(meshOfRecord);
+	*this = TwoLevelState{};
+}
+
+cudaError_t rebuildTlas(const BuildInputs& in, cudaStream_t stream, TwoLevelState* out) {
+	const uint32_t count = out->numRecords;
+	Scratch sc;
+	Events ev;
+	CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+	CK(cudaEventRecord(ev.a, stream));
+	TriRecord* prims = nullptr; float4 *leafLo = nullptr, *leafHi = nullptr; uint32_t* bounds = nullptr;
+	CK(sc.alloc(&prims, count)); CK(sc.alloc(&leafLo, count)); CK(sc.alloc(&leafHi, count)); CK(sc.alloc(&bounds, 8));
+	const uint32_t initBounds[8] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u };
+	CK(cudaMemcpyAsync(bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, stream));
+	instanceRecordKernel<<<(count + 127) / 128, 128, 0, stream>>>(count, in.instances, out->meshOfRecord, out->blasInfo, in.triOffsets,
+	                                                              out->records, prims, leafLo, leafHi, bounds);
+	BuildOutputs tl;
+	CK(buildFromLeaves(count, prims, leafLo, leafHi, bounds, stream, &tl));
+	cudaFree(out->tlasNodes); cudaFree(out->tlasLeaves);
+	out->tlasNodes = tl.nodes; out->tlasLeaves = tl.tris; out->numTlasNodes = tl.numNodes; out->tlasDepth = tl.depth;
+	if (out->tlasDepth + out->maxBlasDepth + 2 > uint32_t(MaxWideTreeDepth) + 2) return cudaErrorInvalidValue;   // (one stack for both levels)
+	CK(cudaEventRecord(ev.b, stream));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaEventElapsedTime(&out->tlasMs, ev.a, ev.b));
+	return cudaSuccess;
+}
+
+cudaError_t buildTwoLevel(const TwoLevelInputs& in, cudaStream_t stream, TwoLevelState* out) {
+	*out = TwoLevelState{};
+	struct Guard { TwoLevelState* s; bool ok = false; ~Guard() { if (!ok) s->release(); } } guard{ out };
+	Scratch sc;
+	Events ev;
+	CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+	CK(cudaEventRecord(ev.a, stream));
+	const uint32_t numMeshes = uint32_t(in.meshes.size());
+	const uint32_t numInstances = in.base.numInstances;
+
+	// one BLAS per unique mesh, built by the single-level builder from an identity pseudo-instance over the mesh's index
+	// range (object space), and one over the light triangles (world space)
+	std::vector<RptObjectInstance> pseudo(std::max(numMeshes, 1u));
+	for (uint32_t m = 0; m < numMeshes; m++) {
+		RptObjectInstance I{};
+		for (int d = 0; d < 4; d++) { I.transform[d * 5] = 1.0f; I.transformInv[d * 5] = 1.0f; I.transformInvT[d * 5] = 1.0f; }
+		I.indexOffset = in.meshes[m].indexOffset; I.indexCount = in.meshes[m].indexCount;
+		pseudo[m] = I;
+	}
+	RptObjectInstance* dPseudo = nullptr; uint32_t* dOffsets = nullptr;
+	CK(sc.alloc(&dPseudo, pseudo.size())); CK(sc.alloc(&dOffsets, 2));
+	CK(cudaMemcpyAsync(dPseudo, pseudo.data(), pseudo.size() * sizeof(RptObjectInstance), cudaMemcpyHostToDevice, stream));
+
+	std::vector<BuildOutputs> blas(numMeshes + 1);
+	struct BlasGuard { std::vector<BuildOutputs>& v; ~BlasGuard() { for (auto& b : v) { cudaFree(b.nodes); cudaFree(b.tris); } } } blasGuard{ blas };
+	std::vector<BlasInfo> info(numMeshes + 1);
+	uint64_t totalNodes = 0, totalTris = 0;
+	for (uint32_t m = 0; m <= numMeshes; m++) {
+		BuildInputs bi = in.base;
+		if (m < numMeshes) {
+			const uint32_t offs[2] = { 0u, in.meshes[m].indexCount / 3u };
+			CK(cudaMemcpyAsync(dOffsets, offs, sizeof(offs), cudaMemcpyHostToDevice, stream));
+			CK(cudaStreamSynchronize(stream));   // (offs is a stack variable)
+			bi.instances = dPseudo + m; bi.triOffsets = dOffsets; bi.numInstances = 1; bi.numLights = 0; bi.numTris = offs[1];
+		}
+		else { bi.numInstances = 0; bi.numTris = in.base.numLights; }
+		CK(buildBvh(bi, stream, &blas[m]));
+		info[m].rootNode = uint32_t(totalNodes); info[m].numTris = blas[m].numTris;
+		info[m].lo = blas[m].rootLo; info[m].hi = blas[m].rootHi;
+		totalNodes += blas[m].numNodes; totalTris += std::max(blas[m].numTris, 1u);
+		out->maxBlasDepth = std::max(out->maxBlasDepth, blas[m].depth);
+	}
+	if (totalNodes > 0x7fffffffull || totalTris > 0x7fffffffull) return cudaErrorInvalidValue;
+	CK(cudaMalloc(reinterpret_cast<void**>(&out->blasNodes), totalNodes * sizeof(WideNode)));
+	CK(cudaMalloc(reinterpret_cast<void**>(&out->blasTris), totalTris * sizeof(TriRecord)));
+	uint32_t nodeAt = 0, triAt = 0;
+	for (uint32_t m = 0; m <= numMeshes; m++) {
+		CK(cudaMemcpyAsync(out->blasNodes + nodeAt, blas[m].nodes, size_t(blas[m].numNodes) * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream));
+		if (blas[m].numTris) CK(cudaMemcpyAsync(out->blasTris + triAt, blas[m].tris, size_t(blas[m].numTris) * sizeof(TriRecord), cudaMemcpyDeviceToDevice, stream));
+		rebaseKernel<<<(blas[m].numNodes + 127) / 128, 128, 0, stream>>>(out->blasNodes + nodeAt, blas[m].numNodes, nodeAt, triAt);
+		nodeAt += blas[m].numNodes; triAt += std::max(blas[m].numTris, 1u);
+	}
+	out->numBlasNodes = uint32_t(totalNodes); out->numBlasTris = uint32_t(totalTris);
+
+	// records: [0] = lights (the last BLAS), [k + 1] = object instance k
+	std::vector<uint32_t> meshOfRecord(size_t(numInstances) + 1);
+	meshOfRecord[0] = numMeshes;
+	for (uint32_t k = 0; k < numInstances; k++) meshOfRecord[k + 1] = in.meshOfInstance[k];
+	out->numRecords = numInstances + 1;
+	CK(cudaMalloc(reinterpret_cast<void**>(&out->records), size_t(out->numRecords) * sizeof(InstanceRecord)));
+	CK(cudaMalloc(reinterpret_cast<void**>(&out->blasInfo), info.size() * sizeof(BlasInfo)));
+	CK(cudaMalloc(reinterpret_cast<void**>(&out->meshOfRecord), meshOfRecord.size() * sizeof(uint32_t)));
+	CK(cudaMemcpyAsync(out->blasInfo, info.data(), info.size() * sizeof(BlasInfo), cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(out->meshOfRecord, meshOfRecord.data(), meshOfRecord.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+	CK(cudaEventRecord(ev.b, stream));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaEventElapsedTime(&out->blasMs, ev.a, ev.b));
+	CK(rebuildTlas(in.base, stream, out));
+	guard.ok = true;
 	return cudaSuccess;
 }
 

@@ -38,6 +38,16 @@ struct __align__(16) TriRecord {
 	float4 t0, t1, t2;
 };
 
+// One entry per TLAS leaf primitive (two-level scenes): the ray is taken into the instance's object space and the BLAS below
+// rootNode is traversed there (bvh_traverse.cuh)
+struct __align__(16) InstanceRecord {
+	float4 r0, r1, r2;        // world -> object: rows of the 3x4 matrix
+	uint32_t rootNode;        // the BLAS root in SceneView::nodes (0xffffffff: nothing to traverse)
+	uint32_t customIndex;     // Intersection.instanceIdx: 0 = the light triangles, k + 1 = object instance k
+	uint32_t flatBase;        // flattened index of this instance's triangle 0 (tie order across instances)
+	uint32_t pad;
+};
+
 struct TextureView {
 	const uchar4* texels;
 	uint32_t width, height, filter;
@@ -47,6 +57,10 @@ struct TextureView {
 struct SceneView {
 	const WideNode* nodes;
 	const TriRecord* tris;
+	// two-level scenes only (tlasNodes != nullptr): nodes / tris then hold the BLASes in object space
+	const WideNode* tlasNodes;
+	const TriRecord* tlasLeaves;
+	const InstanceRecord* instRecords;
 	const RptMeshVertex* vertices;
 	const uint32_t* indices;
 	const RptMaterial* materials;
