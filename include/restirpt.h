@@ -172,7 +172,15 @@ typedef struct RptSceneDesc {
 	const RptTriangleLight* triangleLights;  uint32_t numTriangleLights;
 	const RptLightSampleTableElement* lightSampleTable;                  /* numTriangleLights + 1 entries */
 	const RptTextureDesc* textures;          uint32_t numTextures;
+	uint32_t flags;                          /* RptSceneFlags */
 } RptSceneDesc;
+
+/* Acceleration-structure arrangement.  Default (0): every instance flattened to world space under ONE wide BVH (the reference's
+ * loader never shares geometry between instances, src/Resource.cpp:183-184).  RPT_SCENE_TWO_LEVEL: the reference's own
+ * arrangement (src/Scene.cpp:448-547): one BLAS per unique (indexOffset, indexCount) range in object space, a BLAS of the light
+ * triangles (custom index 0) and a TLAS over the instances; rays are transformed at the instance boundary.  Memory is per
+ * unique mesh, and rpt_scene_update_instances only rebuilds the TLAS. */
+typedef enum RptSceneFlags { RPT_SCENE_TWO_LEVEL = 1 } RptSceneFlags;
 
 typedef enum RptBufferId {
 	RPT_BUF_DIRECT_OUTPUT = 0,    /* float4 / px   (layouts.glsl:180)      */
@@ -209,6 +217,13 @@ typedef struct RptBvhStats {
 	uint64_t triBytes;
 	float buildMs;            /* GPU time of the build (CUDA events) */
 	float sahCost;
+	/* two-level scenes (0 otherwise): numNodes / numTriangles / *Bytes above then count the BLASes, once per unique mesh */
+	uint32_t twoLevel;
+	uint32_t numMeshes;       /* BLASes, including the one of the light triangles */
+	uint32_t numTlasNodes;
+	uint32_t numInstanceRecords;
+	float tlasBuildMs;        /* instance records + TLAS: what rpt_scene_update_instances costs on a two-level scene */
+	uint32_t pad;
 } RptBvhStats;
 
 /* per-pass device timing (new): CUDA events recorded on the frame's stream around every pass launch */
@@ -250,11 +265,13 @@ const char* rpt_last_error(const RptCtx* ctx);  /* ctx may be NULL: last error o
 int rpt_version(void);
 
 /* ---- scene (replaces DeviceScene ctor, reference src/Scene.cpp:324-330: buffer upload + BLAS/TLAS build).
- * Builds the flattened world-space compressed wide BVH on the GPU. */
+ * Builds the compressed wide BVH(s) on the GPU: flattened to world space, or BLAS + TLAS (desc->flags).  The arrays are checked
+ * first (index / instance / material / texture / alias-table ranges): RPT_ERR_INVALID instead of an out-of-bounds device read. */
 int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* desc, RptScene** out);
 void rpt_scene_destroy(RptScene* scene);
 /* dynamic scenes (new; the reference is static): new transforms / radiance of the object instances, same
- * geometry ranges; rebuilds the acceleration structure on the GPU.  Synchronises the device. */
+ * geometry ranges.  Flattened scenes rebuild the whole structure on the GPU; two-level scenes rebuild the instance records and
+ * the TLAS only.  The new state is committed only if the rebuild succeeds.  Synchronises the device. */
 int rpt_scene_update_instances(RptScene* scene, const RptObjectInstance* instances, uint32_t numInstances);
 int rpt_scene_bvh_stats(const RptScene* scene, RptBvhStats* out);
 

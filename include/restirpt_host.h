@@ -25,6 +25,10 @@ RhScene* rh_scene_load_xml(const char* path);
 RhScene* rh_scene_cornell(void);
 RhScene* rh_scene_room(uint32_t trisTarget, uint32_t seed);
 RhScene* rh_scene_field(uint32_t meshSubdiv, uint32_t gridN, uint32_t seed);
+/* the same field with ONE copy of the mesh referenced by every instance (BASELINE config 5's instanced variant) */
+RhScene* rh_scene_field_shared(uint32_t meshSubdiv, uint32_t gridN, uint32_t seed);
+/* ask rpt_scene_create for BLAS + TLAS (RPT_SCENE_TWO_LEVEL in the desc's flags) instead of the flattened structure */
+void rh_scene_set_two_level(RhScene* s, int on);
 void rh_scene_destroy(RhScene* s);
 void rh_scene_desc(const RhScene* s, RptSceneDesc* out);   /* pointers stay valid until rh_scene_destroy */
 void rh_scene_camera(const RhScene* s, RptCamera* out);

@@ -93,7 +93,7 @@ OrcScene* orc_scene_create(const RptSceneDesc* desc) {
 }
 void orc_scene_destroy(OrcScene* s) { delete s; }
 void orc_scene_set_brute_force(OrcScene* s, int on) { s->scene.bruteForce = on != 0; }
-uint32_t orc_scene_num_triangles(const OrcScene* s) { return uint32_t(s->scene.tris.size()); }
+uint32_t orc_scene_num_triangles(const OrcScene* s) { return s->scene.numFlatTris; }
 
 OrcFrame* orc_frame_create(uint32_t w, uint32_t h) {
 	OrcFrame* f = new OrcFrame;

@@ -26,33 +26,78 @@ void Scene::build(const RptSceneDesc& d) {
 		srgbToLinear[i] = float(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
 	}
 
-	// flattened world-space triangle list.  The reference keeps one BLAS per model plus a light BLAS under a
-	// TLAS (src/Scene.cpp:448-547); every instance has its own geometry, so flattening loses nothing.
-	tris.clear();
-	for (uint32_t i = 0; i < lights.size(); i++) {   // light BLAS: custom index 0, primitive i
-		const RptTriangleLight& L = lights[i];
-		WorldTri t;
-		t.v0 = V3(L.v0); t.e1 = V3(L.v1) - V3(L.v0); t.e2 = V3(L.v2) - V3(L.v0);
-		t.instanceIdx = 0; t.triangleIdx = i;
-		tris.push_back(t);
+	twoLevel = (d.flags & RPT_SCENE_TWO_LEVEL) != 0;
+	sets.clear(); records.clear();
+	auto lightSet = [&](TriSet& set) {
+		for (uint32_t i = 0; i < lights.size(); i++) {   // light BLAS: custom index 0, primitive i
+			const RptTriangleLight& L = lights[i];
+			WorldTri t;
+			t.v0 = V3(L.v0); t.e1 = V3(L.v1) - V3(L.v0); t.e2 = V3(L.v2) - V3(L.v0);
+			t.instanceIdx = 0; t.triangleIdx = i;
+			set.tris.push_back(t);
+		}
+	};
+	if (!twoLevel) {
+		// flattened world-space triangle list: lights first (instance 0), then every object instance in order
+		sets.emplace_back();
+		TriSet& set = sets[0];
+		lightSet(set);
+		for (uint32_t k = 0; k < instances.size(); k++) {
+			const RptObjectInstance& inst = instances[k];
+			for (uint32_t j = 0; j < inst.indexCount / 3; j++) {
+				vec3 w[3];
+				for (int c = 0; c < 3; c++) {
+					const RptMeshVertex& mv = vertices[indices[inst.indexOffset + j * 3 + c]];
+					w[c] = xformPoint(inst.transform, V3(mv.pos));
+				}
+				WorldTri t;
+				t.v0 = w[0]; t.e1 = w[1] - w[0]; t.e2 = w[2] - w[0];
+				t.instanceIdx = k + 1; t.triangleIdx = j;
+				set.tris.push_back(t);
+			}
+		}
+		numFlatTris = uint32_t(set.tris.size());
+		set.buildTree();
+		return;
 	}
-	firstObjectTri = uint32_t(tris.size());
+	// two-level: set 0 = lights (world space), then one object-space set per unique (indexOffset, indexCount)
+	sets.emplace_back();
+	lightSet(sets[0]);
+	InstanceRecord lr{};
+	lr.r[0][0] = lr.r[1][1] = lr.r[2][2] = 1.0f;
+	lr.set = 0; lr.customIndex = 0; lr.flatBase = 0;
+	records.push_back(lr);
+	std::vector<std::pair<uint32_t, uint32_t>> ranges;
+	uint32_t flat = uint32_t(lights.size());
 	for (uint32_t k = 0; k < instances.size(); k++) {
 		const RptObjectInstance& inst = instances[k];
-		for (uint32_t j = 0; j < inst.indexCount / 3; j++) {
-			vec3 w[3];
-			for (int c = 0; c < 3; c++) {
-				const RptMeshVertex& mv = vertices[indices[inst.indexOffset + j * 3 + c]];
-				w[c] = xformPoint(inst.transform, V3(mv.pos));
+		const auto key = std::make_pair(inst.indexOffset, inst.indexCount);
+		uint32_t m = uint32_t(std::find(ranges.begin(), ranges.end(), key) - ranges.begin());
+		if (m == ranges.size()) {
+			ranges.push_back(key);
+			sets.emplace_back();
+			TriSet& set = sets.back();
+			for (uint32_t j = 0; j < inst.indexCount / 3; j++) {
+				vec3 w[3];
+				for (int c = 0; c < 3; c++) w[c] = V3(vertices[indices[inst.indexOffset + j * 3 + c]].pos);
+				WorldTri t;
+				t.v0 = w[0]; t.e1 = w[1] - w[0]; t.e2 = w[2] - w[0];
+				t.instanceIdx = 0; t.triangleIdx = j;
+				set.tris.push_back(t);
 			}
-			WorldTri t;
-			t.v0 = w[0]; t.e1 = w[1] - w[0]; t.e2 = w[2] - w[0];
-			t.instanceIdx = k + 1; t.triangleIdx = j;
-			tris.push_back(t);
 		}
+		InstanceRecord r{};
+		const float* mi = inst.transformInv;   // column-major
+		for (int row = 0; row < 3; row++) for (int c = 0; c < 4; c++) r.r[row][c] = mi[c * 4 + row];
+		r.set = m + 1; r.customIndex = k + 1; r.flatBase = flat;
+		records.push_back(r);
+		flat += inst.indexCount / 3;
 	}
+	numFlatTris = flat;
+	for (TriSet& set : sets) set.buildTree();
+}
 
-	// BVH2
+void Scene::TriSet::buildTree() {
 	const uint32_t n = uint32_t(tris.size());
 	order.resize(n);
 	std::vector<vec3> cen(n);
@@ -85,7 +130,7 @@ static void triBounds(const WorldTri& t, float lo[3], float hi[3]) {
 	}
 }
 
-void Scene::buildNode(uint32_t nodeIdx, uint32_t begin, uint32_t end, std::vector<vec3>& cen, int depth) {
+void Scene::TriSet::buildNode(uint32_t nodeIdx, uint32_t begin, uint32_t end, std::vector<vec3>& cen, int depth) {
 	float lo[3] = { 1e30f, 1e30f, 1e30f }, hi[3] = { -1e30f, -1e30f, -1e30f };
 	float clo[3] = { 1e30f, 1e30f, 1e30f }, chi[3] = { -1e30f, -1e30f, -1e30f };
 	for (uint32_t i = begin; i < end; i++) {
@@ -183,6 +228,59 @@ static inline bool degenerateRay(vec3 o, float tmin, vec3 d, float tmax) {
 	return !(tmin < tmax) || !(abs_(o.x) + abs_(o.y) + abs_(o.z) + abs_(d.x) + abs_(d.y) + abs_(d.z) < 3.0e38f);
 }
 
+template <typename TFar, typename Fn>
+void Scene::TriSet::candidates(vec3 o, vec3 d, float tmin, TFar tfar, bool brute, Fn fn) const {
+	if (brute) {
+		for (uint32_t i = 0; i < tris.size(); i++) fn(i);
+		return;
+	}
+	if (tris.empty()) return;
+	const double od[3] = { o.x, o.y, o.z };
+	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
+	uint32_t stack[128];
+	int sp = 0;
+	stack[sp++] = 0;
+	while (sp) {
+		const Node& n = nodes[stack[--sp]];
+		if (!hitBox(n, od, inv, double(tmin), double(tfar()))) continue;
+		if (n.count) {
+			for (uint32_t i = 0; i < n.count; i++) fn(order[n.left + i]);
+		}
+		else {
+			stack[sp++] = n.left;
+			stack[sp++] = n.left + 1;
+		}
+	}
+}
+
+// the ray in an instance's object space, in the fixed operation order of the numeric contract (CUDA: toObjectSpace)
+static inline void toObjectSpace(const Scene::InstanceRecord& rec, vec3 o, vec3 d, vec3& oo, vec3& od) {
+	const float (*r)[4] = rec.r;
+	oo = V3(fma_(r[0][2], o.z, fma_(r[0][1], o.y, fma_(r[0][0], o.x, r[0][3]))),
+	        fma_(r[1][2], o.z, fma_(r[1][1], o.y, fma_(r[1][0], o.x, r[1][3]))),
+	        fma_(r[2][2], o.z, fma_(r[2][1], o.y, fma_(r[2][0], o.x, r[2][3]))));
+	od = V3(fma_(r[0][2], d.z, fma_(r[0][1], d.y, r[0][0] * d.x)),
+	        fma_(r[1][2], d.z, fma_(r[1][1], d.y, r[1][0] * d.x)),
+	        fma_(r[2][2], d.z, fma_(r[2][1], d.y, r[2][0] * d.x)));
+}
+
+template <typename TFar, typename Fn>
+void Scene::forCandidates(vec3 o, vec3 d, float tmin, TFar tfar, Fn fn) const {
+	if (!twoLevel) {
+		const TriSet& set = sets[0];
+		set.candidates(o, d, tmin, tfar, bruteForce, [&](uint32_t i) { return fn(set.tris[i], i, set.tris[i].instanceIdx, o, d); });
+		return;
+	}
+	for (const InstanceRecord& rec : records) {
+		vec3 oo, od;
+		toObjectSpace(rec, o, d, oo, od);
+		// a NaN / infinite object-space ray (degenerate instance matrix) cannot pass the triangle test; the accelerated path skips it
+		if (!bruteForce && degenerateRay(oo, tmin, od, 1e30f)) continue;
+		const TriSet& set = sets[rec.set];
+		set.candidates(oo, od, tmin, tfar, bruteForce, [&](uint32_t i) { return fn(set.tris[i], rec.flatBase + i, rec.customIndex, oo, od); });
+	}
+}
+
 Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool skipLights) const {
 	counters.closestRays.fetch_add(1, std::memory_order_relaxed);
 	Intersection best;
@@ -191,97 +289,41 @@ Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool
 	best.triangleIdx = 0;
 	float bestT = tmax;
 	uint32_t bestId = 0xffffffffu;
-
-	auto test = [&](uint32_t id) {
-		const WorldTri& t = tris[id];
-		if (skipLights && t.instanceIdx == 0) return;
+	if (!bruteForce && degenerateRay(o, tmin, d, tmax)) return best;
+	forCandidates(o, d, tmin, [&] { return bestT; }, [&](const WorldTri& t, uint32_t id, uint32_t inst, vec3 ro, vec3 rd) {
+		if (skipLights && inst == 0) return;
 		float tt, u, v;
 		// candidates at exactly the current best distance are still considered (tie rule below)
-		if (intersectTri(t, o, d, tmin, tmax, tt, u, v)) {
+		if (intersectTri(t, ro, rd, tmin, tmax, tt, u, v)) {
 			if (tt < bestT || (tt == bestT && id < bestId)) {
 				bestT = tt; bestId = id;
 				best.bary = { u, v };
-				best.instanceIdx = t.instanceIdx;
+				best.instanceIdx = inst;
 				best.triangleIdx = t.triangleIdx;
 			}
 		}
-	};
-
-	if (bruteForce) {
-		for (uint32_t i = 0; i < tris.size(); i++) test(i);
-		return best;
-	}
-	if (tris.empty() || degenerateRay(o, tmin, d, tmax)) return best;
-	const double od[3] = { o.x, o.y, o.z };
-	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
-	uint32_t stack[128];
-	int sp = 0;
-	stack[sp++] = 0;
-	while (sp) {
-		const Node& n = nodes[stack[--sp]];
-		if (!hitBox(n, od, inv, double(tmin), double(bestT))) continue;
-		if (n.count) {
-			for (uint32_t i = 0; i < n.count; i++) test(order[n.left + i]);
-		}
-		else {
-			stack[sp++] = n.left;
-			stack[sp++] = n.left + 1;
-		}
-	}
+	});
 	return best;
 }
 
 bool Scene::traceShadow(vec3 o, float tmin, vec3 d, float tmax) const {
 	counters.shadowRays.fetch_add(1, std::memory_order_relaxed);
-	float tt, u, v;
-	if (bruteForce) {
-		for (const WorldTri& t : tris) if (intersectTri(t, o, d, tmin, tmax, tt, u, v)) return true;
-		return false;
-	}
-	if (tris.empty() || degenerateRay(o, tmin, d, tmax)) return false;
-	const double od[3] = { o.x, o.y, o.z };
-	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
-	uint32_t stack[128];
-	int sp = 0;
-	stack[sp++] = 0;
-	while (sp) {
-		const Node& n = nodes[stack[--sp]];
-		if (!hitBox(n, od, inv, double(tmin), double(tmax))) continue;
-		if (n.count) {
-			for (uint32_t i = 0; i < n.count; i++) {
-				if (intersectTri(tris[order[n.left + i]], o, d, tmin, tmax, tt, u, v)) return true;
-			}
-		}
-		else {
-			stack[sp++] = n.left;
-			stack[sp++] = n.left + 1;
-		}
-	}
-	return false;
+	if (!bruteForce && degenerateRay(o, tmin, d, tmax)) return false;
+	bool hit = false;
+	forCandidates(o, d, tmin, [&] { return hit ? -1.0f : tmax; }, [&](const WorldTri& t, uint32_t, uint32_t, vec3 ro, vec3 rd) {
+		float tt, u, v;
+		if (!hit && intersectTri(t, ro, rd, tmin, tmax, tt, u, v)) hit = true;   // (tfar < tmin from here on: every remaining box is culled)
+	});
+	return hit;
 }
 
 uint32_t Scene::countCandidates(vec3 o, vec3 d) const {
 	uint32_t count = 0;
-	float tt, u, v;
-	const double od[3] = { o.x, o.y, o.z };
-	const double inv[3] = { 1.0 / double(d.x), 1.0 / double(d.y), 1.0 / double(d.z) };
-	if (tris.empty() || degenerateRay(o, MinRayDistance, d, MaxRayDistance)) return 0;
-	uint32_t stack[128];
-	int sp = 0;
-	stack[sp++] = 0;
-	while (sp) {
-		const Node& n = nodes[stack[--sp]];
-		if (!hitBox(n, od, inv, double(MinRayDistance), double(MaxRayDistance))) continue;
-		if (n.count) {
-			for (uint32_t i = 0; i < n.count; i++) {
-				if (intersectTri(tris[order[n.left + i]], o, d, MinRayDistance, MaxRayDistance, tt, u, v)) count++;
-			}
-		}
-		else {
-			stack[sp++] = n.left;
-			stack[sp++] = n.left + 1;
-		}
-	}
+	if (degenerateRay(o, MinRayDistance, d, MaxRayDistance)) return 0;
+	forCandidates(o, d, MinRayDistance, [] { return MaxRayDistance; }, [&](const WorldTri& t, uint32_t, uint32_t, vec3 ro, vec3 rd) {
+		float tt, u, v;
+		if (intersectTri(t, ro, rd, MinRayDistance, MaxRayDistance, tt, u, v)) count++;
+	});
 	return count;
 }
 

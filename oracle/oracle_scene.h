@@ -48,14 +48,35 @@ struct Scene {
 	std::vector<Texture> textures;
 	float srgbToLinear[256];
 
-	std::vector<WorldTri> tris;
-	uint32_t firstObjectTri = 0;   // tris[0 .. firstObjectTri) are light triangles
-
-	// BVH2 over tris (median-of-centroid splits with SAH binning); only an accelerator for the brute-force
-	// definition below — both give the same answer by construction (conservative boxes, same tie rule)
+	// Single-level scenes: every instance flattened to world space (the reference never shares geometry between instances,
+	// src/Resource.cpp:183-184), one set.  Two-level scenes (RPT_SCENE_TWO_LEVEL — the reference's own BLAS / TLAS arrangement,
+	// src/Scene.cpp:448-547): the light triangles in world space (record 0) and one set per unique mesh in OBJECT space; a ray
+	// is taken into the object space of every instance (direction not renormalised, so t is shared) and the triangle test runs
+	// there.  Hit definition either way: the triangle test below, minimum t, ties to the lower flattened index.
+	//
+	// A set = triangles + a BVH2 (median-of-centroid splits with SAH binning), which is only an accelerator for the
+	// brute-force definition — both give the same answer by construction (conservative boxes, same tie rule).
 	struct Node { float lo[3], hi[3]; uint32_t left, count; };   // count > 0: leaf over order[left .. left+count)
-	std::vector<Node> nodes;
-	std::vector<uint32_t> order;
+	struct TriSet {
+		std::vector<WorldTri> tris;
+		std::vector<Node> nodes;
+		std::vector<uint32_t> order;
+		void buildTree();
+		void buildNode(uint32_t nodeIdx, uint32_t begin, uint32_t end, std::vector<vec3>& cen, int depth);
+		// calls fn(index in tris) for every triangle whose box the ray interval [tmin, tfar()] may enter (all of them when brute)
+		template <typename TFar, typename Fn>
+		void candidates(vec3 o, vec3 d, float tmin, TFar tfar, bool brute, Fn fn) const;
+	};
+	struct InstanceRecord {      // record 0 = the light triangles, k + 1 = object instance k
+		float r[3][4];           // world -> object, rows
+		uint32_t set;            // index into sets
+		uint32_t customIndex;    // Intersection.instanceIdx
+		uint32_t flatBase;       // flattened index of the instance's triangle 0
+	};
+	std::vector<TriSet> sets;                // single-level: one
+	std::vector<InstanceRecord> records;     // two-level only
+	bool twoLevel = false;
+	uint32_t numFlatTris = 0;
 
 	mutable Counters counters;
 	bool bruteForce = false;
@@ -75,7 +96,9 @@ struct Scene {
 	vec3 sampleTexture(uint32_t texIdx, float u, float v) const;
 
 private:
-	void buildNode(uint32_t nodeIdx, uint32_t begin, uint32_t end, std::vector<vec3>& cen, int depth);
+	// fn(triangle, flattened index, custom instance index, object-space o, d) for every candidate of the ray
+	template <typename TFar, typename Fn>
+	void forCandidates(vec3 o, vec3 d, float tmin, TFar tfar, Fn fn) const;
 };
 
 // Möller–Trumbore on (v0, e1, e2) with the operation order fixed by the numeric contract (oracle_math.h).

@@ -265,3 +265,52 @@ def test_oracle_furnace_lambert_energy(orc):
     assert np.isfinite(out).all() and (out[..., :3] >= 0).all() and out[..., :3].max() <= 1e4
     assert 0.01 < out[..., :3].mean() < 5.0
     b.close()
+
+
+# ---- two-level scenes: the oracle's instanced definition (object-space triangle test under every instance) ----------------
+def test_oracle_two_level_equals_its_brute_force_and_agrees_with_the_flattened_scene(orc):
+    """RPT_SCENE_TWO_LEVEL (reference src/Scene.cpp:448-547: BLAS per mesh, TLAS of instances, ray transformed at the instance
+    boundary): (1) the per-mesh BVHs are only accelerators of the instanced brute force — same bits; (2) against the flattened
+    world-space definition of the same scene the triangle hit is the same except for rays within rounding of an edge, and t is
+    shared because the direction is not renormalised (barycentrics agree to ~1e-4); (3) one copy of the shared mesh."""
+    from common import Backend, random_rays, camera_rays
+    sc = restirpt.HostScene.field(1, 3, 42, shared=True)
+    w, h = 64, 36
+    flat = Backend("oracle", sc, w, h)
+    sc.set_two_level(True)
+    two = Backend("oracle", sc, w, h)
+    assert flat.lib.orc_scene_num_triangles(flat.scene) == two.lib.orc_scene_num_triangles(two.scene)   # flattened numbering is the tie order
+    cam = sc.camera(w, h)
+    o, d = camera_rays(cam, w, h)
+    rays = np.zeros((w * h, 8), dtype=np.float32)
+    rays[:, 0:3] = o; rays[:, 3] = 1e-4; rays[:, 4:7] = d.reshape(-1, 3); rays[:, 7] = 1e7
+    rng = np.random.default_rng(5)
+    rays = np.concatenate([rays, random_rays(rng, 3000, -2.0, 2.0)])
+    a, b = flat.trace_closest(rays), two.trace_closest(rays)
+    same = (a["instanceIdx"] == b["instanceIdx"]) & (a["triangleIdx"] == b["triangleIdx"])
+    assert same.mean() > 0.998, same.mean()
+    hit = same & (a["instanceIdx"] != 0xffffffff)
+    assert hit.mean() > 0.5 and (a["instanceIdx"][hit] > 1).mean() > 0.03     # the instanced blobs are hit, not only the room
+    assert np.abs(a["bary"][hit] - b["bary"][hit]).max() < 1e-3
+    sa, sb = flat.trace_shadow(rays), two.trace_shadow(rays)
+    assert (sa == sb).mean() > 0.998
+    two.lib.orc_scene_set_brute_force(two.scene, 1)
+    assert np.array_equal(two.trace_closest(rays), b)
+    assert np.array_equal(two.trace_shadow(rays), sb)
+    flat.close(); two.close()
+
+
+def test_shared_field_scene_references_one_mesh(orc):
+    sc = restirpt.HostScene.field(1, 3, 42, shared=True)
+    dup = restirpt.HostScene.field(1, 3, 42)
+    d, e = sc.desc, dup.desc
+    assert d.numInstances == e.numInstances == 10 and d.flags == 0
+    inst = (restirpt.ObjectInstance * d.numInstances).from_address(d.instances)
+    ranges = {(i.indexOffset, i.indexCount) for i in inst}
+    assert len(ranges) == 2                                  # the room + ONE blob mesh
+    assert d.numIndices < e.numIndices / 4
+    other = (restirpt.ObjectInstance * e.numInstances).from_address(e.instances)
+    for a, b in zip(inst, other):                            # same placements as the duplicated-geometry scene
+        assert list(a.transform) == list(b.transform)
+    sc.set_two_level(True)
+    assert sc.desc.flags == restirpt.SCENE_TWO_LEVEL

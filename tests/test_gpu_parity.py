@@ -25,7 +25,16 @@ SCENES = {
     "cornell": lambda: restirpt.HostScene.cornell(),
     "room": lambda: restirpt.HostScene.room(6000, 7),
     "field": lambda: restirpt.HostScene.field(1, 3, 42),
+    # two-level scenes (RPT_SCENE_TWO_LEVEL: BLAS per unique mesh in object space + TLAS, reference src/Scene.cpp:448-547): nine
+    # instances of ONE mesh, and the room with a BLAS per object — against the oracle's instanced definition
+    "field_tlas": lambda: restirpt.HostScene.field(1, 3, 42, shared=True, two_level=True),
+    "room_tlas": lambda: _two_level(restirpt.HostScene.room(6000, 7)),
 }
+
+
+def _two_level(sc):
+    sc.set_two_level(True)
+    return sc
 
 
 @pytest.fixture(scope="module", params=list(SCENES))
@@ -246,3 +255,122 @@ def test_dynamic_scene_update_equals_a_fresh_scene(device):
     assert device.lib.rpt_scene_update_instances(moved.scene, tampered, sc.desc.numInstances) < 0
     for bk in (moved, fresh, cpu):
         bk.close()
+
+
+def test_two_level_scene_finds_the_flattened_scenes_triangles(device):
+    """the same scene description built both ways: the BLAS / TLAS traversal intersects in object space, the flattened one in
+    world space, so t and the barycentrics differ in their last bits — but the triangle a ray hits is the same except where two
+    triangles are within rounding of each other (edges, grazing rays)"""
+    sc = restirpt.HostScene.field(1, 3, 42, shared=True)
+    w, h = 192, 108
+    flat = Backend("cuda", sc, w, h, device)
+    sc.set_two_level(True)
+    two = Backend("cuda", sc, w, h, device)
+    st = restirpt.BvhStats()
+    device.lib.rpt_scene_bvh_stats(two.scene, st)
+    assert st.twoLevel == 1 and st.numMeshes == 3 and st.numInstanceRecords == sc.desc.numInstances + 1   # room, blob, lights
+    sf = restirpt.BvhStats()
+    device.lib.rpt_scene_bvh_stats(flat.scene, sf)
+    assert sf.twoLevel == 0 and st.numTriangles < sf.numTriangles / 4   # one copy of the blob instead of nine
+    cam = sc.camera(w, h)
+    o, d = camera_rays(cam, w, h)
+    rays = np.zeros((w * h, 8), dtype=np.float32)
+    rays[:, 0:3] = o; rays[:, 3] = 1e-4; rays[:, 4:7] = d.reshape(-1, 3); rays[:, 7] = 1e7
+    rng = np.random.default_rng(99)
+    rays = np.concatenate([rays, random_rays(rng, 20000, -3.0, 3.0)])
+    a, b = flat.trace_closest(rays), two.trace_closest(rays)
+    same = (a["instanceIdx"] == b["instanceIdx"]) & (a["triangleIdx"] == b["triangleIdx"])
+    assert same.mean() > 0.999, same.mean()
+    hit = same & (a["instanceIdx"] != 0xffffffff)
+    assert hit.mean() > 0.5
+    assert np.abs(a["bary"][hit] - b["bary"][hit]).max() < 1e-3
+    assert (flat.trace_shadow(rays) == two.trace_shadow(rays)).mean() > 0.999
+    flat.close(); two.close()
+
+
+def test_two_level_update_instances_rebuilds_the_tlas_only(device):
+    """on a two-level scene rpt_scene_update_instances leaves the BLASes alone (object space) and makes new instance records and
+    a new TLAS; the result is the state of a scene created from scratch with those transforms, and matches the oracle"""
+    sc = restirpt.HostScene.field(1, 3, 42, shared=True, two_level=True)
+    w, h = 96, 54
+    moved = Backend("cuda", sc, w, h, device)
+    before = restirpt.BvhStats()
+    device.lib.rpt_scene_bvh_stats(moved.scene, before)
+    sc.set_object_transform(3, (0.4, -0.3, 1.4), (1.3, 1.3, 1.3), (0.0, 40.0, 10.0))
+    sc.set_object_transform(7, (-0.9, 0.6, 0.8), (0.7, 0.7, 0.7), (75.0, 0.0, 0.0))
+    restirpt.check(device.ctx, device.lib.rpt_scene_update_instances(moved.scene, sc.desc.instances, sc.desc.numInstances),
+                   "rpt_scene_update_instances")
+    after = restirpt.BvhStats()
+    device.lib.rpt_scene_bvh_stats(moved.scene, after)
+    assert after.numNodes == before.numNodes and after.numTriangles == before.numTriangles and after.tlasBuildMs > 0
+    fresh = Backend("cuda", sc, w, h, device)
+    cpu = Backend("oracle", sc, w, h)
+    cam = sc.camera(w, h)
+    o, d = camera_rays(cam, w, h)
+    rays = np.zeros((w * h, 8), dtype=np.float32)
+    rays[:, 0:3] = o; rays[:, 3] = 1e-4; rays[:, 4:7] = d.reshape(-1, 3); rays[:, 7] = 1e7
+    a, b, c = moved.trace_closest(rays), fresh.trace_closest(rays), cpu.trace_closest(rays)
+    assert np.array_equal(a, b) and np.array_equal(a["instanceIdx"], c["instanceIdx"]) and np.array_equal(a["triangleIdx"], c["triangleIdx"])
+    for bk in (moved, fresh, cpu):
+        run_frames(bk, cam, "gris", 2)
+    for buf in ("GRIS_PREV", "INDIRECT_OUTPUT", "DEPTH_NORMAL_PREV"):
+        assert bitwise_mismatch(moved.read(buf), fresh.read(buf)) == 0, buf
+        assert bitwise_mismatch(moved.read(buf), cpu.read(buf)) == 0, buf
+    for bk in (moved, fresh, cpu):
+        bk.close()
+
+
+def test_scene_arrays_are_validated_at_the_boundary(device):
+    """rpt_scene_create checks index / material / instance / alias-table ranges on the host: RPT_ERR_INVALID with a message,
+    not an out-of-bounds device read"""
+    import ctypes as C
+    from restirpt import P
+    sc = restirpt.HostScene.cornell()
+
+    def attempt(mutate):
+        d = restirpt.SceneDesc()
+        C.memmove(C.byref(d), C.byref(sc.desc), C.sizeof(d))
+        keep = mutate(d)
+        out = P()
+        rc = device.lib.rpt_scene_create(device.ctx, C.byref(d), C.byref(out))
+        assert rc < 0 and not out.value, rc
+        return device.lib.rpt_last_error(device.ctx).decode(), keep
+
+    def bad_index(d):
+        idx = (C.c_uint32 * d.numIndices).from_address(d.indices)
+        copy = (C.c_uint32 * d.numIndices)(*idx)
+        copy[5] = d.numVertices
+        d.indices = C.cast(copy, C.c_void_p).value
+        return copy
+
+    def bad_material(d):
+        mi = (C.c_int32 * d.numMaterialIndices).from_address(d.materialIndices)
+        copy = (C.c_int32 * d.numMaterialIndices)(*mi)
+        copy[0] = d.numMaterials
+        d.materialIndices = C.cast(copy, C.c_void_p).value
+        return copy
+
+    def bad_instance(d):
+        n = d.numInstances
+        src = (restirpt.ObjectInstance * n).from_address(d.instances)
+        copy = (restirpt.ObjectInstance * n)()
+        C.memmove(copy, src, C.sizeof(copy))
+        copy[1].indexCount = d.numIndices + 3
+        d.instances = C.cast(copy, C.c_void_p).value
+        return copy
+
+    def bad_table(d):
+        n = d.numTriangleLights + 1
+        src = (restirpt.LightSampleTableElement * n).from_address(d.lightSampleTable)
+        copy = (restirpt.LightSampleTableElement * n)()
+        C.memmove(copy, src, C.sizeof(copy))
+        copy[1].failId = 0
+        d.lightSampleTable = C.cast(copy, C.c_void_p).value
+        return copy
+
+    def bad_count(d):
+        d.numMaterialIndices -= 1
+
+    for mutate, word in ((bad_index, "index"), (bad_material, "material"), (bad_instance, "instance"), (bad_table, "failId"), (bad_count, "numMaterialIndices")):
+        msg, _ = attempt(mutate)
+        assert word in msg, (word, msg)

@@ -123,7 +123,7 @@ RT_DEV uint32_t expandSlotsToTriples(uint32_t x) {
 // new node group (inner children hit, near to far) plus the hit leaf children.  The remainder of the old
 // group is pushed first.  Precondition: ngroup.y > 0x00ffffff.
 template <typename Stack>
-RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, LeafHits& leaves) {
+RT_DEV void nodeStep(const WideNode* __restrict__ nodes, const TravRay& r, float tfar, uint2& ngroup, Stack& stack, int& sp, LeafHits& leaves) {
 	const bool negx = !(r.octinv & 1u), negy = !(r.octinv & 2u), negz = !(r.octinv & 4u);   // (makeTravRay: octinv = 7 ^ sign bits of 1/d)
 	const uint32_t hits = ngroup.y;
 	const uint32_t bit = 31u - uint32_t(__clz(int(hits)));
@@ -131,7 +131,7 @@ RT_DEV void nodeStep(const SceneView& s, const TravRay& r, float tfar, uint2& ng
 	if (ngroup.y > 0x00ffffffu && sp < TraversalStackSize) stack[sp++] = ngroup;
 	const uint32_t slot = (bit - 24u) ^ r.octinv;
 	const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
-	const float4* np = reinterpret_cast<const float4*>(s.nodes + (ngroup.x + rel));
+	const float4* np = reinterpret_cast<const float4*>(nodes + (ngroup.x + rel));
 	const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 
 	const uint32_t ebits = __float_as_uint(n0.w);
@@ -236,18 +236,106 @@ struct TravResult {
 };
 
 // The hit leaf triangles of one node against the ray; returns true when the traversal may stop (any hit accepted).
-template <int MODE>
-RT_DEV bool triLoop(const SceneView& s, const TravRay& r, LeafHits leaves, float tmaxOrig, TravResult& res, uint32_t& triTests) {
+// INSTANCED (two-level scenes): the ray is in the object space of an instance whose BLAS these triangles belong to — the
+// record's ids are mesh-local, the hit takes the instance's custom index and its place in the flattened tie order.
+template <int MODE, bool INSTANCED = false>
+RT_DEV bool triLoop(const SceneView& s, const TravRay& r, LeafHits leaves, float tmaxOrig, TravResult& res, uint32_t& triTests,
+                    uint32_t customIndex = 0, uint32_t flatBase = 0) {
 	while (leaves.bits) {
 		const uint32_t one = 1u << (31u - uint32_t(__clz(int(leaves.bits))));
 		leaves.bits ^= one;
 		triTests++;
 		TriHit h;
 		if (triTest(s, r, leaves.triBase + uint32_t(__popc(leaves.valid & (one - 1u))), tmaxOrig, h)) {
+			if (INSTANCED) { h.instanceIdx = customIndex; h.flat += flatBase; }
 			if (res.accept<MODE>(h)) return true;
 		}
 	}
 	return false;
+}
+
+// ---- two-level scenes (SceneView::tlasNodes != nullptr) ------------------------------------------------------------------------
+// The reference's arrangement (src/Scene.cpp:448-547): a TLAS over the instances, a BLAS per mesh in object space, the ray taken
+// into object space at the instance boundary — WITHOUT renormalising the direction, so t means the same on both sides and the
+// running closest t prunes across instances.  Hit definition = the triangle test above applied to the object-space ray;
+// closest hit = minimum t, ties to the lower flattened index (instance's first triangle + triangle within the mesh), as the
+// CPU oracle's instanced brute force defines it.
+struct ObjectRay { float3 o, d; };
+RT_DEV InstanceRecord loadInstanceRecord(const SceneView& s, uint32_t tlasLeaf) {
+	const uint32_t recIdx = __float_as_uint(__ldg(&s.tlasLeaves[tlasLeaf].t0).w);
+	const float4* p = reinterpret_cast<const float4*>(s.instRecords + recIdx);
+	InstanceRecord rec;
+	rec.r0 = __ldg(p + 0); rec.r1 = __ldg(p + 1); rec.r2 = __ldg(p + 2);
+	const float4 ids = __ldg(p + 3);
+	rec.rootNode = __float_as_uint(ids.x); rec.customIndex = __float_as_uint(ids.y); rec.flatBase = __float_as_uint(ids.z); rec.pad = 0;
+	return rec;
+}
+RT_DEV ObjectRay toObjectSpace(const InstanceRecord& rec, float3 o, float3 d) {   // fixed operation order (numeric contract)
+	ObjectRay r;
+	r.o = make_float3(fma_(rec.r0.z, o.z, fma_(rec.r0.y, o.y, fma_(rec.r0.x, o.x, rec.r0.w))),
+	                  fma_(rec.r1.z, o.z, fma_(rec.r1.y, o.y, fma_(rec.r1.x, o.x, rec.r1.w))),
+	                  fma_(rec.r2.z, o.z, fma_(rec.r2.y, o.y, fma_(rec.r2.x, o.x, rec.r2.w))));
+	r.d = make_float3(fma_(rec.r0.z, d.z, fma_(rec.r0.y, d.y, rec.r0.x * d.x)),
+	                  fma_(rec.r1.z, d.z, fma_(rec.r1.y, d.y, rec.r1.x * d.x)),
+	                  fma_(rec.r2.z, d.z, fma_(rec.r2.y, d.y, rec.r2.x * d.x)));
+	return r;
+}
+
+// One ray per thread through TLAS and BLASes, run to completion.  A real call (not inlined): it is compiled into every pass
+// kernel but only two-level scenes take it, and the single-level path below must not pay registers for it.
+template <int MODE>
+__device__ __noinline__ Hit traceRayTwoLevel(const SceneView& s, float3 o, float tmin, float3 d, float tmax, uint32_t* candidateCount) {
+	TravResult res;
+	res.init(tmax);
+	uint32_t nodeVisits = 0, triTests = 0;
+	const TravRay rw = makeTravRay(o, tmin, d);
+	const float tmaxOrig = tmax;
+	uint2 stack[TraversalStackSize];
+	int sp = 0;
+	uint2 tgroup = make_uint2(0u, 0x80000000u);
+	bool done = false;
+	while (!done) {
+		LeafHits inst{ 0u, 0u, 0u };
+		if (tgroup.y > 0x00ffffffu) {
+			nodeStep(s.tlasNodes, rw, res.bestT, tgroup, stack, sp, inst);
+			nodeVisits++;
+		}
+		while (inst.bits && !done) {
+			const uint32_t one = 1u << (31u - uint32_t(__clz(int(inst.bits))));
+			inst.bits ^= one;
+			const InstanceRecord rec = loadInstanceRecord(s, inst.triBase + uint32_t(__popc(inst.valid & (one - 1u))));
+			if (rec.rootNode == 0xffffffffu) continue;
+			const ObjectRay ob = toObjectSpace(rec, o, d);
+			if (rayIsDegenerate(ob.o, tmin, ob.d, tmax)) continue;
+			const TravRay r = makeTravRay(ob.o, tmin, ob.d);
+			const int base = sp;
+			uint2 ngroup = make_uint2(rec.rootNode, 0x80000000u);
+			for (;;) {
+				LeafHits leaves{ 0u, 0u, 0u };
+				if (ngroup.y > 0x00ffffffu) {
+					nodeStep(s.nodes, r, res.bestT, ngroup, stack, sp, leaves);
+					nodeVisits++;
+				}
+				if (triLoop<MODE, true>(s, r, leaves, tmaxOrig, res, triTests, rec.customIndex, rec.flatBase)) { done = true; break; }
+				if (ngroup.y <= 0x00ffffffu) {
+					if (sp == base) break;
+					ngroup = stack[--sp];
+				}
+			}
+		}
+		if (!done && tgroup.y <= 0x00ffffffu) {
+			if (sp == 0) break;
+			tgroup = stack[--sp];
+		}
+	}
+	if (s.counters != nullptr) {
+		atomicAdd(&s.counters[MODE == TraceAny ? 1 : 0], 1ull);
+		atomicAdd(&s.counters[2], (unsigned long long)nodeVisits);
+		if (MODE == TraceAny) { atomicAdd(&s.counters[5], (unsigned long long)nodeVisits); atomicAdd(&s.counters[6], (unsigned long long)triTests); }
+		atomicAdd(&s.counters[3], (unsigned long long)triTests);
+	}
+	if (MODE == TraceCount && candidateCount) *candidateCount = res.count;
+	return res.best;
 }
 
 // One ray per thread, run to completion (the per-pixel passes call this in line).
@@ -261,6 +349,7 @@ RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tm
 		if (MODE == TraceCount && candidateCount) *candidateCount = 0;
 		return res.best;
 	}
+	if (s.tlasNodes != nullptr) return traceRayTwoLevel<MODE>(s, o, tmin, d, tmax, candidateCount);
 	const TravRay r = makeTravRay(o, tmin, d);
 	const float tmaxOrig = tmax;
 	uint2 stack[TraversalStackSize];
@@ -270,7 +359,7 @@ RT_DEV Hit traceRay(const SceneView& s, float3 o, float tmin, float3 d, float tm
 	for (;;) {
 		LeafHits leaves{ 0u, 0u, 0u };
 		if (ngroup.y > 0x00ffffffu) {
-			nodeStep(s, r, res.bestT, ngroup, stack, sp, leaves);
+			nodeStep(s.nodes, r, res.bestT, ngroup, stack, sp, leaves);
 			nodeVisits++;
 		}
 		if (triLoop<MODE>(s, r, leaves, tmaxOrig, res, triTests)) break;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 #include "../../include/restirpt.h"
 #include "bvh_build.h"
@@ -32,6 +33,9 @@ struct RptScene {
 	std::vector<void*> allocations;   // everything but the acceleration structure
 	BuildInputs buildInputs{};        // device views kept for rpt_scene_update_instances
 	RptBvhStats stats{};
+	bool twoLevel = false;
+	TwoLevelState tl{};               // two-level scenes: BLASes, TLAS, instance records (view.nodes / tris alias tl.blas*)
+	std::vector<MeshRange> geometry;  // (indexOffset, indexCount) of every instance, as created
 };
 
 struct RptFrame {
@@ -199,6 +203,8 @@ static cudaError_t upload(RptScene* sc, const T* host, size_t n, const T** dev, 
 
 static void adoptBvh(RptScene* sc, const BuildOutputs& bo) {
 	sc->view.nodes = bo.nodes; sc->view.tris = bo.tris;
+	sc->view.tlasNodes = nullptr; sc->view.tlasLeaves = nullptr; sc->view.instRecords = nullptr;
+	sc->stats = RptBvhStats{};
 	sc->stats.numTriangles = bo.numTris;
 	sc->stats.numNodes = bo.numNodes;
 	sc->stats.nodeBytes = uint64_t(bo.numNodes) * sizeof(WideNode);
@@ -207,11 +213,52 @@ static void adoptBvh(RptScene* sc, const BuildOutputs& bo) {
 	sc->stats.sahCost = 0.0f;
 }
 
+static void adoptTwoLevel(RptScene* sc, uint32_t numMeshes) {
+	const TwoLevelState& t = sc->tl;
+	sc->view.nodes = t.blasNodes; sc->view.tris = t.blasTris;
+	sc->view.tlasNodes = t.tlasNodes; sc->view.tlasLeaves = t.tlasLeaves; sc->view.instRecords = t.records;
+	RptBvhStats& st = sc->stats;
+	st = RptBvhStats{};
+	st.numTriangles = t.numBlasTris; st.numNodes = t.numBlasNodes;
+	st.nodeBytes = uint64_t(t.numBlasNodes + t.numTlasNodes) * sizeof(WideNode);
+	st.triBytes = uint64_t(t.numBlasTris) * sizeof(TriRecord) + uint64_t(t.numRecords) * (sizeof(TriRecord) + sizeof(InstanceRecord));
+	st.buildMs = t.blasMs + t.tlasMs; st.tlasBuildMs = t.tlasMs;
+	st.twoLevel = 1; st.numMeshes = numMeshes; st.numTlasNodes = t.numTlasNodes; st.numInstanceRecords = t.numRecords;
+}
+
+// The arrays cross the integration boundary unchecked by anyone else (only the bundled loaders validate their own output): an
+// index past its array would be an out-of-bounds device read that poisons the CUDA context.  One linear host pass.
+static std::string validateDesc(const RptSceneDesc* d) {
+	auto bad = [](const char* what, uint64_t i) { return std::string("rpt_scene_create: ") + what + " (element " + std::to_string(i) + ")"; };
+	if ((d->numVertices && !d->vertices) || (d->numIndices && !d->indices) || (d->numMaterials && !d->materials) ||
+	    (d->numMaterialIndices && !d->materialIndices) || (d->numInstances && !d->instances) || !d->triangleLights || !d->lightSampleTable ||
+	    (d->numTextures && !d->textures))
+		return "rpt_scene_create: an array pointer is NULL while its count is not 0";
+	if (d->numMaterials == 0) return "rpt_scene_create: at least one material is needed (materials[0] is the fallback of light surfaces)";
+	if (d->numMaterialIndices != d->numIndices / 3) return "rpt_scene_create: numMaterialIndices must be numIndices / 3 (one per object triangle)";
+	for (uint32_t i = 0; i < d->numIndices; i++) if (d->indices[i] >= d->numVertices) return bad("an index points past the vertex array", i);
+	for (uint32_t i = 0; i < d->numMaterialIndices; i++)
+		if (d->materialIndices[i] < 0 || uint32_t(d->materialIndices[i]) >= d->numMaterials) return bad("a material index is out of range", i);
+	for (uint32_t i = 0; i < d->numMaterials; i++)
+		if (d->materials[i].textureIdx != 0xffffffffu && d->materials[i].textureIdx >= d->numTextures) return bad("a material's textureIdx is out of range", i);
+	for (uint32_t i = 0; i < d->numInstances; i++) {
+		const RptObjectInstance& I = d->instances[i];
+		if (I.indexOffset % 3 != 0 || I.indexCount % 3 != 0 || uint64_t(I.indexOffset) + I.indexCount > d->numIndices)
+			return bad("an instance's index range is not whole triangles inside the index array", i);
+	}
+	for (uint32_t i = 1; i <= d->numTriangleLights; i++)
+		if (d->lightSampleTable[i].failId < 1 || d->lightSampleTable[i].failId > d->numTriangleLights) return bad("a light sample table failId is not in 1..N", i);
+	for (uint32_t i = 0; i < d->numTextures; i++)
+		if (!d->textures[i].rgba8 || d->textures[i].width == 0 || d->textures[i].height == 0) return bad("an empty texture", i);
+	return std::string();
+}
+
 RPT_API int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* d, RptScene** out) {
 	if (!ctx || !d || !out) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: NULL argument");
 	*out = nullptr;
 	if (d->numTriangleLights == 0) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: the scene needs at least one triangle light (the light sample table divides by its total power)");
 	if (d->numIndices % 3 != 0) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_create: numIndices must be a multiple of 3");
+	{ const std::string why = validateDesc(d); if (!why.empty()) return fail(ctx, RPT_ERR_INVALID, why); }
 	CU(ctx, cudaSetDevice(ctx->device));
 	RptScene* sc = new RptScene;
 	sc->ctx = ctx;
@@ -259,14 +306,29 @@ RPT_API int rpt_scene_create(RptCtx* ctx, const RptSceneDesc* d, RptScene** out)
 	BuildInputs in{};
 	in.vertices = v.vertices; in.indices = v.indices; in.instances = v.instances; in.lights = v.lights;
 	in.triOffsets = dTriOffsets; in.numInstances = d->numInstances; in.numLights = d->numTriangleLights; in.numTris = uint32_t(total);
-	BuildOutputs bo;
-	if ((e = buildBvh(in, st, &bo)) != cudaSuccess) {
-		if (bo.nodes) cudaFree(bo.nodes);
-		if (bo.tris) cudaFree(bo.tris);
-		return bail(e, "buildBvh");
-	}
 	sc->buildInputs = in;
-	adoptBvh(sc, bo);
+	sc->geometry.resize(d->numInstances);
+	for (uint32_t k = 0; k < d->numInstances; k++) sc->geometry[k] = MeshRange{ d->instances[k].indexOffset, d->instances[k].indexCount };
+	sc->twoLevel = (d->flags & RPT_SCENE_TWO_LEVEL) != 0;
+	if (sc->twoLevel) {
+		TwoLevelInputs ti;
+		ti.base = in;
+		ti.meshOfInstance.resize(d->numInstances);
+		std::map<std::pair<uint32_t, uint32_t>, uint32_t> seen;
+		for (uint32_t k = 0; k < d->numInstances; k++) {
+			const auto key = std::make_pair(d->instances[k].indexOffset, d->instances[k].indexCount);
+			auto it = seen.find(key);
+			if (it == seen.end()) { it = seen.emplace(key, uint32_t(ti.meshes.size())).first; ti.meshes.push_back(MeshRange{ key.first, key.second }); }
+			ti.meshOfInstance[k] = it->second;
+		}
+		if ((e = buildTwoLevel(ti, st, &sc->tl)) != cudaSuccess) return bail(e, "buildTwoLevel");
+		adoptTwoLevel(sc, uint32_t(ti.meshes.size()) + 1);
+	}
+	else {
+		BuildOutputs bo;
+		if ((e = buildBvh(in, st, &bo)) != cudaSuccess) return bail(e, "buildBvh");
+		adoptBvh(sc, bo);
+	}
 	v.counters = nullptr;
 	*out = sc;
 	return RPT_OK;
@@ -280,25 +342,43 @@ RPT_API int rpt_scene_update_instances(RptScene* s, const RptObjectInstance* ins
 	if (!s || !instances) return fail(s ? s->ctx : nullptr, RPT_ERR_INVALID, "rpt_scene_update_instances: NULL argument");
 	RptCtx* ctx = s->ctx;
 	if (numInstances != s->buildInputs.numInstances) return fail(ctx, RPT_ERR_INVALID, "rpt_scene_update_instances: the instance count cannot change");
-	CU(ctx, cudaSetDevice(ctx->device));
-	CU(ctx, cudaDeviceSynchronize());
-	std::vector<RptObjectInstance> old(numInstances);
-	CU(ctx, cudaMemcpy(old.data(), s->view.instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyDeviceToHost));
 	for (uint32_t k = 0; k < numInstances; k++) {
-		if (old[k].indexOffset != instances[k].indexOffset || old[k].indexCount != instances[k].indexCount)
+		if (s->geometry[k].indexOffset != instances[k].indexOffset || s->geometry[k].indexCount != instances[k].indexCount)
 			return fail(ctx, RPT_ERR_INVALID, "rpt_scene_update_instances: an instance's geometry range (indexOffset / indexCount) cannot change");
 	}
-	CU(ctx, cudaMemcpy(const_cast<RptObjectInstance*>(s->view.instances), instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyHostToDevice));
-	BuildOutputs bo;
-	cudaError_t e = buildBvh(s->buildInputs, ctx->stream, &bo);
-	if (e != cudaSuccess) {
-		if (bo.nodes) cudaFree(bo.nodes);
-		if (bo.tris) cudaFree(bo.tris);
-		return cudaFail(ctx, e, "buildBvh");
+	CU(ctx, cudaSetDevice(ctx->device));
+	CU(ctx, cudaDeviceSynchronize());
+	// the new instances go to a staged copy; the scene's own array and its structure change together, and only on success
+	RptObjectInstance* staged = nullptr;
+	CU(ctx, cudaMalloc(reinterpret_cast<void**>(&staged), std::max<size_t>(numInstances, 1) * sizeof(RptObjectInstance)));
+	cudaError_t e = cudaMemcpy(staged, instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyHostToDevice);
+	BuildInputs in = s->buildInputs;
+	in.instances = staged;
+	if (e == cudaSuccess && s->twoLevel) {
+		// the BLASes are in object space and do not move: new instance records and a new TLAS over them
+		TwoLevelState next = s->tl;
+		next.tlasNodes = nullptr; next.tlasLeaves = nullptr; next.records = nullptr;
+		e = cudaMalloc(reinterpret_cast<void**>(&next.records), size_t(next.numRecords) * sizeof(InstanceRecord));
+		if (e == cudaSuccess) e = rebuildTlas(in, ctx->stream, &next);
+		if (e != cudaSuccess) { cudaFree(next.tlasNodes); cudaFree(next.tlasLeaves); cudaFree(next.records); }
+		else {
+			cudaFree(s->tl.tlasNodes); cudaFree(s->tl.tlasLeaves); cudaFree(s->tl.records);
+			s->tl = next;
+			adoptTwoLevel(s, s->stats.numMeshes);
+		}
 	}
-	cudaFree(const_cast<WideNode*>(s->view.nodes));
-	cudaFree(const_cast<TriRecord*>(s->view.tris));
-	adoptBvh(s, bo);
+	else if (e == cudaSuccess) {
+		BuildOutputs bo;
+		e = buildBvh(in, ctx->stream, &bo);
+		if (e == cudaSuccess) {
+			cudaFree(const_cast<WideNode*>(s->view.nodes));
+			cudaFree(const_cast<TriRecord*>(s->view.tris));
+			adoptBvh(s, bo);
+		}
+	}
+	if (e == cudaSuccess) e = cudaMemcpy(const_cast<RptObjectInstance*>(s->view.instances), staged, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyDeviceToDevice);
+	cudaFree(staged);
+	if (e != cudaSuccess) return cudaFail(ctx, e, "rpt_scene_update_instances: rebuild");
 	return RPT_OK;
 }
 
@@ -306,8 +386,11 @@ RPT_API void rpt_scene_destroy(RptScene* s) {
 	if (!s) return;
 	cudaSetDevice(s->ctx->device);
 	for (void* p : s->allocations) cudaFree(p);
-	if (s->view.nodes) cudaFree(const_cast<WideNode*>(s->view.nodes));
-	if (s->view.tris) cudaFree(const_cast<TriRecord*>(s->view.tris));
+	if (s->twoLevel) s->tl.release();
+	else {
+		if (s->view.nodes) cudaFree(const_cast<WideNode*>(s->view.nodes));
+		if (s->view.tris) cudaFree(const_cast<TriRecord*>(s->view.tris));
+	}
 	delete s;
 }
 

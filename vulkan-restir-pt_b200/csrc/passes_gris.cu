@@ -694,7 +694,12 @@ __global__ void __launch_bounds__(ShadeBlock, RT_BOUNCE_MINBLOCKS) grisBounceKer
 // registers and mostly waits on memory, so the grid is kept to a few small blocks per SM (a sixth to a third of the
 // register file) and every thread pulls its next path from the list as soon as one ends.
 constexpr int TailBlock = 64;
-__global__ void __launch_bounds__(TailBlock) grisTailKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set) {
+// register cap of the tail kernel = 65536 / (64 * blocks).  The compiler's own choice is ~128 for the single-level code; with the
+// two-level traversal compiled in as a call it would take 168 and crowd the temporal pass it runs next to (profiles/r2_09_*)
+#ifndef RT_TAIL_MINBLOCKS
+#define RT_TAIL_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(TailBlock, RT_TAIL_MINBLOCKS) grisTailKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings set) {
 	const int first = WavefrontTailStart;
 	const uint32_t n = f.wf.counters[4 * first];
 	uint32_t* head = f.wf.counters + 4 * first + 2;   // (the fetch counter of the wavefront traversal of this bounce: unused here, zero)

@@ -483,6 +483,13 @@ void Scene::commitInstance(uint32_t modelIdx, bool isLight, vec3 power) {
 	}
 }
 
+uint32_t Scene::addModelInstanceOf(uint32_t modelIdx) {
+	if (modelIdx >= models[0].size()) throw std::runtime_error("Scene: no such object model");
+	ModelInstance copy = models[0][modelIdx];   // same meshOffset / numIndices: the geometry is referenced, not duplicated
+	models[0].push_back(copy);
+	return uint32_t(models[0].size() - 1);
+}
+
 void Scene::setObjectTransform(uint32_t modelIdx, vec3 pos, vec3 scale, vec3 rotationDeg) {
 	if (modelIdx >= models[0].size() || modelIdx >= objectInstances.size()) throw std::runtime_error("Scene: no such object model");
 	ModelInstance& model = models[0][modelIdx];
@@ -517,6 +524,7 @@ RptSceneDesc Scene::desc() const {
 	mTexDescs.clear();
 	for (auto& t : textures) mTexDescs.push_back({ t.rgba8.data(), t.width, t.height, t.filter });
 	d.textures = mTexDescs.data();              d.numTextures = uint32_t(mTexDescs.size());
+	d.flags = twoLevel ? uint32_t(RPT_SCENE_TWO_LEVEL) : 0u;
 	return d;
 }
 
@@ -826,7 +834,7 @@ void makeAjarLikeRoom(Scene& scene, uint32_t trisTarget, uint32_t seed) {
 	scene.camera.setFilmSize(1280, 720);
 }
 
-void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint32_t seed) {
+void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint32_t seed, bool shareGeometry) {
 	scene.clear();
 	const float cell = 1.0f;
 	const float half = 0.5f * cell * gridN + 1.0f;
@@ -844,6 +852,7 @@ void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint3
 	MeshBuilder proto;
 	blob(proto, vec3(0.f), 0.38f, nu, nv, 0.08f, seed);
 	uint32_t st = seed * 9781u + 7u;
+	uint32_t protoModel = InvalidResourceIdx;
 	for (uint32_t gy = 0; gy < gridN; gy++) for (uint32_t gx = 0; gx < gridN; gx++) {
 		vec3 p((gx + 0.5f) * cell - 0.5f * cell * gridN + (pcgFloat(st) - 0.5f) * 0.2f,
 		       (gy + 0.5f) * cell - 0.5f * cell * gridN + (pcgFloat(st) - 0.5f) * 0.2f,
@@ -852,7 +861,16 @@ void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint3
 		float k = pcgFloat(st);
 		RptMaterial mat = k < 0.5f ? lambert() : metalWorkflow(k < 0.8f ? 0.0f : 1.0f, 0.15f + 0.4f * pcgFloat(st));
 		vec3 col(0.35f + 0.6f * pcgFloat(st), 0.35f + 0.6f * pcgFloat(st), 0.35f + 0.6f * pcgFloat(st));
-		addObject(scene, proto, mat, col, InvalidResourceIdx, p, vec3(s), vec3(360.f * pcgFloat(st), 0.f, 0.f));
+		const vec3 rot(360.f * pcgFloat(st), 0.f, 0.f);
+		if (!shareGeometry || protoModel == InvalidResourceIdx) {
+			const uint32_t id = addObject(scene, proto, mat, col, InvalidResourceIdx, p, vec3(s), rot);
+			if (protoModel == InvalidResourceIdx) protoModel = id;
+		}
+		else {   // the same triangles (and the first blob's material) under another transform
+			const uint32_t id = scene.addModelInstanceOf(protoModel);
+			scene.models[0][id].pos = p; scene.models[0][id].scale = vec3(s); scene.models[0][id].rotation = rot;
+			scene.commitInstance(id, false, vec3(0.f));
+		}
 	}
 	{ MeshBuilder m; float q = half * 0.5f;
 	  m.quad(vec3(-q, -q, 5.99f), vec3(-q, q, 5.99f), vec3(q, q, 5.99f), vec3(q, -q, 5.99f), vec3(0, 0, -1));

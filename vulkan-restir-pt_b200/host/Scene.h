@@ -56,6 +56,9 @@ public:
 	// finalises instance `modelIdx` (transform already set on the ModelInstance): appends an ObjectInstance or
 	// the world-space TriangleLights of power `power` (reference Scene::loadModels, src/Scene.cpp:192-300)
 	void commitInstance(uint32_t modelIdx, bool isLight, vec3 power);
+	// another placement of object model `modelIdx` that SHARES its geometry and per-triangle materials (what a TLAS instance is);
+	// returns the new model index (still one ObjectInstance per object model, in model order, once committed)
+	uint32_t addModelInstanceOf(uint32_t modelIdx);
 	// dynamic scenes: a new placement for object model `modelIdx` (its ObjectInstance is rewritten in place; the device
 	// scene follows with Renderer::updateInstances / rpt_scene_update_instances)
 	void setObjectTransform(uint32_t modelIdx, vec3 pos, vec3 scale, vec3 rotationDeg);
@@ -82,6 +85,9 @@ public:
 	std::vector<RptTriangleLight> triangleLights;
 	std::vector<RptLightSampleTableElement> lightSampleTable;
 	std::string path;
+	// acceleration-structure arrangement asked of rpt_scene_create (RptSceneFlags): BLAS per unique mesh + TLAS instead of the
+	// flattened world-space structure
+	bool twoLevel = false;
 
 	Scene();
 
@@ -96,7 +102,9 @@ void makeCornellBox(Scene& scene);
 // `detail`-controlled tessellation (≈ trisTarget triangles).  Used when the VeachAjar asset is absent.
 void makeAjarLikeRoom(Scene& scene, uint32_t trisTarget, uint32_t seed);
 // Displaced icosphere mesh instanced on a jittered grid inside a lit box (config 5 stress scene).
-void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint32_t seed);
+// shareGeometry: the instances reference ONE copy of the mesh (and of its material) instead of each carrying their own — the
+// "instanced ... through TLAS" variant of config 5, meant for two-level scenes.
+void makeInstancedField(Scene& scene, uint32_t meshSubdiv, uint32_t gridN, uint32_t seed, bool shareGeometry = false);
 
 // PNG writer (stored deflate blocks; no zlib needed) and PPM reader
 bool writePNG(const std::string& path, const uint8_t* rgba8, uint32_t w, uint32_t h);

@@ -43,6 +43,8 @@ RhScene* rh_scene_load_xml(const char* path) { return makeScene([&](Scene& s) { 
 RhScene* rh_scene_cornell(void) { return makeScene([&](Scene& s) { makeCornellBox(s); }); }
 RhScene* rh_scene_room(uint32_t tris, uint32_t seed) { return makeScene([&](Scene& s) { makeAjarLikeRoom(s, tris, seed); }); }
 RhScene* rh_scene_field(uint32_t subdiv, uint32_t gridN, uint32_t seed) { return makeScene([&](Scene& s) { makeInstancedField(s, subdiv, gridN, seed); }); }
+RhScene* rh_scene_field_shared(uint32_t subdiv, uint32_t gridN, uint32_t seed) { return makeScene([&](Scene& s) { makeInstancedField(s, subdiv, gridN, seed, true); }); }
+void rh_scene_set_two_level(RhScene* s, int on) { s->scene.twoLevel = on != 0; }
 void rh_scene_destroy(RhScene* s) { delete s; }
 void rh_scene_desc(const RhScene* s, RptSceneDesc* out) { *out = s->scene.desc(); }
 void rh_scene_camera(const RhScene* s, RptCamera* out) { *out = s->scene.camera.data(); }

@@ -87,7 +87,10 @@ class SceneDesc(C.Structure):
                 ("instances", C.c_void_p), ("numInstances", C.c_uint32),
                 ("triangleLights", C.c_void_p), ("numTriangleLights", C.c_uint32),
                 ("lightSampleTable", C.c_void_p),
-                ("textures", C.c_void_p), ("numTextures", C.c_uint32)]
+                ("textures", C.c_void_p), ("numTextures", C.c_uint32), ("flags", C.c_uint32)]
+
+
+SCENE_TWO_LEVEL = 1
 
 
 class Counters(C.Structure):
@@ -124,7 +127,9 @@ PASS_NAMES = ["gbuffer", "di_naive", "gi_naive", "di_pathgen", "di_temporal", "d
 
 class BvhStats(C.Structure):
     _fields_ = [("numTriangles", C.c_uint32), ("numNodes", C.c_uint32), ("nodeBytes", C.c_uint64),
-                ("triBytes", C.c_uint64), ("buildMs", C.c_float), ("sahCost", C.c_float)]
+                ("triBytes", C.c_uint64), ("buildMs", C.c_float), ("sahCost", C.c_float),
+                ("twoLevel", C.c_uint32), ("numMeshes", C.c_uint32), ("numTlasNodes", C.c_uint32),
+                ("numInstanceRecords", C.c_uint32), ("tlasBuildMs", C.c_float), ("pad", C.c_uint32)]
 
 
 assert C.sizeof(Material) == 32 and C.sizeof(MeshVertex) == 32 and C.sizeof(ObjectInstance) == 224
@@ -231,6 +236,8 @@ HOST_API = {
     "rh_scene_cornell": (P, []),
     "rh_scene_room": (P, [C.c_uint32, C.c_uint32]),
     "rh_scene_field": (P, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rh_scene_field_shared": (P, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "rh_scene_set_two_level": (None, [P, C.c_int]),
     "rh_scene_destroy": (None, [P]),
     "rh_scene_desc": (None, [P, C.POINTER(SceneDesc)]),
     "rh_scene_camera": (None, [P, C.POINTER(Camera)]),
@@ -329,8 +336,16 @@ class HostScene:
         return HostScene(host_lib().rh_scene_room(tris, seed))
 
     @staticmethod
-    def field(subdiv=2, grid=4, seed=42):
-        return HostScene(host_lib().rh_scene_field(subdiv, grid, seed))
+    def field(subdiv=2, grid=4, seed=42, shared=False, two_level=False):
+        """shared: one copy of the mesh referenced by every instance; two_level: BLAS per unique mesh + TLAS"""
+        sc = HostScene((host_lib().rh_scene_field_shared if shared else host_lib().rh_scene_field)(subdiv, grid, seed))
+        if two_level:
+            sc.set_two_level(True)
+        return sc
+
+    def set_two_level(self, on=True):
+        host_lib().rh_scene_set_two_level(self.handle, 1 if on else 0)
+        host_lib().rh_scene_desc(self.handle, C.byref(self.desc))
 
     @staticmethod
     def xml(path):
