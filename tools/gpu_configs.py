@@ -5,6 +5,9 @@
     python tools/gpu_configs.py field [subdiv grid]
                                       instanced field (~50 M world-space triangles), 1920x1080, ReSTIR GI temporal   (config 5)
                                       reports BVH build ms, BVH bytes / triangle, node + triangle bytes / ray
+    python tools/gpu_configs.py field_tlas [subdiv grid]
+                                      config 5's instanced variant: ONE copy of the mesh, BLAS + TLAS (RPT_SCENE_TWO_LEVEL), then the
+                                      same scene description flattened; also times rpt_scene_update_instances on both
 
 Prints one JSON line per configuration (frames/s from CUDA events on the frame's stream, counters from one
 instrumented, untimed frame)."""
@@ -23,7 +26,7 @@ from common import Backend, FrameDriver, METHOD_PASSES
 import prepare_assets
 
 
-def measure(sc, scene_name, w, h, method, frames, warm, moves=None):
+def measure(sc, scene_name, w, h, method, frames, warm, moves=None, time_update=False):
     dev = restirpt.Device(0)
     t0 = time.time()
     b = Backend("cuda", sc, w, h, dev)
@@ -61,8 +64,24 @@ def measure(sc, scene_name, w, h, method, frames, warm, moves=None):
     dev.lib.rpt_counters_enable(dev.ctx, 0)
     rays = c.closestRays + c.shadowRays
     alg = 80 * c.nodeVisits + 48 * c.triTests + 48 * rays + 272 * c.shadedHits
+    inst = (restirpt.ObjectInstance * sc.desc.numInstances).from_address(sc.desc.instances)
+    instanced = sum(i.indexCount // 3 for i in inst) + sc.desc.numTriangleLights
+    update_ms = None
+    if time_update:
+        dev.lib.rpt_sync(b.frame)
+        update_ms = []
+        for _ in range(3):
+            t0 = time.time()
+            restirpt.check(dev.ctx, dev.lib.rpt_scene_update_instances(b.scene, sc.desc.instances, sc.desc.numInstances), "rpt_scene_update_instances")
+            update_ms.append(round((time.time() - t0) * 1e3, 3))
+            dev.lib.rpt_scene_bvh_stats(b.scene, C.byref(st))
+            update_ms.append(round(float(st.buildMs), 3))
     line = {
-        "scene": scene_name, "film": [w, h], "method": method, "triangles": int(st.numTriangles), "bvh_nodes": int(st.numNodes),
+        "scene": scene_name, "film": [w, h], "method": method, "two_level": int(st.twoLevel), "instanced_triangles": instanced,
+        "meshes": int(st.numMeshes), "tlas_nodes": int(st.numTlasNodes), "tlas_build_ms": float(st.tlasBuildMs),
+        "update_instances_wall_ms": update_ms, "bvh_bytes_per_instanced_triangle": (st.nodeBytes + st.triBytes) / max(instanced, 1),
+        "bvh_bytes": int(st.nodeBytes + st.triBytes),
+        "triangles": int(st.numTriangles), "bvh_nodes": int(st.numNodes),
         "bvh_build_ms": float(st.buildMs), "scene_create_s": create_s,
         "bvh_bytes_per_triangle": (st.nodeBytes + st.triBytes) / max(st.numTriangles, 1),
         "ms_per_frame": ms, "frames_per_s": 1000.0 / ms, "rays_per_pixel": rays / (w * h), "mrays_per_s": rays / 1e6 / (ms * 1e-3),
@@ -92,8 +111,17 @@ def main():
         print(f"host scene: {sc.num_triangles} triangles in {time.time() - t0:.1f} s", flush=True)
         measure(sc, f"instanced field subdiv {subdiv} grid {grid}", 1920, 1080, "gi", 30, 10)
         measure(sc, f"instanced field subdiv {subdiv} grid {grid}", 1920, 1080, "gris", 30, 10)
+    elif which == "field_tlas":
+        subdiv = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+        grid = int(sys.argv[3]) if len(sys.argv) > 3 else 28
+        sc = restirpt.HostScene.field(subdiv, grid, 42, shared=True, two_level=True)
+        name = f"instanced field subdiv {subdiv} grid {grid}, shared mesh"
+        measure(sc, name + ", BLAS + TLAS", 1920, 1080, "gi", 30, 10, time_update=True)
+        measure(sc, name + ", BLAS + TLAS", 1920, 1080, "gris", 30, 10)
+        sc.set_two_level(False)
+        measure(sc, name + ", flattened", 1920, 1080, "gi", 30, 10, time_update=True)
     else:
-        raise SystemExit("usage: gpu_configs.py di | field [subdiv grid]")
+        raise SystemExit("usage: gpu_configs.py di | field [subdiv grid] | field_tlas [subdiv grid]")
 
 
 if __name__ == "__main__":

@@ -183,11 +183,16 @@ __global__ void RT_TRACE_BOUNDS traceQueueTwoLevelKernel(const __grid_constant__
 
 		if (rayIdx != NoRay) {
 			bool finished = false;
+			// ONE node step per iteration for the lanes of both levels (the node format is the same; only the array differs), so a
+			// warp with lanes in the TLAS and lanes in a BLAS does not run the box tests twice
+			LeafHits leaves{ 0u, 0u, 0u };
+			const bool step = ngroup.y > 0x00ffffffu && (inBlas || inst.bits == 0u);
+			if (step) {
+				nodeStep(inBlas ? s.nodes : s.tlasNodes, r, res.bestT, ngroup, stack, sp, leaves);
+				nodeVisits++;
+			}
 			if (!inBlas) {
-				if (inst.bits == 0u && ngroup.y > 0x00ffffffu) {
-					nodeStep(s.tlasNodes, r, res.bestT, ngroup, stack, sp, inst);
-					nodeVisits++;
-				}
+				if (step) inst = leaves;
 				if (inst.bits) {   // enter the next hit instance
 					const uint32_t one = 1u << (31u - uint32_t(__clz(int(inst.bits))));
 					inst.bits ^= one;
@@ -208,11 +213,6 @@ __global__ void RT_TRACE_BOUNDS traceQueueTwoLevelKernel(const __grid_constant__
 				}
 			}
 			else {
-				LeafHits leaves{ 0u, 0u, 0u };
-				if (ngroup.y > 0x00ffffffu) {
-					nodeStep(s.nodes, r, res.bestT, ngroup, stack, sp, leaves);
-					nodeVisits++;
-				}
 				finished = triLoop<MODE, true>(s, r, leaves, tmaxOrig, res, triTests, customIndex, flatBase);
 				if (!finished && ngroup.y <= 0x00ffffffu) {
 					if (sp > baseSp) ngroup = stack[--sp];
