@@ -306,6 +306,12 @@ int rpt_visualize_as(RptFrame* f, const RptScene* s);                          /
 /* PostProcessFrag::render, src/PostProcessFrag.cpp:156-184.  rgba8Out may be NULL (device-only run);
  * otherwise it receives ownedRows*fullWidth*4 bytes (R,G,B,A order) after an implicit sync. */
 int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out);
+/* The same pass with a pipelined read-back (new; the reference presents from the GPU and only reads back for a screenshot,
+ * src/Renderer.cpp:758-793): returns at once with a ticket; the image travels to rgba8Out (pinned host memory, for the copy to
+ * be asynchronous) on a copy stream while the next frame renders.  rpt_readback_wait(ticket) blocks until rgba8Out is complete.
+ * Two read-backs may be in flight; use a different rgba8Out for consecutive tickets. */
+int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out, uint64_t* ticket);
+int rpt_readback_wait(RptFrame* f, uint64_t ticket);
 
 int rpt_sync(RptFrame* f);
 

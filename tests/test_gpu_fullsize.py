@@ -144,3 +144,56 @@ def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, meth
     assert out["two"][1][..., :3].mean() > 0
     assert bitwise_mismatch(out["two"][0], out["one"][0]) == 0
     assert bitwise_mismatch(out["two"][1], out["one"][1]) == 0
+
+
+def test_pipelined_readback_delivers_the_blocking_calls_images(built):
+    """Renderer::drawFrameAsync (rpt_postprocess_async: two device images, a copy stream, tickets) against Renderer::drawFrame
+    (rpt_postprocess with a host pointer) on the same seeds: the same RGBA8 image for every frame, also when the host collects
+    a frame's image only after the next frame has been issued, and when blocking and pipelined calls are mixed"""
+    import ctypes as C
+    import torch
+    from restirpt import P, GRISSettings
+    host = restirpt.host_lib()
+    sc = restirpt.HostScene.room(6000, 7)
+    w, h = 320, 180
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+
+    def renderer():
+        r = host.rh_renderer_create(sc.handle, w, h, 0, 0, h, 0)
+        assert r, host.rh_last_error()
+        host.rh_renderer_set_methods(r, 0, 3, 1, 1, 0)
+        host.rh_renderer_set_gris(r, C.byref(gs))
+        return r
+
+    n = 7
+    ra, rb = renderer(), renderer()
+    want = []
+    for i in range(n):
+        img = np.zeros((h, w, 4), dtype=np.uint8)
+        assert host.rh_renderer_draw_frame(ra, restirpt.hash2(50 + i), img.ctypes.data_as(P)) == 0, host.rh_last_error()
+        want.append(img)
+    pinned = [torch.empty(w * h * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    got, ticket, prev = [], C.c_uint64(), None
+    for i in range(n):
+        if i == 4:   # a blocking frame in between must not disturb the images in flight
+            collect = prev
+            assert host.rh_renderer_wait_readback(rb, collect) == 0
+            got.append(pinned[(i - 1) & 1].numpy().reshape(h, w, 4).copy())
+            img = np.zeros((h, w, 4), dtype=np.uint8)
+            assert host.rh_renderer_draw_frame(rb, restirpt.hash2(50 + i), img.ctypes.data_as(P)) == 0, host.rh_last_error()
+            got.append(img)
+            prev = None
+            continue
+        assert host.rh_renderer_draw_frame_async(rb, restirpt.hash2(50 + i), P(pinned[i & 1].data_ptr()), C.byref(ticket)) == 0, host.rh_last_error()
+        if prev is not None:
+            assert host.rh_renderer_wait_readback(rb, prev) == 0
+            got.append(pinned[(i - 1) & 1].numpy().reshape(h, w, 4).copy())
+        prev = ticket.value
+    assert host.rh_renderer_wait_readback(rb, prev) == 0
+    got.append(pinned[(n - 1) & 1].numpy().reshape(h, w, 4).copy())
+    assert len(got) == n
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), i
+    assert want[-1][..., :3].mean() > 1
+    assert host.rh_renderer_wait_readback(rb, 99) != 0      # no such ticket
+    host.rh_renderer_destroy(ra); host.rh_renderer_destroy(rb)

@@ -51,6 +51,11 @@ struct RptFrame {
 	RptGRISReservoir *gris[2] = { nullptr, nullptr }, *grisTemp = nullptr;
 	RptIntersection* primaryIsec = nullptr;
 	uchar4* rgba8 = nullptr;
+	// pipelined read-back (rpt_postprocess_async): a second device image, a copy stream, one event pair per image
+	uchar4* rgba8Alt = nullptr;
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t postDone[2] = { nullptr, nullptr }, copyDone[2] = { nullptr, nullptr };
+	uint64_t asyncTicket = 0;                  // read-backs issued so far; ticket t used image / events [t & 1]
 	RptCamera camera{}, prevCamera{};
 	size_t pixels() const { return size_t(width) * (storeEnd - storeBegin); }
 
@@ -555,6 +560,9 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->gatherImageOwned) cudaFree(f->gatherImageOwned);
 	if (f->gatherFlagsOwned) cudaFree(f->gatherFlagsOwned);
 	if (f->hostError) cudaFreeHost(f->hostError);
+	if (f->copyStream) { cudaStreamSynchronize(f->copyStream); cudaStreamDestroy(f->copyStream); }
+	for (int i = 0; i < 2; i++) { if (f->postDone[i]) cudaEventDestroy(f->postDone[i]); if (f->copyDone[i]) cudaEventDestroy(f->copyDone[i]); }
+	if (f->rgba8Alt) cudaFree(f->rgba8Alt);
 	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
@@ -794,21 +802,68 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 	PASS_EPILOGUE("rpt_gris_spatial")
 }
 
-RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
-	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
-	CU(f->ctx, cudaSetDevice(f->ctx->device));
+static int postprocessInto(RptFrame* f, const RptPostSettings* st, uchar4* image) {
 	joinTail(f);
 	if (f->gather.connected) {   // the film image on the root must have been released by the gather of the previous frame
 		f->gather.epoch++;
 		launchPeerWait(f->gather.flags + GatherReleaseFlag, nullptr, f->gather.epoch - 1, f->flags + PeerError, f->hostErrorDev, f->stream);
 	}
-	{ PassTimer timer(f, RPT_PASS_POSTPROCESS); launchPostProcess(makeView(f), *st, f->rgba8, f->stream); }
+	{ PassTimer timer(f, RPT_PASS_POSTPROCESS); launchPostProcess(makeView(f), *st, image, f->stream); }
 	if (f->gather.connected) launchPeerSignal(f->gather.flags + GatherArrivalFlag0 + f->gather.strip, nullptr, f->gather.epoch, f->stream);
 	CU(f->ctx, cudaGetLastError());
+	return RPT_OK;
+}
+
+RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
+	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	if (f->asyncTicket) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[(f->asyncTicket - 1) & 1], 0));   // (f->rgba8 may still be being read back)
+	const int rc = postprocessInto(f, st, f->rgba8);
+	if (rc != RPT_OK) return rc;
 	if (rgba8Out) {
 		CU(f->ctx, cudaMemcpyAsync(rgba8Out, f->rgba8, size_t(f->width) * (f->rowEnd - f->rowBegin) * 4, cudaMemcpyDeviceToHost, f->stream));
 		CU(f->ctx, cudaStreamSynchronize(f->stream));
 	}
+	return RPT_OK;
+}
+
+// The same pass with the read-back taken off the frame's stream: the image goes to one of two device buffers, a copy stream
+// carries it to (pinned) host memory while the frame's stream is already rendering the next frame, and the caller collects it
+// with rpt_readback_wait(ticket).  At most two read-backs are in flight: issuing ticket t waits (on the device) for the copy of
+// ticket t - 2, which used the same device image — the caller must have collected that one, or not care about it.
+RPT_API int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out, uint64_t* ticket) {
+	if (!f || !st || !rgba8Out || !ticket) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess_async: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	const size_t bytes = size_t(f->width) * (f->rowEnd - f->rowBegin) * 4;
+	if (!f->copyStream) {
+		CU(f->ctx, cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			CU(f->ctx, cudaEventCreateWithFlags(&f->postDone[i], cudaEventDisableTiming));
+			CU(f->ctx, cudaEventCreateWithFlags(&f->copyDone[i], cudaEventDisableTiming));
+		}
+		CU(f->ctx, cudaMalloc(reinterpret_cast<void**>(&f->rgba8Alt), std::max<size_t>(bytes, 4)));
+	}
+	const uint64_t t = f->asyncTicket;
+	const int slot = int(t & 1);
+	uchar4* image = slot ? f->rgba8Alt : f->rgba8;
+	if (t >= 2) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[slot], 0));
+	const int rc = postprocessInto(f, st, image);
+	if (rc != RPT_OK) return rc;
+	CU(f->ctx, cudaEventRecord(f->postDone[slot], f->stream));
+	CU(f->ctx, cudaStreamWaitEvent(f->copyStream, f->postDone[slot], 0));
+	CU(f->ctx, cudaMemcpyAsync(rgba8Out, image, bytes, cudaMemcpyDeviceToHost, f->copyStream));
+	CU(f->ctx, cudaEventRecord(f->copyDone[slot], f->copyStream));
+	f->asyncTicket = t + 1;
+	*ticket = t;
+	return RPT_OK;
+}
+
+RPT_API int rpt_readback_wait(RptFrame* f, uint64_t ticket) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_readback_wait: NULL frame");
+	if (ticket >= f->asyncTicket) return fail(f->ctx, RPT_ERR_INVALID, "rpt_readback_wait: no such read-back");
+	if (ticket + 2 < f->asyncTicket) return RPT_OK;   // its device image has been reused since: that copy completed long ago
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, cudaEventSynchronize(f->copyDone[ticket & 1]));
 	return RPT_OK;
 }
 

@@ -47,6 +47,17 @@ void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
 	drawStage(1, seed, rgba8Out);
 }
 
+uint64_t Renderer::drawFrameAsync(uint32_t seed, uint8_t* rgba8Out) {
+	if (rpt_frame_peers_in_process(mFrame)) throw std::runtime_error("Renderer::drawFrameAsync: strips of one process are drawn together with Renderer::drawStrips");
+	if (!rgba8Out) throw std::runtime_error("Renderer::drawFrameAsync: no host buffer");
+	uint64_t ticket = 0;
+	drawStage(0, seed, nullptr);
+	drawStage(1, seed, rgba8Out, &ticket);
+	return ticket;
+}
+
+void Renderer::waitReadback(uint64_t ticket) { check(rpt_readback_wait(mFrame, ticket), "rpt_readback_wait"); }
+
 void Renderer::drawStrips(Renderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs) {
 	for (uint32_t i = 0; i < count; i++) strips[i]->drawStage(0, seed, nullptr);
 	for (uint32_t i = 0; i < count; i++) strips[i]->drawStage(1, seed, rgba8Outs ? rgba8Outs[i] : nullptr);
@@ -55,7 +66,7 @@ void Renderer::drawStrips(Renderer* const* strips, uint32_t count, uint32_t seed
 // stage 0: camera upload, G-buffer and everything up to and including the temporal passes (candidate generation, path tracing,
 //          temporal reuse, ReSTIR GI); stage 1: the spatial passes (they read the neighbours' temporal output), post-process, flip.
 // The direct and the indirect method write disjoint buffers, so running di_spatial after gris_temporal changes no result.
-void Renderer::drawStage(int stage, uint32_t seed, uint8_t* rgba8Out) {
+void Renderer::drawStage(int stage, uint32_t seed, uint8_t* rgba8Out, uint64_t* asyncTicket) {
 	if (stage == 0) {
 		// processGUI tail (src/Renderer.cpp:654-660): without accumulation the camera is re-updated every
 		// frame, which zeroes frameIndex so every frame is shown un-accumulated
@@ -121,7 +132,8 @@ void Renderer::drawStage(int stage, uint32_t seed, uint8_t* rgba8Out) {
 	post.correctGamma = settings.correctGamma ? 1u : 0u;
 	post.noDirect = settings.directMethod == RayTracingMethod::None;
 	post.noIndirect = settings.indirectMethod == RayTracingMethod::None;
-	check(rpt_postprocess(mFrame, &post, rgba8Out), "rpt_postprocess");
+	if (asyncTicket) check(rpt_postprocess_async(mFrame, &post, rgba8Out, asyncTicket), "rpt_postprocess_async");
+	else check(rpt_postprocess(mFrame, &post, rgba8Out), "rpt_postprocess");
 
 	check(rpt_frame_flip(mFrame), "rpt_frame_flip");   // mCurFrame ^= 1 (src/Renderer.cpp:567)
 	mFrameCount++;

@@ -39,6 +39,10 @@ public:
 
 	// one frame; rgba8Out may be null (no read-back).  seed = this frame's Camera::seed
 	void drawFrame(uint32_t seed, uint8_t* rgba8Out);
+	// the same frame with a pipelined read-back: returns once the frame is enqueued; the image is complete in rgba8Out (pinned
+	// host memory) after waitReadback(ticket).  Alternate between two host buffers: two read-backs may be in flight.
+	uint64_t drawFrameAsync(uint32_t seed, uint8_t* rgba8Out);
+	void waitReadback(uint64_t ticket);
 	// all strips of one film that live in this process (multi-GPU from one host thread, or several strips on one device): the
 	// same frame on every strip, stage by stage, so that every device-side hand-over wait finds its signal already enqueued
 	static void drawStrips(Renderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs);
@@ -59,7 +63,7 @@ public:
 
 private:
 	void check(int status, const char* what);
-	void drawStage(int stage, uint32_t seed, uint8_t* rgba8Out);
+	void drawStage(int stage, uint32_t seed, uint8_t* rgba8Out, uint64_t* asyncTicket = nullptr);
 
 	RptCtx* mCtx = nullptr;
 	RptScene* mDeviceScene = nullptr;

@@ -114,6 +114,26 @@ int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out) {
 		return -1;
 	}
 }
+int rh_renderer_draw_frame_async(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out, uint64_t* ticket) {
+	try {
+		*ticket = r->r->drawFrameAsync(seed, rgba8Out);
+		return 0;
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		return -1;
+	}
+}
+int rh_renderer_wait_readback(RhRenderer* r, uint64_t ticket) {
+	try {
+		r->r->waitReadback(ticket);
+		return 0;
+	}
+	catch (const std::exception& e) {
+		gLastError = e.what();
+		return -1;
+	}
+}
 int rh_draw_strips(RhRenderer* const* strips, uint32_t count, uint32_t seed, uint8_t* const* rgba8Outs) {
 	try {
 		std::vector<Renderer*> rs(count);

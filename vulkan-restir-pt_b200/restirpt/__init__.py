@@ -201,6 +201,8 @@ DEVICE_API = {
     "rpt_gris_temporal": (C.c_int, [P, P, C.POINTER(GRISSettings)]),
     "rpt_gris_spatial": (C.c_int, [P, P, C.POINTER(GRISSettings)]),
     "rpt_visualize_as": (C.c_int, [P, P]),
+    "rpt_postprocess_async": (C.c_int, [P, C.POINTER(PostSettings), P, C.POINTER(C.c_uint64)]),
+    "rpt_readback_wait": (C.c_int, [P, C.c_uint64]),
     "rpt_postprocess": (C.c_int, [P, C.POINTER(PostSettings), P]),
     "rpt_sync": (C.c_int, [P]),
     "rpt_frame_export_peer": (C.c_int, [P, C.POINTER(PeerInfo)]),
@@ -264,6 +266,8 @@ HOST_API = {
     "rh_renderer_camera": (None, [P, C.POINTER(Camera)]),
     "rh_renderer_set_halo_exchange": (None, [P, HALO_FN, P]),
     "rh_renderer_draw_frame": (C.c_int, [P, C.c_uint32, P]),
+    "rh_renderer_draw_frame_async": (C.c_int, [P, C.c_uint32, P, C.POINTER(C.c_uint64)]),
+    "rh_renderer_wait_readback": (C.c_int, [P, C.c_uint64]),
     "rh_draw_strips": (C.c_int, [C.POINTER(P), C.c_uint32, C.c_uint32, C.POINTER(P)]),
     "rh_renderer_frame": (P, [P]),
     "rh_renderer_scene": (P, [P]),
