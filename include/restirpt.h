@@ -273,6 +273,12 @@ void rpt_scene_destroy(RptScene* scene);
  * geometry ranges.  Flattened scenes rebuild the whole structure on the GPU; two-level scenes rebuild the instance records and
  * the TLAS only.  The new state is committed only if the rebuild succeeds.  Synchronises the device. */
 int rpt_scene_update_instances(RptScene* scene, const RptObjectInstance* instances, uint32_t numInstances);
+/* Per-instance motion vectors (new).  After an update the scene is "in motion": rpt_gbuffer follows every surface point back
+ * through its instance's PREVIOUS placement before it applies lastProjView, so the motion image (and with it the temporal
+ * reprojection of every ReSTIR pass) carries the objects' movement as well as the camera's — the reference's GBuffer.frag:40-44
+ * reprojects the current position only, its scenes being static.  Call rpt_scene_end_motion once the frame that shows the
+ * movement has been issued; until then "previous" stays the placement before the last update. */
+int rpt_scene_end_motion(RptScene* scene);
 int rpt_scene_bvh_stats(const RptScene* scene, RptBvhStats* out);
 
 /* ---- frame resources (replaces Renderer::createRayImage + GBufferPass::createResource,

@@ -22,6 +22,7 @@ def oracle_lib():
         "orc_scene_create": (P, [P]),
         "orc_scene_destroy": (None, [P]),
         "orc_scene_set_brute_force": (None, [P, C.c_int]),
+        "orc_scene_set_prev_instances": (None, [P, P, C.c_uint32]),
         "orc_scene_num_triangles": (C.c_uint32, [P]),
         "orc_frame_create": (P, [C.c_uint32, C.c_uint32]),
         "orc_frame_destroy": (None, [P]),

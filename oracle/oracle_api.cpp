@@ -92,6 +92,11 @@ OrcScene* orc_scene_create(const RptSceneDesc* desc) {
 	return s;
 }
 void orc_scene_destroy(OrcScene* s) { delete s; }
+// the oracle's twin of rpt_scene_update_instances / rpt_scene_end_motion: a scene created from the NEW placements is told the
+// previous ones (numInstances == 0 ends the motion)
+void orc_scene_set_prev_instances(OrcScene* s, const RptObjectInstance* prev, uint32_t numInstances) {
+	s->scene.prevInstances.assign(prev, prev + numInstances);
+}
 void orc_scene_set_brute_force(OrcScene* s, int on) { s->scene.bruteForce = on != 0; }
 uint32_t orc_scene_num_triangles(const OrcScene* s) { return s->scene.numFlatTris; }
 

@@ -129,7 +129,9 @@ void passGBuffer(const Scene& s, Frame2D& f, uint32_t y0, uint32_t y1) {
 		const RptMaterial& mat = s.materials[matIndex];
 		vec3 albedo = (mat.textureIdx == InvalidResourceIdx) ? V3(mat.baseColor) : s.sampleTexture(mat.textureIdx, uvx, uvy);
 
-		vec4 last = xformPoint4(cam.lastProjView, P);
+		// per-instance motion (rpt_scene_update_instances .. rpt_scene_end_motion): the point's position under last frame's placement
+		vec3 Plast = s.prevInstances.empty() ? P : xformPoint(s.prevInstances[instIdx].transform, posL);
+		vec4 last = xformPoint4(cam.lastProjView, Plast);
 		vec2 lastCoord = { (last.x / last.w) * 0.5f + 0.5f, (last.y / last.w) * 0.5f + 0.5f };
 		vec2 motion = { lastCoord.x - uv.x, lastCoord.y - uv.y };
 

@@ -43,6 +43,7 @@ struct Scene {
 	std::vector<RptMaterial> materials;
 	std::vector<int32_t> materialIndices;
 	std::vector<RptObjectInstance> instances;
+	std::vector<RptObjectInstance> prevInstances;   // non-empty while an instance update is "in motion" (rpt_scene_end_motion)
 	std::vector<RptTriangleLight> lights;
 	std::vector<RptLightSampleTableElement> lightTable;
 	std::vector<Texture> textures;

@@ -314,3 +314,36 @@ def test_shared_field_scene_references_one_mesh(orc):
         assert list(a.transform) == list(b.transform)
     sc.set_two_level(True)
     assert sc.desc.flags == restirpt.SCENE_TWO_LEVEL
+
+
+def test_oracle_per_instance_motion_vectors(orc):
+    """orc_scene_set_prev_instances (the oracle's twin of rpt_scene_update_instances .. rpt_scene_end_motion): the motion image
+    carries an object's own movement — for a translation across the view it is the projected shift, to first order"""
+    from common import Backend
+    sc = restirpt.HostScene.cornell()
+    n = sc.desc.numInstances
+    before = (restirpt.ObjectInstance * n)()
+    C.memmove(before, sc.desc.instances, C.sizeof(before))
+    sc.set_object_transform(6, (0.1, 0.0, 0.0), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0))   # the short box, +0.1 along x
+    w, h = 160, 90
+    b = Backend("oracle", sc, w, h)
+    cam = sc.camera(w, h)
+    b.clear(); b.set_camera(cam, cam); b.run("gbuffer")
+    assert np.abs(b.read("MOTION")).max() < 1e-3                       # camera-only motion of a static camera
+    b.lib.orc_scene_set_prev_instances(b.scene, C.cast(before, C.c_void_p), n)
+    b.run("gbuffer")
+    mv = b.read("MOTION")
+    ids = b.read("ALBEDO_MATID")[..., 1] & 0xffff
+    depth = b.read("DEPTH_NORMAL")[..., 0]
+    box = (ids == 6) & (depth > 0)
+    assert box.sum() > 200 and np.abs(mv[~box]).max() < 1e-3
+    # the camera looks down +y from (0, -3.4, 1): x is screen-right, so last frame the point was further LEFT (negative u motion);
+    # at distance d the shift is 0.1 / (2 d tan(fov/2) aspect) of the film width
+    d = depth[box]
+    expect = -0.1 / (2.0 * d * math.tan(math.radians(22.5)) * (w / h))
+    assert np.abs(mv[box][:, 0] - expect).max() < 0.25 * np.abs(expect).max()
+    assert np.abs(mv[box][:, 1]).max() < 0.2 * np.abs(expect).max()
+    b.lib.orc_scene_set_prev_instances(b.scene, None, 0)
+    b.run("gbuffer")
+    assert np.abs(b.read("MOTION")).max() < 1e-3
+    b.close()

@@ -234,6 +234,7 @@ def test_dynamic_scene_update_equals_a_fresh_scene(device):
     sc.set_object_transform(6, (0.2, 0.15, 0.3), (1.0, 1.0, 1.0), (25.0, 0.0, 0.0))   # lift and turn the short box
     restirpt.check(device.ctx, device.lib.rpt_scene_update_instances(moved.scene, sc.desc.instances, sc.desc.numInstances),
                    "rpt_scene_update_instances")
+    restirpt.check(device.ctx, device.lib.rpt_scene_end_motion(moved.scene), "rpt_scene_end_motion")   # (a fresh scene has no "previous placement")
     fresh = Backend("cuda", sc, w, h, device)
     cpu = Backend("oracle", sc, w, h)
     cam = sc.camera(w, h)
@@ -300,6 +301,7 @@ def test_two_level_update_instances_rebuilds_the_tlas_only(device):
     sc.set_object_transform(7, (-0.9, 0.6, 0.8), (0.7, 0.7, 0.7), (75.0, 0.0, 0.0))
     restirpt.check(device.ctx, device.lib.rpt_scene_update_instances(moved.scene, sc.desc.instances, sc.desc.numInstances),
                    "rpt_scene_update_instances")
+    restirpt.check(device.ctx, device.lib.rpt_scene_end_motion(moved.scene), "rpt_scene_end_motion")   # (a fresh scene has no "previous placement")
     after = restirpt.BvhStats()
     device.lib.rpt_scene_bvh_stats(moved.scene, after)
     assert after.numNodes == before.numNodes and after.numTriangles == before.numTriangles and after.tlasBuildMs > 0
@@ -374,3 +376,42 @@ def test_scene_arrays_are_validated_at_the_boundary(device):
     for mutate, word in ((bad_index, "index"), (bad_material, "material"), (bad_instance, "instance"), (bad_table, "failId"), (bad_count, "numMaterialIndices")):
         msg, _ = attempt(mutate)
         assert word in msg, (word, msg)
+
+
+@pytest.mark.parametrize("two_level", [False, True])
+def test_per_instance_motion_vectors(device, two_level):
+    """After rpt_scene_update_instances the G-buffer's motion image follows every surface point back through its instance's
+    previous placement (until rpt_scene_end_motion): bit-exact against the oracle's twin, different from the camera-only motion
+    exactly on the moved object, and equal to it again once the motion has ended"""
+    import ctypes as C
+    sc = restirpt.HostScene.cornell()
+    if two_level:
+        sc.set_two_level(True)
+    w, h = 160, 90
+    gpu = Backend("cuda", sc, w, h, device)
+    n = sc.desc.numInstances
+    before = (restirpt.ObjectInstance * n)()
+    C.memmove(before, sc.desc.instances, C.sizeof(before))
+    sc.set_object_transform(6, (0.12, -0.1, 0.05), (1.0, 1.0, 1.0), (10.0, 0.0, 0.0))      # the short box slides and turns
+    restirpt.check(device.ctx, device.lib.rpt_scene_update_instances(gpu.scene, sc.desc.instances, n), "rpt_scene_update_instances")
+    cpu = Backend("oracle", sc, w, h)                                                       # the new placements ...
+    cpu.lib.orc_scene_set_prev_instances(cpu.scene, C.cast(before, C.c_void_p), n)          # ... and the old ones
+    cam = sc.camera(w, h)
+    for b in (gpu, cpu):
+        b.clear(); b.set_camera(cam, cam); b.run("gbuffer")
+    moving, want = gpu.read("MOTION"), cpu.read("MOTION")
+    assert bitwise_mismatch(moving, want) == 0
+    ids = gpu.read("ALBEDO_MATID").reshape(h, w, 2)[..., 1] & 0xffff
+    depth = gpu.read("DEPTH_NORMAL").reshape(h, w, 4)[..., 0]
+    moved_px = (ids == 6) & (depth > 0)
+    assert moved_px.sum() > 200
+    mv = moving.reshape(h, w, 2)
+    assert np.abs(mv[moved_px]).max() > 1.0 / w                     # the box moved by more than a pixel
+    assert np.abs(mv[~moved_px]).max() < 1e-3                       # static camera: nothing else moves
+    restirpt.check(device.ctx, device.lib.rpt_scene_end_motion(gpu.scene), "rpt_scene_end_motion")
+    cpu.lib.orc_scene_set_prev_instances(cpu.scene, None, 0)
+    for b in (gpu, cpu):
+        b.run("gbuffer")
+    still = gpu.read("MOTION")
+    assert bitwise_mismatch(still, cpu.read("MOTION")) == 0 and np.abs(still).max() < 1e-3
+    gpu.close(); cpu.close()

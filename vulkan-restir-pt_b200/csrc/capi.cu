@@ -36,6 +36,7 @@ struct RptScene {
 	bool twoLevel = false;
 	TwoLevelState tl{};               // two-level scenes: BLASes, TLAS, instance records (view.nodes / tris alias tl.blas*)
 	std::vector<MeshRange> geometry;  // (indexOffset, indexCount) of every instance, as created
+	RptObjectInstance* prevInstances = nullptr;   // device copy of the placements before the last update (per-instance motion vectors)
 };
 
 struct RptFrame {
@@ -381,15 +382,28 @@ RPT_API int rpt_scene_update_instances(RptScene* s, const RptObjectInstance* ins
 			adoptBvh(s, bo);
 		}
 	}
+	if (e == cudaSuccess) {
+		// the placements being replaced become "last frame's" for the G-buffer's motion vectors, until rpt_scene_end_motion
+		if (!s->prevInstances) e = cudaMalloc(reinterpret_cast<void**>(&s->prevInstances), std::max<size_t>(numInstances, 1) * sizeof(RptObjectInstance));
+		if (e == cudaSuccess) e = cudaMemcpy(s->prevInstances, s->view.instances, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyDeviceToDevice);
+		if (e == cudaSuccess) s->view.prevInstances = s->prevInstances;
+	}
 	if (e == cudaSuccess) e = cudaMemcpy(const_cast<RptObjectInstance*>(s->view.instances), staged, size_t(numInstances) * sizeof(RptObjectInstance), cudaMemcpyDeviceToDevice);
 	cudaFree(staged);
 	if (e != cudaSuccess) return cudaFail(ctx, e, "rpt_scene_update_instances: rebuild");
 	return RPT_OK;
 }
 
+RPT_API int rpt_scene_end_motion(RptScene* s) {
+	if (!s) return fail(nullptr, RPT_ERR_INVALID, "rpt_scene_end_motion: NULL scene");
+	s->view.prevInstances = nullptr;   // (kernel parameters are by value: frames already enqueued keep the view they were given)
+	return RPT_OK;
+}
+
 RPT_API void rpt_scene_destroy(RptScene* s) {
 	if (!s) return;
 	cudaSetDevice(s->ctx->device);
+	if (s->prevInstances) cudaFree(s->prevInstances);
 	for (void* p : s->allocations) cudaFree(p);
 	if (s->twoLevel) s->tl.release();
 	else {

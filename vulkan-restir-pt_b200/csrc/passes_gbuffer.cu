@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY) gbufferKernel(const __
 	const Mat mat = loadMaterial(s, matIndex);
 	const float3 albedo = (mat.textureIdx == InvalidResourceIdx) ? mat.baseColor : sampleTexture(s, mat.textureIdx, uvx, uvy);
 
-	const float4 last = xformPoint4(cam.lastProjView, P);
+	// GBuffer.frag:40-44 reprojects the CURRENT world position (the reference's scenes are static).  While an instance update is
+	// in motion the surface point is followed back through its instance's previous placement, so the motion vector carries
+	// the object's movement as well as the camera's.
+	const float3 Plast = s.prevInstances == nullptr ? P : xformPoint(s.prevInstances[instIdx].transform, interp(f3(p0), f3(p1), f3(p2), bary));
+	const float4 last = xformPoint4(cam.lastProjView, Plast);
 	const float2 lastCoord = make_float2((last.x / last.w) * 0.5f + 0.5f, (last.y / last.w) * 0.5f + 0.5f);
 	const float2 motion = make_float2(lastCoord.x - uv.x, lastCoord.y - uv.y);
 

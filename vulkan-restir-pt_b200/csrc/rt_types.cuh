@@ -66,6 +66,7 @@ struct SceneView {
 	const RptMaterial* materials;
 	const int32_t* materialIndices;
 	const RptObjectInstance* instances;
+	const RptObjectInstance* prevInstances;   // last frame's placements while an rpt_scene_update_instances is "in motion", else nullptr
 	const RptTriangleLight* lights;
 	const RptLightSampleTableElement* lightTable;
 	const TextureView* textures;

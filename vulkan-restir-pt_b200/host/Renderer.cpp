@@ -34,6 +34,7 @@ Renderer::~Renderer() {
 void Renderer::updateInstances(const Scene& scene) {
 	check(rpt_scene_update_instances(mDeviceScene, scene.objectInstances.data(), uint32_t(scene.objectInstances.size())),
 	      "rpt_scene_update_instances");
+	mMotionPending = true;   // the next frame's G-buffer carries the objects' motion; it ends with that frame
 }
 
 void Renderer::drawFrame(uint32_t seed, uint8_t* rgba8Out) {
@@ -135,6 +136,7 @@ void Renderer::drawStage(int stage, uint32_t seed, uint8_t* rgba8Out, uint64_t* 
 	if (asyncTicket) check(rpt_postprocess_async(mFrame, &post, rgba8Out, asyncTicket), "rpt_postprocess_async");
 	else check(rpt_postprocess(mFrame, &post, rgba8Out), "rpt_postprocess");
 
+	if (mMotionPending) { check(rpt_scene_end_motion(mDeviceScene), "rpt_scene_end_motion"); mMotionPending = false; }
 	check(rpt_frame_flip(mFrame), "rpt_frame_flip");   // mCurFrame ^= 1 (src/Renderer.cpp:567)
 	mFrameCount++;
 }

@@ -69,6 +69,7 @@ private:
 	RptScene* mDeviceScene = nullptr;
 	RptFrame* mFrame = nullptr;
 	Camera mCamera, mPrevCamera;
+	bool mMotionPending = false;
 	bool mClearNext = false;
 	uint32_t mFrameCount = 0;
 	HaloExchangeFn mHaloFn = nullptr;

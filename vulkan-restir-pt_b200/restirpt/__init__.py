@@ -180,6 +180,7 @@ DEVICE_API = {
     "rpt_ctx_create": (C.c_int, [C.c_int, C.POINTER(P)]),
     "rpt_ctx_destroy": (None, [P]),
     "rpt_scene_create": (C.c_int, [P, C.POINTER(SceneDesc), C.POINTER(P)]),
+    "rpt_scene_end_motion": (C.c_int, [P]),
     "rpt_scene_destroy": (None, [P]),
     "rpt_scene_update_instances": (C.c_int, [P, P, C.c_uint32]),
     "rpt_scene_bvh_stats": (C.c_int, [P, C.POINTER(BvhStats)]),
