@@ -305,7 +305,7 @@ class Arm:
         balance_log = []
         if bounds is None:
             bounds = multigpu.partition(fh, world)
-            rounds = 0 if world == 1 or self.args.no_balance else 3
+            rounds = 0 if world == 1 or self.args.no_balance else 4
             for _ in range(rounds):
                 r, frame, link = self.open_strip(fw, fh, *bounds[rank])
                 for i in range(6):
