@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Regenerates profiles/ncu_traffic.json from this round's ncu captures (no hand-copied numbers).
 
-Captures (tools/gpu_r2_capture.sh, one B200, the bench.py frame: VeachAjar 1920x1080 ReSTIR PT):
+Captures (tools/gpu_capture.sh, one B200, the bench.py frame: VeachAjar 1920x1080 ReSTIR PT):
     ncu --set full --cache-control none --clock-control none -k regex:traceQueue -s 39 -c 13 ...   -> one frame's 13 traversal launches
     ncu --set full --cache-control none --clock-control none -k regex:grisBounceKernel -s 18 -c 6 ...  -> one frame's 6 bounce launches
 (--cache-control none: the scene's BVH stays in L2 between launches as in the real frame; ncu's default flush would show the
