@@ -54,6 +54,9 @@ def oracle_lib():
         "orc_sincos": (None, [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "orc_round_through_half": (C.c_float, [C.c_float]),
         "orc_concentric_disk": (None, [C.c_float, C.c_float, C.POINTER(C.c_float)]),
+        "orc_sample_light": (None, [P, P, P, P, P, P, P, P, P, P]),
+        "orc_is_bsdf_delta": (C.c_int, [P]),
+        "orc_is_bsdf_connectible": (C.c_int, [P]),
         "orc_eval_bsdf": (None, [P, P, P, P, P, P, C.POINTER(C.c_float)]),
         "orc_sample_bsdf": (C.c_int, [P, P, P, P, P, P, P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     }

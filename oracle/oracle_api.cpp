@@ -181,6 +181,16 @@ void orc_eval_bsdf(const RptMaterial* m, const float* albedo, const float* n, co
 	out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
 	*pdf = evalPdf(*m, V3(n), V3(wo), V3(wi));
 }
+// light_sampling.glsl:24-53 on the scene's light table (for the pin against the reference's own text, tests/test_cpu_ref_pins.py)
+void orc_sample_light(const OrcScene* s, const float* ref, const float* r4, float* radiance, float* wi, float* dist, float* pdf,
+                      float* jacobian, float* bary, uint32_t* id) {
+	LightSample L = sampleLight(s->scene, V3(ref), vec4{ r4[0], r4[1], r4[2], r4[3] });
+	radiance[0] = L.radiance.x; radiance[1] = L.radiance.y; radiance[2] = L.radiance.z;
+	wi[0] = L.wi.x; wi[1] = L.wi.y; wi[2] = L.wi.z;
+	*dist = L.dist; *pdf = L.pdf; *jacobian = L.jacobian; bary[0] = L.bary.x; bary[1] = L.bary.y; *id = L.id;
+}
+int orc_is_bsdf_delta(const RptMaterial* m) { return isBSDFDelta(*m) ? 1 : 0; }
+int orc_is_bsdf_connectible(const RptMaterial* m) { return isBSDFConnectible(*m) ? 1 : 0; }
 int orc_sample_bsdf(const RptMaterial* m, const float* albedo, const float* n, const float* wo, const float* r3, float* wi, float* bsdf, float* pdf, uint32_t* type) {
 	BSDFSample s;
 	bool ok = sampleBSDF(*m, V3(albedo), V3(n), V3(wo), V3(r3), s);
