@@ -200,4 +200,36 @@ int orc_sample_bsdf(const RptMaterial* m, const float* albedo, const float* n, c
 	return ok ? 1 : 0;
 }
 
+// ---- "driver" call-backs for the reference's shaders compiled for the CPU (oracle/ref/ref_shaders.cpp, RefDriver) ----------------
+// What the Vulkan driver supplies to the reference — ray / triangle intersection, texture and G-buffer filtering — is supplied to
+// its shader text here by the oracle's definitions of them, so that tests/test_cpu_ref_shaders.py compares shader text with
+// restatement and nothing else.
+struct OrcDriverCtx { const OrcScene* scene; const OrcFrame* frame; };
+OrcDriverCtx* orc_driver_create(const OrcScene* s, const OrcFrame* f) { return new OrcDriverCtx{ s, f }; }
+void orc_driver_destroy(OrcDriverCtx* c) { delete c; }
+int orc_cb_trace_closest(void* user, const float* o, float tmin, const float* d, float tmax, float* bary, uint32_t* instance, uint32_t* primitive) {
+	const Scene& sc = static_cast<OrcDriverCtx*>(user)->scene->scene;
+	Intersection i = sc.traceClosestHit(V3(o), tmin, V3(d), tmax);
+	if (i.instanceIdx == InvalidHitIndex) return 0;
+	bary[0] = i.bary.x; bary[1] = i.bary.y; *instance = i.instanceIdx; *primitive = i.triangleIdx;
+	return 1;
+}
+int orc_cb_trace_any(void* user, const float* o, float tmin, const float* d, float tmax) {
+	return static_cast<OrcDriverCtx*>(user)->scene->scene.traceShadow(V3(o), tmin, V3(d), tmax) ? 1 : 0;
+}
+uint32_t orc_cb_count_candidates(void* user, const float* o, const float* d) {
+	return static_cast<OrcDriverCtx*>(user)->scene->scene.countCandidates(V3(o), V3(d));
+}
+void orc_cb_sample_texture(void* user, uint32_t tex, float u, float v, float* rgb) {
+	vec3 c = static_cast<OrcDriverCtx*>(user)->scene->scene.sampleTexture(tex, u, v);
+	rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
+}
+void orc_cb_sample_depth_normal(void* user, int which, float u, float v, float* out4) {
+	const Frame2D& f = static_cast<OrcDriverCtx*>(user)->frame->frame;
+	vec4 r = fetchDepthNormalBilinear(f.depthNormal[which ? (f.cur ^ 1u) : f.cur], f.width, f.height, vec2{ u, v });
+	out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+// the frame's buffers in place (the reference's shaders write their reservoirs / outputs into a second oracle frame)
+void* orc_frame_ptr(OrcFrame* f, int id) { size_t bytes; return f->frame.bufferPtr(RptBufferId(id), &bytes); }
+
 } // extern "C"

@@ -35,7 +35,9 @@ inline vec3 operator-(vec3 a, vec3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z
 inline vec3 operator-(vec3 a) { return { -a.x, -a.y, -a.z }; }
 inline vec3 operator*(vec3 a, vec3 b) { return { a.x * b.x, a.y * b.y, a.z * b.z }; }
 inline vec3 operator*(vec3 a, float s) { return { a.x * s, a.y * s, a.z * s }; }
-inline vec3 operator/(vec3 a, float s) { return { a.x / s, a.y / s, a.z / s }; }
+// vec3 / float: one correctly rounded reciprocal, three multiplies (the form a GPU compiler gives GLSL's vector-by-scalar division;
+// part of the numeric contract shared with rt_math.cuh)
+inline vec3 operator/(vec3 a, float s) { const float r = 1.0f / s; return { a.x * r, a.y * r, a.z * r }; }
 inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
 inline vec3& operator*=(vec3& a, float s) { a = a * s; return a; }
@@ -59,8 +61,10 @@ inline vec3 mix(vec3 a, vec3 b, float t) { return { mix(a.x, b.x, t), mix(a.y, b
 inline vec3 mix(vec3 a, vec3 b, vec3 t) { return { mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z) }; }
 // GLSL reflect(I, N) = I - 2 dot(N, I) N
 inline vec3 reflect(vec3 I, vec3 N) { float k = 2.0f * dot(N, I); return I - N * k; }
-// a*w.x + b*w.y + c*w.z (barycentric interpolation)
-inline float interp(float a, float b, float c, vec3 w) { return fma_(c, w.z, fma_(b, w.y, a * w.x)); }
+// a*w.x + b*w.y + c*w.z (barycentric interpolation), evaluated as the shader text writes it (ray_layouts.glsl:72-75: no built-in is
+// involved, so nothing is fused) — with this the reference's own shaders, compiled for the CPU, reproduce every buffer of every
+// pass bit for bit (tests/test_cpu_ref_shaders.py)
+inline float interp(float a, float b, float c, vec3 w) { return a * w.x + b * w.y + c * w.z; }
 inline vec3 interp(vec3 a, vec3 b, vec3 c, vec3 w) {
 	return { interp(a.x, b.x, c.x, w), interp(a.y, b.y, c.y, w), interp(a.z, b.z, c.z, w) };
 }

@@ -1,4 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_scene.h).
+#include <cstdio>
+#include <cstdlib>
 #include "oracle_scene.h"
 #include <algorithm>
 #include <cmath>
@@ -281,8 +283,15 @@ void Scene::forCandidates(vec3 o, vec3 d, float tmin, TFar tfar, Fn fn) const {
 	}
 }
 
+// debugging aid for the lock-step comparisons with the reference's shaders: prints every ray of the calling thread (ORC_RAY_LOG=1)
+static const bool gRayLog = std::getenv("ORC_RAY_LOG") != nullptr;
+static void logRay(const char* kind, vec3 o, float tmin, vec3 d, float tmax) {
+	std::fprintf(stderr, "%s o %.9g %.9g %.9g tmin %.9g d %.9g %.9g %.9g tmax %.9g\n", kind, o.x, o.y, o.z, tmin, d.x, d.y, d.z, tmax);
+}
+
 Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool skipLights) const {
 	counters.closestRays.fetch_add(1, std::memory_order_relaxed);
+	if (gRayLog) logRay("closest", o, tmin, d, tmax);
 	Intersection best;
 	best.bary = { 0.f, 0.f };
 	best.instanceIdx = InvalidHitIndex;
@@ -308,6 +317,7 @@ Intersection Scene::traceClosestHit(vec3 o, float tmin, vec3 d, float tmax, bool
 
 bool Scene::traceShadow(vec3 o, float tmin, vec3 d, float tmax) const {
 	counters.shadowRays.fetch_add(1, std::memory_order_relaxed);
+	if (gRayLog) logRay("shadow ", o, tmin, d, tmax);
 	if (!bruteForce && degenerateRay(o, tmin, d, tmax)) return false;
 	bool hit = false;
 	forCandidates(o, d, tmin, [&] { return hit ? -1.0f : tmax; }, [&](const WorldTri& t, uint32_t, uint32_t, vec3 ro, vec3 rd) {

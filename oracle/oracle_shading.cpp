@@ -47,7 +47,7 @@ static bool lambertSample(vec3 albedo, vec3 n, vec2 r, BSDFSample& s) {
 
 // :149-172
 static bool dielectricSample(RptMaterial mat, vec3 albedo, vec3 n, vec3 wo, vec3 r, BSDFSample& s) {
-	float pdfReflect = fresnelSchlick(dot(n, wo), mat.ior);
+	float pdfReflect = fresnel(dot(n, wo), mat.ior);
 	s.bsdf = albedo;
 	if (r.z < pdfReflect) {
 		s.wi = reflect(-wo, n);

@@ -34,6 +34,21 @@ inline float fresnelSchlick(float cosTheta, float ior) {                       /
 inline vec3 fresnelSchlick(float cosTheta, vec3 f0) {                          // :36-38
 	return mix(f0, V3(1.0f), pow5(1.0f - cosTheta));
 }
+// :40-57.  `#define MATERIAL_DIELECTRIC_USE_SCHLICK_APPROX true` + `#if MATERIAL_DIELECTRIC_USE_SCHLICK_APPROX`: inside #if the GLSL
+// preprocessor gives an identifier that is no macro — `true` — the value 0, so the compiled reference takes the #else branch, the
+// exact Fresnel equations, whatever the macro's name promises (found by running the reference's own shaders on the CPU,
+// tests/test_cpu_ref_shaders.py; DESIGN.md §2 "defined behaviours" 9)
+inline float fresnel(float cosIn, float ior) {
+	if (cosIn < 0) {
+		ior = 1.0f / ior;
+		cosIn = -cosIn;
+	}
+	float sinIn = std::sqrt(1.0f - cosIn * cosIn);
+	float sinTr = sinIn / ior;
+	if (sinTr >= 1.0f) return 1.0f;
+	float cosTr = std::sqrt(1.0f - sinTr * sinTr);
+	return (square((cosIn - ior * cosTr) / (cosIn + ior * cosTr)) + square((ior * cosIn - cosTr) / (ior * cosIn + cosTr))) * 0.5f;
+}
 inline float schlickG(float cosTheta, float alpha) {                           // :59-62
 	float a = alpha * 0.5f;
 	return cosTheta / (cosTheta * (1.0f - a) + a);

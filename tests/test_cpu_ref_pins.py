@@ -312,3 +312,62 @@ def test_light_sampling_equals_the_references_light_sampling_glsl(glsl):
                 assert abs(A[k].value - Bv[k].value) <= 2e-5 * abs(A[k].value) + 1e-7, k
             assert list(A[5]) == list(Bv[5])                     # barycentrics: one IEEE sqrt, two multiplies — the same bits
         b.close()
+
+
+# ---- the same library with the numeric contract's built-ins (refc_*): bit for bit -------------------------------------------------
+def test_bsdf_library_with_contract_builtins_equals_the_oracle_bit_for_bit(glsl):
+    """material.glsl compiled with the built-in library of the numeric contract (glsl_compat.h -DGLSL_BUILTINS_CONTRACT: dot / cross /
+    normalize / mix / reflect / mat3 * vec3 / sin / cos as oracle_math.h evaluates them): evalBSDF, evalPdf and sampleBSDF of every
+    material type return the oracle's bits on 3000 random configurations each — including the dielectric, whose Fresnel term is
+    the #else branch of material.glsl:41-57 (`#if MATERIAL_DIELECTRIC_USE_SCHLICK_APPROX` is false: the macro is `true`, no macro)"""
+    ref, orc = glsl
+    f32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    ref.refc_eval_bsdf.restype, ref.refc_eval_bsdf.argtypes = None, [C.c_void_p] + [f32p] * 6
+    ref.refc_sample_bsdf.restype, ref.refc_sample_bsdf.argtypes = C.c_int, [C.c_void_p] + [f32p] * 7 + [u32p]
+    bits = lambda a: np.array(list(a), dtype=np.float32).view(np.uint32).tolist()
+    for mtype, metallic, roughness, ior in MATS + [(0, 0.0, 0.5, 1.5), (5, 0.0, 0.2, 1.5)]:
+        mat = restirpt.Material()
+        mat.baseColor[:] = [0.8, 0.6, 0.3]
+        mat.type, mat.textureIdx, mat.metallic, mat.roughness, mat.ior = mtype, 0xffffffff, metallic, roughness, ior
+        mp = C.cast(C.byref(mat), C.c_void_p)
+        rng = np.random.default_rng(mtype * 7 + 1)
+        albedo = _f(0.7, 0.5, 0.4)
+        for nrm, wo, wi, r in zip(_dirs(rng, 3000), _dirs(rng, 3000), _dirs(rng, 3000), rng.random((3000, 3)).astype(np.float32)):
+            if np.dot(nrm, wo) < 0 and mtype != 4:
+                wo = -wo
+            fa, fb, pa, pb = _f(0, 0, 0), _f(0, 0, 0), C.c_float(), C.c_float()
+            ref.refc_eval_bsdf(mp, albedo, _f(*nrm), _f(*wo), _f(*wi), fa, C.byref(pa))
+            orc.orc_eval_bsdf(mp, albedo, _f(*nrm), _f(*wo), _f(*wi), fb, C.byref(pb))
+            assert bits(fa) == bits(fb) and bits([pa.value]) == bits([pb.value]), (mtype, list(fa), list(fb))
+            wa, wb, ba, bb, ta, tb = _f(0, 0, 0), _f(0, 0, 0), _f(0, 0, 0), _f(0, 0, 0), C.c_uint32(), C.c_uint32()
+            oka = ref.refc_sample_bsdf(mp, albedo, _f(*nrm), _f(*wo), _f(*r), wa, ba, C.byref(pa), C.byref(ta))
+            okb = orc.orc_sample_bsdf(mp, albedo, _f(*nrm), _f(*wo), _f(*r), wb, bb, C.byref(pb), C.byref(tb))
+            assert oka == okb and ta.value == tb.value, (mtype, oka, okb, ta.value, tb.value)
+            if oka:
+                assert bits(wa) == bits(wb) and bits(ba) == bits(bb) and bits([pa.value]) == bits([pb.value]), (mtype, list(wa), list(wb))
+
+
+def test_light_sampling_with_contract_builtins_equals_the_oracle_bit_for_bit(glsl):
+    ref, orc = glsl
+    from common import Backend
+    f32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    ref.refc_sample_light.restype, ref.refc_sample_light.argtypes = None, [C.c_void_p, C.c_void_p] + [f32p] * 8 + [u32p]
+    scenes = [restirpt.HostScene.cornell(), restirpt.HostScene.room(2000, 3)]
+    xml = prepare_assets.ajar_xml()
+    if xml:
+        scenes.append(restirpt.HostScene.xml(xml))
+    rng = np.random.default_rng(19)
+    for sc in scenes:
+        b = Backend("oracle", sc, 8, 8)
+        d = sc.desc
+        for _ in range(3000):
+            p = _f(*rng.uniform(-2.0, 2.0, 3))
+            r4 = _f(*rng.random(4).astype(np.float32))
+            A = [_f(0, 0, 0), _f(0, 0, 0), C.c_float(), C.c_float(), C.c_float(), _f(0, 0), C.c_uint32()]
+            Bv = [_f(0, 0, 0), _f(0, 0, 0), C.c_float(), C.c_float(), C.c_float(), _f(0, 0), C.c_uint32()]
+            ref.refc_sample_light(d.lightSampleTable, d.triangleLights, p, r4, A[0], A[1], C.byref(A[2]), C.byref(A[3]), C.byref(A[4]), A[5], C.byref(A[6]))
+            orc.orc_sample_light(b.scene, p, r4, Bv[0], Bv[1], C.byref(Bv[2]), C.byref(Bv[3]), C.byref(Bv[4]), Bv[5], C.byref(Bv[6]))
+            va = np.array(list(A[0]) + list(A[1]) + [A[2].value, A[3].value, A[4].value] + list(A[5]), dtype=np.float32).view(np.uint32)
+            vb = np.array(list(Bv[0]) + list(Bv[1]) + [Bv[2].value, Bv[3].value, Bv[4].value] + list(Bv[5]), dtype=np.float32).view(np.uint32)
+            assert A[6].value == Bv[6].value and np.array_equal(va, vb)
+        b.close()

@@ -26,6 +26,7 @@ import restirpt
 from restirpt import DISettings, GRISSettings
 from common import Backend, FrameDriver, METHOD_PASSES, bitwise_mismatch, camera_rays
 from test_gpu_parity import PASS_BUFFERS
+import ref_shaders
 
 pytestmark = pytest.mark.gpu
 
@@ -46,11 +47,15 @@ def ajar(built):
     return restirpt.HostScene.xml(xml)
 
 
-def lockstep(sc, w, h, device, method, frames, moves=None, seeds=None, di=None, gris=None):
+def lockstep(sc, w, h, device, method, frames, moves=None, seeds=None, di=None, gris=None, against="oracle"):
     """Runs both implementations pass by pass and compares the buffers each pass writes; returns the per-buffer mismatch
-    counts (empty = bit-exact) and the last output images of the CUDA side."""
+    counts (empty = bit-exact) and the last output images of the CUDA side.  against="reference": the other side is not the
+    oracle's restatement but the reference's own compute shaders compiled for the CPU (tests/ref_shaders.py, oracle/_ref/libref.so;
+    the G-buffer — rasterised in the reference — stays the oracle's)."""
     gpu = Backend("cuda", sc, w, h, device)
     cpu = Backend("oracle", sc, w, h)
+    if against == "reference":
+        cpu = ref_shaders.RefShaderBackend(cpu, sc, True)
     drivers = [FrameDriver(sc.camera(w, h)), FrameDriver(sc.camera(w, h))]
     settings = {"di": di, "gris": gris}
     bad, checked, last = {}, 0, {}
@@ -154,3 +159,31 @@ def test_ajar_closest_hit_ids_two_million_rays(device, ajar):
     cpu.lib.orc_scene_set_brute_force(cpu.scene, 0)
     assert np.array_equal(c, b[pick])
     gpu.close(); cpu.close()
+
+
+# ---- the CUDA library against the reference's OWN shaders (compiled for the CPU from /root/reference, oracle/_ref/libref.so) -----
+needs_ref = pytest.mark.skipif(not ref_shaders.available(), reason="oracle/_ref/libref.so did not travel (built where /root/reference "
+                               "exists): CUDA is NOT compared with the reference's own shaders in this run")
+
+
+@needs_ref
+def test_config1_cuda_equals_the_references_own_shaders(device):
+    sc = restirpt.HostScene.cornell()
+    bad, checked, _ = lockstep(sc, 640, 360, device, "naive", 3, moves=DOLLY[:3], against="reference")
+    assert checked == 3 * (4 + 2) and not bad, f"config 1 vs di_naive.comp / gi_naive.comp: {bad}"
+
+
+@needs_ref
+def test_config2_cuda_equals_the_references_own_shaders(device, ajar):
+    bad, checked, last = lockstep(ajar, 1280, 720, device, "di", 3, moves=DOLLY[:3], di=DISettings(0, 0, 1, 1), against="reference")
+    assert checked == 3 * (4 + 1 + 1 + 2) and not bad, f"config 2 vs di_path_gen / di_temporal / di_spatial.comp: {bad}"
+    assert (last["DI_THIS"]["sampleCount"] > 1).mean() > 0.3
+
+
+@needs_ref
+def test_config3_cuda_equals_the_references_own_shaders(device, ajar):
+    """rpt_gris_pathtrace / _temporal / _spatial on a B200 against gris_path_trace.comp, gris_resample_temporal.comp and
+    gris_resample_spatial.comp executed on the host: VeachAjar 1920x1080 {Hybrid, 1, 1, 1, 20}, dolly, every reservoir and output"""
+    bad, checked, last = lockstep(ajar, 1920, 1080, device, "gris", 2, moves=DOLLY[:2], gris=GRISSettings(2, 1.0, 1, 1, 20), against="reference")
+    assert checked == 2 * (4 + 1 + 1 + 2) and not bad, f"config 3 vs the reference's GRIS shaders: {bad}"
+    assert (last["GRIS_THIS"]["sampleCount"] > 1).mean() > 0.3

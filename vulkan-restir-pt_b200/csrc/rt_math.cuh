@@ -28,7 +28,9 @@ RT_DEV float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y 
 RT_DEV float3 operator-(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
 RT_DEV float3 operator*(float3 a, float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
 RT_DEV float3 operator*(float3 a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
-RT_DEV float3 operator/(float3 a, float s) { return make_float3(a.x / s, a.y / s, a.z / s); }
+// vec3 / float: one correctly rounded reciprocal and three multiplies — the form a GPU compiler gives GLSL's vector-by-scalar
+// division (the oracle divides the same way; three IEEE divisions per vector cost grisBounceKernel 9 %, profiles/r2_13_*)
+RT_DEV float3 operator/(float3 a, float s) { const float r = 1.0f / s; return make_float3(a.x * r, a.y * r, a.z * r); }
 RT_DEV float3& operator+=(float3& a, float3 b) { a = a + b; return a; }
 RT_DEV float3& operator*=(float3& a, float3 b) { a = a * b; return a; }
 RT_DEV float3& operator*=(float3& a, float s) { a = a * s; return a; }
@@ -47,7 +49,9 @@ RT_DEV float mix(float a, float b, float t) { return fma_(b, t, a * (1.0f - t));
 RT_DEV float3 mix(float3 a, float3 b, float t) { return make_float3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
 RT_DEV float3 mix(float3 a, float3 b, float3 t) { return make_float3(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z)); }
 RT_DEV float3 reflect(float3 I, float3 N) { float k = 2.0f * dot(N, I); return I - N * k; }
-RT_DEV float interp(float a, float b, float c, float3 w) { return fma_(c, w.z, fma_(b, w.y, a * w.x)); }
+// barycentric interpolation as the shader text writes it (ray_layouts.glsl:72-75; the unit is compiled with -fmad=false, so the
+// three products and two sums stay separate, as in the oracle and in the reference's text compiled for the CPU)
+RT_DEV float interp(float a, float b, float c, float3 w) { return a * w.x + b * w.y + c * w.z; }
 RT_DEV float3 interp(float3 a, float3 b, float3 c, float3 w) {
 	return make_float3(interp(a.x, b.x, c.x, w), interp(a.y, b.y, c.y, w), interp(a.z, b.z, c.z, w));
 }

@@ -50,6 +50,19 @@ RT_DEV float fresnelSchlick(float cosTheta, float ior) {
 	return mix(f0, 1.0f, pow5(1.0f - cosTheta));
 }
 RT_DEV float3 fresnelSchlick(float cosTheta, float3 f0) { return mix(f0, f3(1.0f), pow5(1.0f - cosTheta)); }
+// material.glsl:40-57: the exact Fresnel equations.  `#if MATERIAL_DIELECTRIC_USE_SCHLICK_APPROX` with the macro defined as `true`
+// is false in the GLSL preprocessor (an identifier that is no macro counts as 0), so this #else branch is what the reference runs
+RT_DEV float fresnel(float cosIn, float ior) {
+	if (cosIn < 0) {
+		ior = 1.0f / ior;
+		cosIn = -cosIn;
+	}
+	const float sinIn = sqrtf(1.0f - cosIn * cosIn);
+	const float sinTr = sinIn / ior;
+	if (sinTr >= 1.0f) return 1.0f;
+	const float cosTr = sqrtf(1.0f - sinTr * sinTr);
+	return (square((cosIn - ior * cosTr) / (cosIn + ior * cosTr)) + square((ior * cosIn - cosTr) / (ior * cosIn + cosTr))) * 0.5f;
+}
 RT_DEV float schlickG(float cosTheta, float alpha) {
 	float a = alpha * 0.5f;
 	return cosTheta / (cosTheta * (1.0f - a) + a);
@@ -184,7 +197,7 @@ RT_DEV bool sampleBSDF(const Mat& mat, float3 albedo, float3 n, float3 wo, float
 	}
 	if (mat.type == MatDielectric) {   // :149-172
 		float ior = mat.ior;
-		const float pdfReflect = fresnelSchlick(dot(n, wo), ior);
+		const float pdfReflect = fresnel(dot(n, wo), ior);
 		s.bsdf = albedo;
 		if (r.z < pdfReflect) {
 			s.wi = reflect(-wo, n);
