@@ -291,6 +291,13 @@ void rpt_frame_destroy(RptFrame* frame);
 int rpt_frame_clear(RptFrame* frame);            /* zero every buffer, reset ping-pong */
 int rpt_frame_flip(RptFrame* frame);             /* mCurFrame ^= 1, reference src/Renderer.cpp:567 */
 void* rpt_frame_stream(RptFrame* frame);         /* cudaStream_t the passes run on (for event timing) */
+/* Frames overlap (new; the reference keeps one frame in flight, HostDevice.h:7): the last passes of a ReSTIR PT frame —
+ * rpt_gris_spatial and the post-process that follows it — run on a second stream set, next to rpt_gbuffer and rpt_gris_pathtrace
+ * of the NEXT frame, which touch none of their buffers; every other call joins them first, so results do not change.
+ * rpt_frame_join makes the frame's stream wait (on the device, the host does not block) for everything enqueued on the frame's
+ * other streams so far: an event recorded on rpt_frame_stream() after it covers all of the frame's work.  Environment
+ * RPT_NO_FRAME_OVERLAP=1 keeps every pass on the one stream. */
+int rpt_frame_join(RptFrame* frame);
 
 /* 2 x 352-byte Camera upload, reference src/Renderer.cpp:358-361 */
 int rpt_set_camera(RptFrame* frame, const RptCamera* cur, const RptCamera* prev);

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference shaders' arithmetic
 // (reference src/shader/math.glsl and the GLSL built-ins it relies on).  Never linked into the product.
-// PARITY UNPINNED: the reference ships no tests / golden vectors and cannot run here (no Vulkan), see DESIGN.md.
+// PARITY PINNED against the reference's own shaders compiled for the CPU (oracle/ref, tests/test_cpu_ref_shaders.py):
+// the reference ships no tests / golden vectors, so its shader text itself, compiled by g++, is the pin.
 //
 // Numeric contract shared (by specification, not by code) with the CUDA kernels, so that both produce
 // bit-identical fp32 results: IEEE single, round-to-nearest, no implicit contraction (-ffp-contract=off here,

@@ -7,7 +7,8 @@
 //                       gris_resample_temporal.glsl, gris_resample_spatial.glsl (+ .comp)
 //   post-process        post_proc.frag:16-42
 // One function per shader entry; locals the GLSL leaves uninitialised are zero here ("defined
-// behaviours").  PARITY UNPINNED: no reference test or golden vector exists for any of this.
+// behaviours").  PARITY PINNED against the reference's own shaders compiled for the CPU (oracle/ref, tests/test_cpu_ref_shaders.py):
+// every ray pass below writes the same bits as the reference's .comp shader executed on the same inputs.
 #include "oracle_shading.h"
 
 namespace orc {

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Scene storage, ray/triangle intersection and texture fetch on the CPU:
 // stands in for what the reference gets from the Vulkan driver (acceleration structures + rayQueryEXT,
-// reference src/shader/ray_query.glsl:6-70; samplers, zvk/core/Memory.cpp:75-92).  PARITY UNPINNED.
+// reference src/shader/ray_query.glsl:6-70; samplers, zvk/core/Memory.cpp:75-92).  These are the DRIVER's parts: there is nothing of the reference to pin them against.
 #pragma once
 #include <atomic>
 #include <cstdint>

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's BSDF library, light sampling,
 // camera and surface fetch (reference src/shader/material.glsl, light_sampling.glsl:1-53, camera.glsl:28-42,
-// gbuffer_util.glsl, ray_layouts.glsl:50-104, ray_gbuffer_util.glsl).  PARITY UNPINNED.
+// gbuffer_util.glsl, ray_layouts.glsl:50-104, ray_gbuffer_util.glsl).  PARITY PINNED against the reference's own shaders compiled for the CPU (oracle/ref, tests/test_cpu_ref_shaders.py).
 #pragma once
 #include "oracle_frame.h"
 

@@ -1,8 +1,9 @@
 """CPU-side tests (no GPU): the oracle's building blocks against independent restatements written here in
 Python / numpy float64 straight from the reference GLSL, plus known-answer vectors for the integer RNG.
 
-The reference ships no tests or golden vectors and cannot run here, so these are the only pins the
-oracle has: PARITY UNPINNED against the reference itself (stated in DESIGN.md)."""
+The reference ships no tests or golden vectors; the pin against the reference itself is its shader source
+compiled for the CPU (tests/test_cpu_ref_pins.py, tests/test_cpu_ref_shaders.py) — the checks here are the independent
+second opinion on the building blocks."""
 import ctypes as C
 import math
 

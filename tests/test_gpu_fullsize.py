@@ -88,7 +88,6 @@ def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
     through nine more wavefront rounds instead.  Same stage functions, so the reservoirs must agree bit for bit — at full
     size, where the tail holds tens of thousands of paths."""
     w, h = 960, 540
-    dev = restirpt.Device(0)
     gs = GRISSettings(2, 1.0, 1, 1, 20)
     out = {}
     for mode in ("inline", "wavefront"):
@@ -96,6 +95,7 @@ def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
             monkeypatch.setenv("RPT_WAVEFRONT_TAIL", "1")
         else:
             monkeypatch.delenv("RPT_WAVEFRONT_TAIL", raising=False)
+        dev = restirpt.Device(0)      # (the switches are read when the context is created)
         b = Backend("cuda", bench_scene, w, h, dev)
         drv = FrameDriver(bench_scene.camera(w, h))
         for _ in range(2):
@@ -108,6 +108,7 @@ def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
         dev.lib.rpt_wavefront_counters(b.frame, wc)
         out[mode] = (b.read("GRIS_PREV"), b.read("INDIRECT_OUTPUT"), wc[4 * 7])
         b.close()
+        dev.close()
     assert out["inline"][2] > 1000, "the scene must have a tail for this test to mean anything"
     assert bitwise_mismatch(out["inline"][0], out["wavefront"][0]) == 0
     assert bitwise_mismatch(out["inline"][1], out["wavefront"][1]) == 0
@@ -121,7 +122,6 @@ def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, meth
     carry every dependency, so the two schedules must produce the same bits — at a film size where the kernels really
     run side by side."""
     w, h = 960, 540
-    dev = restirpt.Device(0)
     gs = GRISSettings(2, 1.0, 1, 1, 20)
     passes = {"gris": ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"), "gi": ("gbuffer", "gi_restir")}[method]
     out = {}
@@ -131,6 +131,7 @@ def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, meth
                 monkeypatch.setenv(var, "1")
             else:
                 monkeypatch.delenv(var, raising=False)
+        dev = restirpt.Device(0)      # (the switches are read when the context is created)
         b = Backend("cuda", bench_scene, w, h, dev)
         drv = FrameDriver(bench_scene.camera(w, h))
         for _ in range(3):
@@ -141,9 +142,52 @@ def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, meth
             b.flip()
         out[mode] = (b.read("GRIS_PREV" if method == "gris" else "GI_PREV"), b.read("INDIRECT_OUTPUT"))
         b.close()
+        dev.close()
     assert out["two"][1][..., :3].mean() > 0
     assert bitwise_mismatch(out["two"][0], out["one"][0]) == 0
     assert bitwise_mismatch(out["two"][1], out["one"][1]) == 0
+
+
+def test_overlapped_frames_equal_serial_frames(bench_scene, monkeypatch):
+    """Two frames in flight: rpt_gris_spatial and the post-process run on the frame's second stream set while rpt_gbuffer and
+    rpt_gris_pathtrace of the next frame are already running on the first (capi.cu, LateScope); RPT_NO_FRAME_OVERLAP=1 keeps every
+    pass on the one stream.  Six frames with a camera dolly and NO read or synchronisation in between (any read would join the
+    streams), at a film size where the passes really overlap: reservoirs, accumulated film and every tone-mapped image must be
+    the same bits either way."""
+    w, h = 1920, 1080
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+    post = restirpt.PostSettings(1, 1)
+    out = {}
+    for mode in ("overlap", "serial"):
+        if mode == "serial":
+            monkeypatch.setenv("RPT_NO_FRAME_OVERLAP", "1")
+        else:
+            monkeypatch.delenv("RPT_NO_FRAME_OVERLAP", raising=False)
+        dev = restirpt.Device(0)
+        b = Backend("cuda", bench_scene, w, h, dev)
+        drv = FrameDriver(bench_scene.camera(w, h))
+        images = [np.zeros((h, w, 4), dtype=np.uint8) for _ in range(6)]
+        tickets = []
+        for i in range(6):
+            cur, prev = drv.begin_frame(move=(0.004 * i, 0.002, 0.0))
+            b.set_camera(cur, prev)
+            for name in ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"):
+                b.run(name, None if name == "gbuffer" else gs)
+            t = C.c_uint64()
+            restirpt.check(dev.ctx, dev.lib.rpt_postprocess_async(b.frame, C.byref(post), images[i].ctypes.data_as(restirpt.P), C.byref(t)), "postprocess_async")
+            tickets.append(t.value)
+            b.flip()
+        for t in tickets[-2:]:
+            restirpt.check(dev.ctx, dev.lib.rpt_readback_wait(b.frame, t), "readback_wait")
+        out[mode] = (b.read("GRIS_PREV"), b.read("GRIS_TEMP"), b.read("INDIRECT_OUTPUT"), images)
+        b.close()
+        dev.close()
+    assert out["overlap"][2][..., :3].mean() > 0
+    for k in range(3):
+        assert bitwise_mismatch(out["overlap"][k], out["serial"][k]) == 0, k
+    for i in range(6):
+        assert np.array_equal(out["overlap"][3][i], out["serial"][3][i]), f"tone-mapped image of frame {i}"
+        assert out["overlap"][3][i][..., :3].mean() > 1
 
 
 def test_pipelined_readback_delivers_the_blocking_calls_images(built):

@@ -24,7 +24,7 @@ struct RptCtx {
 	unsigned long long* counters = nullptr;
 	bool countersOn = false;
 	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
-	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false;
+	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false, noFrameOverlap = false;
 };
 
 struct RptScene {
@@ -69,6 +69,13 @@ struct RptFrame {
 	cudaStream_t tailStream = nullptr;         // the long tail of the path-tracing pass runs here ...
 	cudaEvent_t tailFork = nullptr, tailDone = nullptr;
 	bool tailPending = false;                  // ... until the next pass joins it back into `stream`
+	// Two frames in flight: the LAST passes of a ReSTIR PT frame — spatial reuse and the post-process, whose replay kernels are
+	// a few long dependent chains that leave most of the GPU idle — run on a stream set of their own, so that the G-buffer and
+	// path-tracing passes of the NEXT frame (which touch none of their buffers: the other half of every ping-pong pair, the
+	// wavefront queues) fill the machine meanwhile.  The next temporal pass, and anything else that touches the frame, joins first.
+	cudaStream_t lateStream = nullptr, lateSide = nullptr;
+	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr;
+	bool latePending = false;
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
@@ -104,6 +111,34 @@ static void joinTail(RptFrame* f) {
 	if (f->tailPending) { cudaStreamWaitEvent(f->stream, f->tailDone, 0); f->tailPending = false; }
 }
 
+// the late passes of the previous frame (spatial reuse, post-process) must be complete before anything but the next frame's
+// G-buffer and path-tracing passes touches the frame
+static void joinLate(RptFrame* f) {
+	if (f->latePending) { cudaStreamWaitEvent(f->stream, f->lateDone, 0); f->latePending = false; }
+}
+static cudaError_t syncFrame(RptFrame* f) {
+	joinTail(f);
+	joinLate(f);
+	return cudaStreamSynchronize(f->stream);
+}
+// runs the calling pass on the late stream set: everything the helpers reach through f->stream / f->tailStream goes there
+struct LateScope {
+	RptFrame* f; bool on; cudaStream_t s0 = nullptr, t0 = nullptr; cudaEvent_t a0 = nullptr, b0 = nullptr;
+	explicit LateScope(RptFrame* f_) : f(f_), on(f_->lateStream != nullptr && !f_->ctx->noFrameOverlap) {
+		if (!on) return;
+		cudaEventRecord(f->lateFork, f->stream);              // after everything enqueued for this frame so far
+		cudaStreamWaitEvent(f->lateStream, f->lateFork, 0);
+		s0 = f->stream; t0 = f->tailStream; a0 = f->tailFork; b0 = f->tailDone;
+		f->stream = f->lateStream; f->tailStream = f->lateSide; f->tailFork = f->lateSideFork; f->tailDone = f->lateSideDone;
+	}
+	~LateScope() {
+		if (!on) return;
+		cudaEventRecord(f->lateDone, f->stream);
+		f->stream = s0; f->tailStream = t0; f->tailFork = a0; f->tailDone = b0;
+		f->latePending = true;
+	}
+};
+
 static cudaEvent_t takeEvent(RptFrame* f) {
 	if (!f->eventPool.empty()) { cudaEvent_t e = f->eventPool.back(); f->eventPool.pop_back(); return e; }
 	cudaEvent_t e = nullptr;
@@ -131,7 +166,7 @@ struct PassTimer {
 		if (f->timing) {
 			cudaEventRecord(b, f->stream);
 			f->pending.push_back({ pass, a, b, true });
-			if (f->pending.size() >= 4096) { cudaStreamSynchronize(f->stream); drainTiming(f); }
+			if (f->pending.size() >= 4096) { cudaStreamSynchronize(f->stream); if (f->lateStream) cudaStreamSynchronize(f->lateStream); drainTiming(f); }
 		}
 	}
 };
@@ -184,6 +219,7 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	ctx->traceOneStream = getenv("RPT_TRACE_ONE_STREAM") != nullptr;
 	ctx->wavefrontTail = getenv("RPT_WAVEFRONT_TAIL") != nullptr;
 	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
+	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
 	*out = ctx;
 	return RPT_OK;
 }
@@ -478,6 +514,7 @@ RPT_API int rpt_frame_clear(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_clear: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
+	joinLate(f);
 	auto slots = frameSlots(f);
 	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, slotBytes(f, i), f->stream));
 	f->cur = 0;
@@ -534,6 +571,15 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailFork, cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailDone, cudaEventDisableTiming);
 		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "tail stream"); }
+		{
+			int lo = 0, hi = 0;
+			cudaDeviceGetStreamPriorityRange(&lo, &hi);
+			e = cudaStreamCreateWithPriority(&f->lateStream, cudaStreamNonBlocking, hi);
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, hi);
+			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone })
+				if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "late stream"); }
+		}
 	}
 	int r = rpt_frame_clear(f);
 	if (r != RPT_OK) { rpt_frame_destroy(f); return r; }
@@ -565,7 +611,12 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device);
 	if (f->tailStream) cudaStreamSynchronize(f->tailStream);
+	if (f->lateSide) cudaStreamSynchronize(f->lateSide);
+	if (f->lateStream) cudaStreamSynchronize(f->lateStream);
 	if (f->stream) cudaStreamSynchronize(f->stream);
+	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone }) if (ev) cudaEventDestroy(ev);
+	if (f->lateSide) cudaStreamDestroy(f->lateSide);
+	if (f->lateStream) cudaStreamDestroy(f->lateStream);
 	if (f->tailFork) cudaEventDestroy(f->tailFork);
 	if (f->tailDone) cudaEventDestroy(f->tailDone);
 	if (f->tailStream) cudaStreamDestroy(f->tailStream);
@@ -649,12 +700,16 @@ static SceneView sceneView(const RptScene* s) {
 	return v;
 }
 
-#define PASS_PROLOGUE(name) \
+#define PASS_PROLOGUE_EARLY(name) \
 	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, name ": NULL argument"); \
 	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, name ": frame and scene belong to different contexts"); \
 	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, name ": a multi-GPU hand-over of an earlier pass timed out on the device (a neighbouring strip died or was not driven in lock step); disconnect the peers to recover"); \
 	CU(f->ctx, cudaSetDevice(f->ctx->device)); \
 	joinTail(f);
+// every pass but the G-buffer and the ReSTIR PT path tracer (PASS_PROLOGUE_EARLY) waits for the previous frame's late passes
+#define PASS_PROLOGUE(name) \
+	PASS_PROLOGUE_EARLY(name) \
+	joinLate(f);
 #define PASS_EPILOGUE(name) \
 	CU(f->ctx, cudaGetLastError()); \
 	return RPT_OK;
@@ -665,7 +720,13 @@ static SceneView sceneView(const RptScene* s) {
 		{ PassTimer timer(f, passId); launcher(makeView(f), sceneView(s), f->stream); } \
 		PASS_EPILOGUE(#fn) \
 	}
-SIMPLE_PASS(rpt_gbuffer, RPT_PASS_GBUFFER, launchGBuffer)
+// (writes the other half of the G-buffer ping-pong pair + the motion vectors, which only a temporal pass reads: it may run next
+// to the previous frame's late passes)
+RPT_API int rpt_gbuffer(RptFrame* f, const RptScene* s) {
+	PASS_PROLOGUE_EARLY("rpt_gbuffer")
+	{ PassTimer timer(f, RPT_PASS_GBUFFER); launchGBuffer(makeView(f), sceneView(s), f->stream); }
+	PASS_EPILOGUE("rpt_gbuffer")
+}
 SIMPLE_PASS(rpt_di_naive, RPT_PASS_DI_NAIVE, launchDINaive)
 SIMPLE_PASS(rpt_di_naive_rt, RPT_PASS_DI_NAIVE, launchDINaiveRT)
 SIMPLE_PASS(rpt_gi_naive, RPT_PASS_GI_NAIVE, launchGINaive)
@@ -750,7 +811,7 @@ SETTINGS_PASS(rpt_di_spatial, RptDISettings, RPT_PASS_DI_SPATIAL, launchDISpatia
 // GRISReSTIR::render step 1.  Bounces 0..WavefrontTailStart-1 (all but a few percent of the rays) run on the frame's
 // stream; the long tail of the few paths that live on is enqueued on the tail stream and joined by the next pass.
 RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
-	PASS_PROLOGUE("rpt_gris_pathtrace")
+	PASS_PROLOGUE_EARLY("rpt_gris_pathtrace")   // (reads the new G-buffer, writes the reservoirs the previous frame read as history)
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_pathtrace: NULL settings");
 	f->wf.epoch++;
 	const FrameView view = makeView(f);
@@ -782,6 +843,7 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: NULL settings");
 	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gris_temporal: a multi-GPU hand-over of an earlier pass timed out on the device; disconnect the peers to recover");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinLate(f);   // the previous frame's spatial pass wrote this frame's history and read the buffers this pass writes
 	peerBefore(f, HookGrisTemporal);
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_TEMPORAL);
@@ -791,9 +853,18 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 		KernelClock* ck = f->timing ? &clock : nullptr;
 		if (f->tailPending) {
 			launchGRISTemporal(view, scene, *st, f->stream, 1, ck);
-			if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
-			joinTail(f);
-			launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
+			const bool peers = f->up.connected || f->down.connected;
+			if (peers || f->ctx->traceOneStream) {   // (the hand-over signal below must follow the tail's pixels too)
+				if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
+				joinTail(f);
+				launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
+			}
+			else {
+				// the tail's pixels are independent of all others in this pass (own reservoir, own history pixel): their temporal
+				// step follows the path-tracing tail on ITS stream, next to the dense kernels here; the spatial pass joins both
+				launchGRISTemporal(view, scene, *st, f->tailStream, 2, nullptr);
+				CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
+			}
 		}
 		else launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
 	}
@@ -803,6 +874,7 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
 	PASS_PROLOGUE("rpt_gris_spatial")
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_spatial: NULL settings");
+	LateScope late(f);
 	peerBefore(f, HookGrisSpatial);
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
@@ -831,6 +903,10 @@ static int postprocessInto(RptFrame* f, const RptPostSettings* st, uchar4* image
 RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out) {
 	if (!f || !st) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	// device-only run after a late spatial pass: the post-process follows it there; with a read-back the streams are joined first
+	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
+	if (f->latePending && !rgba8Out) late.l = new LateScope(f);
+	else joinLate(f);
 	if (f->asyncTicket) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[(f->asyncTicket - 1) & 1], 0));   // (f->rgba8 may still be being read back)
 	const int rc = postprocessInto(f, st, f->rgba8);
 	if (rc != RPT_OK) return rc;
@@ -860,6 +936,9 @@ RPT_API int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_
 	const uint64_t t = f->asyncTicket;
 	const int slot = int(t & 1);
 	uchar4* image = slot ? f->rgba8Alt : f->rgba8;
+	// after a late spatial pass the post-process follows it there (it reads what that pass accumulated); otherwise the frame's stream
+	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
+	if (f->latePending) late.l = new LateScope(f);
 	if (t >= 2) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[slot], 0));
 	const int rc = postprocessInto(f, st, image);
 	if (rc != RPT_OK) return rc;
@@ -885,14 +964,23 @@ RPT_API int rpt_sync(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_sync: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
+	return RPT_OK;
+}
+
+RPT_API int rpt_frame_join(RptFrame* f) {
+	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_join: NULL frame");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	joinTail(f);
+	joinLate(f);
 	return RPT_OK;
 }
 
 RPT_API int rpt_frame_timing(RptFrame* f, int enable) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_timing: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	CU(f->ctx, syncFrame(f));
 	drainTiming(f);
 	f->timing = enable != 0;
 	if (enable) f->stats = RptPassStats{};
@@ -903,7 +991,8 @@ RPT_API int rpt_frame_pass_stats(RptFrame* f, RptPassStats* out) {
 	if (!f || !out) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_frame_pass_stats: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
 	drainTiming(f);
 	*out = f->stats;
 	return RPT_OK;
@@ -921,8 +1010,9 @@ RPT_API int rpt_read(RptFrame* f, RptBufferId id, void* dst, size_t bytes) {
 	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_read: bad buffer id or size");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
+	joinLate(f);
 	CU(f->ctx, cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, f->stream));
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	CU(f->ctx, syncFrame(f));
 	return RPT_OK;
 }
 
@@ -932,8 +1022,9 @@ RPT_API int rpt_write(RptFrame* f, RptBufferId id, const void* src, size_t bytes
 	if (!p || bytes != f->pixels() * rpt_buffer_stride(id)) return fail(f->ctx, RPT_ERR_INVALID, "rpt_write: bad buffer id or size");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
+	joinLate(f);
 	CU(f->ctx, cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, f->stream));
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	CU(f->ctx, syncFrame(f));
 	return RPT_OK;
 }
 
@@ -1022,7 +1113,8 @@ RPT_API int rpt_frame_connect_peers(RptFrame* f, const RptPeerInfo* up, const Rp
 	if (up && up->rowBegin != 0 && up->rowEnd - up->rowBegin < f->halo) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: the strip above is shorter than the halo");
 	if (down && down->rowEnd != f->height && down->rowEnd - down->rowBegin < f->halo) return fail(f->ctx, RPT_ERR_INVALID, "rpt_frame_connect_peers: the strip below is shorter than the halo");
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
 	disconnectPeers(f);   // also: epochs, flag words and the sticky error back to zero
 	int r = connectOne(f, f->up, up);
 	if (r != RPT_OK) return r;
@@ -1035,7 +1127,8 @@ RPT_API int rpt_frame_disconnect_peers(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_disconnect_peers: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
 	disconnectPeers(f);
 	return RPT_OK;
 }
@@ -1103,7 +1196,8 @@ RPT_API int rpt_frame_gather_disconnect(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_gather_disconnect: NULL frame");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
 	disconnectGather(f);
 	return RPT_OK;
 }
@@ -1116,12 +1210,13 @@ RPT_API int rpt_gather_output(RptFrame* f, uint8_t* rgba8FullFilm) {
 	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gather_output: a multi-GPU hand-over timed out on the device");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
+	joinLate(f);
 	const uint32_t epoch = ++f->gather.gathered;
 	launchPeerWaitMany(f->gatherFlagsOwned + GatherArrivalFlag0, f->gather.numStrips, epoch, f->flags + PeerError, f->hostErrorDev, f->stream);
 	CU(f->ctx, cudaMemcpyAsync(rgba8FullFilm, f->gatherImageOwned, size_t(f->width) * f->height * 4, cudaMemcpyDeviceToHost, f->stream));
 	launchPeerSignal(f->gatherFlagsOwned + GatherReleaseFlag, nullptr, epoch, f->stream);
 	CU(f->ctx, cudaGetLastError());
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	CU(f->ctx, syncFrame(f));
 	if (*reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gather_output: a strip's rows did not arrive within the time limit");
 	return RPT_OK;
 }
@@ -1130,7 +1225,7 @@ RPT_API int rpt_frame_peer_error(RptFrame* f) {
 	if (!f) return 1;
 	cudaSetDevice(f->ctx->device);
 	uint32_t e = 0;
-	if (cudaStreamSynchronize(f->stream) != cudaSuccess) return 1;
+	if (syncFrame(f) != cudaSuccess) return 1;
 	if (cudaMemcpy(&e, f->flags + PeerError, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
 	return int(e);
 }
@@ -1199,7 +1294,8 @@ RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
 	if (!f || !out64) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_wavefront_counters: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
-	CU(f->ctx, cudaStreamSynchronize(f->stream));
+	joinLate(f);
+	CU(f->ctx, syncFrame(f));
 	CU(f->ctx, cudaMemcpy(out64, f->wf.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return RPT_OK;
 }

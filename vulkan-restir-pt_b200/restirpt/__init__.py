@@ -189,6 +189,7 @@ DEVICE_API = {
     "rpt_frame_clear": (C.c_int, [P]),
     "rpt_frame_flip": (C.c_int, [P]),
     "rpt_frame_stream": (P, [P]),
+    "rpt_frame_join": (C.c_int, [P]),
     "rpt_set_camera": (C.c_int, [P, C.POINTER(Camera), C.POINTER(Camera)]),
     "rpt_gbuffer": (C.c_int, [P, P]),
     "rpt_di_naive": (C.c_int, [P, P]),
