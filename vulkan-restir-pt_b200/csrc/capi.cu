@@ -851,22 +851,34 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 		const SceneView scene = sceneView(s);
 		FrameKernelClock clock(f);
 		KernelClock* ck = f->timing ? &clock : nullptr;
-		if (f->tailPending) {
+		// Second stream: (a) the pixels of the path-tracing tail — independent of all others in this pass (own reservoir, own
+		// history pixel) — take their temporal step right behind the tail kernel on ITS stream; (b) the pixels whose history
+		// sample needs replay rays follow there as soon as gen has listed them.  The spatial pass (or whatever touches the
+		// frame next) joins that stream; with neighbouring strips connected the join comes at once, because the hand-over
+		// signal below must follow every pixel of the pass.
+		const bool oneStream = f->ctx->traceOneStream;
+		const bool hadTail = f->tailPending;
+		if (hadTail && oneStream) {
 			launchGRISTemporal(view, scene, *st, f->stream, 1, ck);
-			const bool peers = f->up.connected || f->down.connected;
-			if (peers || f->ctx->traceOneStream) {   // (the hand-over signal below must follow the tail's pixels too)
-				if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
-				joinTail(f);
-				launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
-			}
-			else {
-				// the tail's pixels are independent of all others in this pass (own reservoir, own history pixel): their temporal
-				// step follows the path-tracing tail on ITS stream, next to the dense kernels here; the spatial pass joins both
-				launchGRISTemporal(view, scene, *st, f->tailStream, 2, nullptr);
-				CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
-			}
+			if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
+			joinTail(f);
+			launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
 		}
-		else launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
+		else if (oneStream) launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
+		else {
+			if (hadTail) launchGRISTemporal(view, scene, *st, f->tailStream, 2, nullptr);
+			// (b) goes to a stream of its own — the late set's side stream, idle here: this pass has joined the previous frame's
+			// late passes — so that the two latency-bound kernels run next to each other, not one behind the other
+			cudaStream_t listStream = f->lateSide ? f->lateSide : f->tailStream;
+			launchGRISTemporal(view, scene, *st, f->stream, hadTail ? 1 : 0, ck, listStream, f->tailFork);
+			if (listStream != f->tailStream) {
+				CU(f->ctx, cudaEventRecord(f->lateSideDone, listStream));
+				CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->lateSideDone, 0));
+			}
+			CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
+			f->tailPending = true;
+			if (f->up.connected || f->down.connected) joinTail(f);
+		}
 	}
 	peerAfter(f, HookGrisTemporal);
 	PASS_EPILOGUE("rpt_gris_temporal")

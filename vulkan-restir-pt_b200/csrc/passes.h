@@ -22,7 +22,8 @@ void launchGRISPathTraceBounces(const FrameView& f, const SceneView& s, const Rp
                                 KernelClock* clock = nullptr, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st);
 // tailMode 0: every pixel; 1: every pixel whose path is not in the tail; 2: only the pixels of the tail list
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0, KernelClock* clock = nullptr);
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0, KernelClock* clock = nullptr,
+                        cudaStream_t side = nullptr, cudaEvent_t fork = nullptr);
 // side / fork / join: a second stream and two events for the kernel that runs next to the main sequence (all NULL: one stream)
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock = nullptr,
                        cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);

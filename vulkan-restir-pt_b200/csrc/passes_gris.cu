@@ -860,6 +860,12 @@ RT_DEV void grisTemporalPixel(const FrameView& f, const SceneView& s, const RptG
 	temporalStore(f, x, y, idx, resv);
 }
 
+// A history sample that reconnects beyond the first bounce (paths through glass, mirrors) needs its prefix replayed from this
+// pixel: a chain of dependent in-line rays, a few long ones per warp.  Such pixels (1 % of VeachAjar's) are taken out of the
+// wavefront — gen marks them TaskDeferred, the merge kernel leaves them alone — and go through the sequential per-pixel form
+// on the second stream (grisTemporalListKernel) while the other 99 % run through gen / visibility queue / merge without any
+// traversal code in their kernels.
+constexpr uint32_t TaskDeferred = 2;
 __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisTemporalGenKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int skipTail) {
 	const uint32_t o = blockIdx.x * ReuseBlock + threadIdx.x;
 	if (o >= f.ru.capacity) return;
@@ -874,10 +880,17 @@ __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisTemporalGe
 		if (p.valid && temporalCandidate(f, st, p, idx, nb)) {
 			const GRISResv prev = loadGRIS(f.grisPrev + nb.pixel);
 			if (prev.valid()) {
-				shiftPrepare(s, st, primarySurface(p), p.uv, p.ray, prev, t);
-				storeShiftTask(f.ru, 0, o, t, uint32_t(nb.pixel));
-				stored = true;
-				rayTask = &t;
+				if (prev.sampleValid() && flagsRcVertexId(prev.flags()) != 1u) {
+					f.ru.redoList[atomicAdd(f.ru.counters + 4, 1u)] = o;
+					f.ru.task[2 * size_t(f.ru.capacity) * 3 + o] = make_float4(0.f, 0.f, 0.f, __uint_as_float(TaskDeferred << 30));
+					stored = true;
+				}
+				else {
+					shiftPrepare<false>(s, st, primarySurface(p), p.uv, p.ray, prev, t);
+					storeShiftTask(f.ru, 0, o, t, uint32_t(nb.pixel));
+					stored = true;
+					rayTask = &t;
+				}
 			}
 		}
 	}
@@ -897,6 +910,7 @@ __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisTemporalMe
 	GRISResv resv = loadGRIS(f.grisThis + idx);
 	ShiftTask t;
 	const uint32_t srcPixel = loadShiftTask(f.ru, 0, o, t);
+	if (t.status == TaskDeferred) return;   // grisTemporalListKernel owns this pixel
 	if (t.status != TaskSkip) {
 		GRISResv prev = loadGRIS(f.grisPrev + srcPixel);
 		shiftFinish(s, prev, t, t.status == TaskRay && f.ru.occluded[o] == 0);
@@ -911,6 +925,14 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalTailKer
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t pix = f.wf.tailList[i];
 		grisTemporalPixel(f, s, st, pix % f.width, f.storeBegin + pix / f.width);
+	}
+}
+
+__global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalListKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = f.ru.counters[4];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t o = f.ru.redoList[i];
+		grisTemporalPixel(f, s, st, o % f.width, f.rowBegin + o / f.width);
 	}
 }
 
@@ -1134,21 +1156,30 @@ void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGR
 	}();
 	grisTailKernel<<<blocks, TailBlock, 0, st>>>(f, s, p);
 }
-void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode, KernelClock* clock) {
+void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode, KernelClock* clock,
+                        cudaStream_t side, cudaEvent_t fork) {
+	static const int blocks = persistentBlocks(reinterpret_cast<const void*>(grisTemporalTailKernel), PassBlockX * PassBlockY);
 	if (tailMode == 2) {
-		static const int blocks = persistentBlocks(reinterpret_cast<const void*>(grisTemporalTailKernel), PassBlockX * PassBlockY);
 		if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 		grisTemporalTailKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 		return;
 	}
-	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
+	const uint32_t n = f.ru.capacity, dense = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
-	grisTemporalGenKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	grisTemporalGenKernel<<<dense, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	// the deferred pixels (replay chains) on the second stream, next to the visibility rays and the merge of all others; the
+	// caller joins `side` before anything reads the pass's output
+	if (side != nullptr && fork != nullptr) {
+		cudaEventRecord(fork, st);
+		cudaStreamWaitEvent(side, fork, 0);
+		grisTemporalListKernel<<<blocks, PassBlockX * PassBlockY, 0, side>>>(f, s, p);
+	}
 	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, n, f.ru.counters + 2, f.ru.occluded, st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
-	grisTemporalMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	grisTemporalMergeKernel<<<dense, ReuseBlock, 0, st>>>(f, s, p, tailMode);
+	if (side == nullptr || fork == nullptr) grisTemporalListKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock,
                        cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
