@@ -349,15 +349,16 @@ typedef struct RptPeerInfo {
 	uint8_t grisTempHandle[64];   /* cudaIpcMemHandle_t of the GRIS temp reservoir buffer */
 	uint8_t diTempHandle[64];     /* ... of the DI temp reservoir buffer */
 	uint8_t flagsHandle[64];      /* ... of the epoch flags */
-	uint8_t grisHandle[2][64];    /* ... of the two ping-pong buffers of the final GRIS / DI / GI reservoirs: the boundary rows of */
-	uint8_t diHandle[2][64];      /*     the spatial (GI: temporal) pass output are mirrored into the neighbours' halo rows, so that */
-	uint8_t giHandle[2][64];      /*     previous-frame lookups that cross a cut stay GPU-local and still find their history */
+	uint8_t grisHandle[3][64];    /* ... of the buffers of the final GRIS (three, in rotation: this frame, the previous one, and the one the */
+	uint8_t diHandle[2][64];      /*     next frame's path tracer already fills) / DI / GI (ping-pong pairs) reservoirs: the boundary rows of the */
+	uint8_t giHandle[2][64];      /*     spatial (GI: temporal) pass output are mirrored into the neighbours' halo rows, so that previous-frame */
+	                              /*     lookups that cross a cut stay GPU-local and still find their history */
 	uint64_t grisTempPtr, diTempPtr, flagsPtr;   /* raw device pointers, used when pid matches */
-	uint64_t grisPtr[2], diPtr[2], giPtr[2];
+	uint64_t grisPtr[3], diPtr[2], giPtr[2];
 	uint64_t pid;
 	int32_t device;
 	uint32_t rowBegin, rowEnd, storeBegin, storeEnd;
-	uint32_t cur;                 /* ping-pong phase at export time (both strips must flip in lock step from here on) */
+	uint32_t cur;                 /* frames flipped at export time: the buffer phases (both strips must flip in lock step from here on) */
 	uint32_t pad[2];
 } RptPeerInfo;
 int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out);

@@ -42,14 +42,23 @@ struct RptScene {
 struct RptFrame {
 	RptCtx* ctx = nullptr;
 	uint32_t width = 0, height = 0, rowBegin = 0, rowEnd = 0, storeBegin = 0, storeEnd = 0;
-	uint32_t cur = 0;
+	// Frames flipped since the last clear.  The DI / GI reservoirs are ping-pong pairs (slot flips & 1 = this frame); the G-buffer
+	// images, the motion vectors and the GRIS reservoirs rotate through THREE slots (flips % 3 = this frame, the one before = the
+	// previous frame), and the wavefront path-tracing state exists twice (flips & 1): the third slot / the other set is what the
+	// G-buffer and path-tracing passes of the NEXT frame fill while this frame's reuse passes still read the other two (below).
+	uint32_t flips = 0;
+	uint32_t c2() const { return flips & 1u; }
+	uint32_t p2() const { return (flips & 1u) ^ 1u; }
+	uint32_t c3() const { return flips % 3u; }
+	uint32_t p3() const { return (flips + 2u) % 3u; }
+	uint32_t n3() const { return (flips + 1u) % 3u; }   // the slot of two frames ago = the slot of the next frame
 	cudaStream_t stream = nullptr;
-	float4 *directOutput = nullptr, *indirectOutput = nullptr, *depthNormal[2] = { nullptr, nullptr };
-	uint2* albedoMatId[2] = { nullptr, nullptr };
-	float2* motion = nullptr;
+	float4 *directOutput = nullptr, *indirectOutput = nullptr, *depthNormal[3] = { nullptr, nullptr, nullptr };
+	uint2* albedoMatId[3] = { nullptr, nullptr, nullptr };
+	float2* motion[3] = { nullptr, nullptr, nullptr };
 	RptDIReservoir *di[2] = { nullptr, nullptr }, *diTemp = nullptr;
 	RptGIReservoir* gi[2] = { nullptr, nullptr };
-	RptGRISReservoir *gris[2] = { nullptr, nullptr }, *grisTemp = nullptr;
+	RptGRISReservoir *gris[3] = { nullptr, nullptr, nullptr }, *grisTemp = nullptr;
 	RptIntersection* primaryIsec = nullptr;
 	uchar4* rgba8 = nullptr;
 	// pipelined read-back (rpt_postprocess_async): a second device image, a copy stream, one event pair per image
@@ -64,24 +73,34 @@ struct RptFrame {
 	uint32_t halo = 0;
 	uint32_t* flags = nullptr;                 // PeerFlagCount words, written by the neighbours
 	uint32_t* work = nullptr;                  // WorkCounterCount queue heads of the persistent kernels
-	WavefrontView wf{};                        // wavefront path-tracing queues (owned rows only)
+	WavefrontView wfSet[2]{};                  // wavefront path-tracing queues (owned rows only), one set per frame parity
+	WavefrontView& wf() { return wfSet[flips & 1u]; }
 	ReuseView ru{};                            // wavefront temporal / spatial reuse
 	cudaStream_t tailStream = nullptr;         // the long tail of the path-tracing pass runs here ...
 	cudaEvent_t tailFork = nullptr, tailDone = nullptr;
 	bool tailPending = false;                  // ... until the next pass joins it back into `stream`
-	// Two frames in flight: the LAST passes of a ReSTIR PT frame — spatial reuse and the post-process, whose replay kernels are
-	// a few long dependent chains that leave most of the GPU idle — run on a stream set of their own, so that the G-buffer and
-	// path-tracing passes of the NEXT frame (which touch none of their buffers: the other half of every ping-pong pair, the
-	// wavefront queues) fill the machine meanwhile.  The next temporal pass, and anything else that touches the frame, joins first.
+	// Two frames in flight: the reuse passes of a ReSTIR PT frame — temporal, spatial, post-process, whose replay kernels and whose
+	// wait for the path tracer's tail are a few long dependent chains that leave most of the GPU idle — run on a stream set of their
+	// own ("late"), in order, while the frame's stream goes on with the G-buffer and the path tracer of the NEXT frame.  Those two
+	// passes touch nothing the late passes read or write: they fill the third slot of the G-buffer / motion / GRIS rotation and the
+	// other set of wavefront queues.  The frame's stream is at most one frame ahead: before the G-buffer of frame k+2 reuses the
+	// slots of frame k-1 it waits for the late passes of frame k (lateFrameDone[k & 1]), the last readers of those slots.  Any other
+	// pass, read-back or query joins everything first.
 	cudaStream_t lateStream = nullptr, lateSide = nullptr;
-	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr;
+	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr, lateHead = nullptr;
+	cudaEvent_t lateFrameDone[2] = { nullptr, nullptr };
 	bool latePending = false;
+	// the path tracer's paired launches (any-hit next to closest-hit) have a side stream of their own: the tail stream still
+	// carries the previous frame's tail when the next path tracer starts
+	cudaStream_t ptSide = nullptr;
+	cudaEvent_t ptFork = nullptr, ptJoin = nullptr;
+	uint32_t lastWfSet = 0;                    // the wavefront set of the last path-tracing pass (rpt_wavefront_counters)
 	struct Peer {
 		bool connected = false, ipc = false;
 		RptGRISReservoir* grisTemp = nullptr; RptDIReservoir* diTemp = nullptr; uint32_t* flags = nullptr;
-		RptGRISReservoir* gris[2] = { nullptr, nullptr };   // the neighbour's ping-pong buffers of final reservoirs,
-		RptDIReservoir* di[2] = { nullptr, nullptr };       // indexed like OUR `cur` (the phase difference at connect
-		RptGIReservoir* gi[2] = { nullptr, nullptr };       // time is folded in)
+		RptGRISReservoir* gris[3] = { nullptr, nullptr, nullptr };   // the neighbour's buffers of final reservoirs, indexed like
+		RptDIReservoir* di[2] = { nullptr, nullptr };                // OUR slots (the phase differences at connect time are
+		RptGIReservoir* gi[2] = { nullptr, nullptr };                // folded in)
 		uint32_t storeBegin = 0;
 	} up, down;
 	uint32_t grisEpoch = 0, diEpoch = 0, giEpoch = 0;
@@ -134,10 +153,16 @@ struct LateScope {
 	~LateScope() {
 		if (!on) return;
 		cudaEventRecord(f->lateDone, f->stream);
+		cudaEventRecord(f->lateFrameDone[f->flips & 1u], f->stream);
 		f->stream = s0; f->tailStream = t0; f->tailFork = a0; f->tailDone = b0;
 		f->latePending = true;
 	}
 };
+static bool pipelined(const RptFrame* f) { return f->lateStream != nullptr && !f->ctx->noFrameOverlap; }
+// G-buffer / path tracer of frame k: the slots they fill were last read by the late passes of frame k-2
+static void waitSlotReaders(RptFrame* f) {
+	if (pipelined(f)) cudaStreamWaitEvent(f->stream, f->lateFrameDone[f->flips & 1u], 0);
+}
 
 static cudaEvent_t takeEvent(RptFrame* f) {
 	if (!f->eventPool.empty()) { cudaEvent_t e = f->eventPool.back(); f->eventPool.pop_back(); return e; }
@@ -469,45 +494,56 @@ RPT_API size_t rpt_buffer_stride(RptBufferId id) {
 }
 
 static void* framePtr(RptFrame* f, RptBufferId id) {
-	const uint32_t c = f->cur, p = f->cur ^ 1u;
+	const uint32_t c = f->c2(), p = f->p2(), c3 = f->c3(), p3 = f->p3();
 	switch (id) {
 	case RPT_BUF_DIRECT_OUTPUT: return f->directOutput;
 	case RPT_BUF_INDIRECT_OUTPUT: return f->indirectOutput;
-	case RPT_BUF_DEPTH_NORMAL: return f->depthNormal[c];
-	case RPT_BUF_DEPTH_NORMAL_PREV: return f->depthNormal[p];
-	case RPT_BUF_ALBEDO_MATID: return f->albedoMatId[c];
-	case RPT_BUF_ALBEDO_MATID_PREV: return f->albedoMatId[p];
-	case RPT_BUF_MOTION: return f->motion;
+	case RPT_BUF_DEPTH_NORMAL: return f->depthNormal[c3];
+	case RPT_BUF_DEPTH_NORMAL_PREV: return f->depthNormal[p3];
+	case RPT_BUF_ALBEDO_MATID: return f->albedoMatId[c3];
+	case RPT_BUF_ALBEDO_MATID_PREV: return f->albedoMatId[p3];
+	case RPT_BUF_MOTION: return f->motion[c3];
 	case RPT_BUF_DI_THIS: return f->di[c];
 	case RPT_BUF_DI_PREV: return f->di[p];
 	case RPT_BUF_DI_TEMP: return f->diTemp;
 	case RPT_BUF_GI_THIS: return f->gi[c];
 	case RPT_BUF_GI_PREV: return f->gi[p];
-	case RPT_BUF_GRIS_THIS: return f->gris[c];
-	case RPT_BUF_GRIS_PREV: return f->gris[p];
+	case RPT_BUF_GRIS_THIS: return f->gris[c3];
+	case RPT_BUF_GRIS_PREV: return f->gris[p3];
 	case RPT_BUF_GRIS_TEMP: return f->grisTemp;
 	case RPT_BUF_PRIMARY_ISEC: return f->primaryIsec;
 	default: return nullptr;
 	}
 }
 
-static std::vector<void**> frameSlots(RptFrame* f) {
-	return { (void**)&f->directOutput, (void**)&f->indirectOutput, (void**)&f->depthNormal[0], (void**)&f->depthNormal[1],
-	         (void**)&f->albedoMatId[0], (void**)&f->albedoMatId[1], (void**)&f->motion, (void**)&f->di[0], (void**)&f->di[1],
-	         (void**)&f->diTemp, (void**)&f->gi[0], (void**)&f->gi[1], (void**)&f->gris[0], (void**)&f->gris[1], (void**)&f->grisTemp,
-	         (void**)&f->primaryIsec, (void**)&f->rgba8 };
+struct FrameSlot { void** ptr; size_t stride; bool wrapRows; };
+// (the depthNormal images carry two extra rows: film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
+static std::vector<FrameSlot> frameSlots(RptFrame* f) {
+	return { { (void**)&f->directOutput, 16, false }, { (void**)&f->indirectOutput, 16, false },
+	         { (void**)&f->depthNormal[0], 16, true }, { (void**)&f->depthNormal[1], 16, true }, { (void**)&f->depthNormal[2], 16, true },
+	         { (void**)&f->albedoMatId[0], 8, false }, { (void**)&f->albedoMatId[1], 8, false }, { (void**)&f->albedoMatId[2], 8, false },
+	         { (void**)&f->motion[0], 8, false }, { (void**)&f->motion[1], 8, false }, { (void**)&f->motion[2], 8, false },
+	         { (void**)&f->di[0], 64, false }, { (void**)&f->di[1], 64, false }, { (void**)&f->diTemp, 64, false },
+	         { (void**)&f->gi[0], 48, false }, { (void**)&f->gi[1], 48, false },
+	         { (void**)&f->gris[0], 96, false }, { (void**)&f->gris[1], 96, false }, { (void**)&f->gris[2], 96, false }, { (void**)&f->grisTemp, 96, false },
+	         { (void**)&f->primaryIsec, 16, false }, { (void**)&f->rgba8, 4, false } };
 }
-static std::vector<void**> wavefrontSlots(RptFrame* f) {
-	return { (void**)&f->wf.state[0], (void**)&f->wf.state[1], (void**)&f->wf.cold, (void**)&f->wf.rays[0], (void**)&f->wf.rays[1],
-	         (void**)&f->wf.pix[0], (void**)&f->wf.pix[1], (void**)&f->wf.hits, (void**)&f->wf.shadowRays[0], (void**)&f->wf.shadowRays[1],
-	         (void**)&f->wf.occluded[0], (void**)&f->wf.occluded[1], (void**)&f->wf.counters, (void**)&f->wf.tailMark, (void**)&f->wf.tailList,
-	         (void**)&f->ru.task, (void**)&f->ru.rays, (void**)&f->ru.occluded, (void**)&f->ru.shadeList, (void**)&f->ru.redoList, (void**)&f->ru.counters };
+static size_t slotBytes(const RptFrame* f, const FrameSlot& s) {
+	return (f->pixels() + (s.wrapRows ? 2 * size_t(f->width) : 0)) * s.stride;
 }
-static const size_t kSlotStride[17] = { 16, 16, 16, 16, 8, 8, 8, 64, 64, 64, 48, 48, 96, 96, 96, 16, 4 };
-// the two depthNormal images carry two extra rows (film rows 0 and H-1 for REPEAT-wrapped taps of a strip)
-static size_t slotBytes(const RptFrame* f, size_t i) {
-	const size_t extra = (i == 2 || i == 3) ? 2 * size_t(f->width) : 0;
-	return (f->pixels() + extra) * kSlotStride[i];
+struct WavefrontSlot { void** ptr; size_t bytes; };
+static std::vector<WavefrontSlot> wavefrontSlots(RptFrame* f) {
+	const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
+	std::vector<WavefrontSlot> v;
+	for (WavefrontView& w : f->wfSet) {
+		v.insert(v.end(), { { (void**)&w.state[0], px * PathStateWords * 16 }, { (void**)&w.state[1], px * PathStateWords * 16 }, { (void**)&w.cold, f->pixels() * 32 },
+		                    { (void**)&w.rays[0], px * 32 }, { (void**)&w.rays[1], px * 32 }, { (void**)&w.pix[0], px * 4 }, { (void**)&w.pix[1], px * 4 }, { (void**)&w.hits, px * 16 },
+		                    { (void**)&w.shadowRays[0], px * 32 }, { (void**)&w.shadowRays[1], px * 32 }, { (void**)&w.occluded[0], px }, { (void**)&w.occluded[1], px },
+		                    { (void**)&w.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) }, { (void**)&w.tailMark, f->pixels() * 4 }, { (void**)&w.tailList, px * 4 } });
+	}
+	v.insert(v.end(), { { (void**)&f->ru.task, px * 3 * ShiftTaskWords * 16 }, { (void**)&f->ru.rays, px * 3 * 32 }, { (void**)&f->ru.occluded, px * 3 }, { (void**)&f->ru.shadeList, px * 3 * 4 },
+	                    { (void**)&f->ru.redoList, px * 4 }, { (void**)&f->ru.counters, 16 * sizeof(uint32_t) } });
+	return v;
 }
 
 RPT_API int rpt_frame_clear(RptFrame* f) {
@@ -515,9 +551,8 @@ RPT_API int rpt_frame_clear(RptFrame* f) {
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	joinTail(f);
 	joinLate(f);
-	auto slots = frameSlots(f);
-	for (size_t i = 0; i < slots.size(); i++) CU(f->ctx, cudaMemsetAsync(*slots[i], 0, slotBytes(f, i), f->stream));
-	f->cur = 0;
+	for (const FrameSlot& sl : frameSlots(f)) CU(f->ctx, cudaMemsetAsync(*sl.ptr, 0, slotBytes(f, sl), f->stream));
+	f->flips = 0;
 	return RPT_OK;
 }
 
@@ -536,9 +571,8 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	f->halo = halo;
 	cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { delete f; return cudaFail(ctx, e, "cudaStreamCreate"); }
-	auto slots = frameSlots(f);
-	for (size_t i = 0; i < slots.size(); i++) {
-		e = cudaMalloc(slots[i], slotBytes(f, i));
+	for (const FrameSlot& sl : frameSlots(f)) {
+		e = cudaMalloc(sl.ptr, slotBytes(f, sl));
 		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc frame buffer"); }
 	}
 	e = cudaMalloc(&f->flags, PeerFlagCount * sizeof(uint32_t));
@@ -552,17 +586,15 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc work counters"); }
 	{
 		const size_t px = size_t(f->width) * (f->rowEnd - f->rowBegin);
-		auto wfs = wavefrontSlots(f);
-		const size_t wfBytes[] = { px * PathStateWords * 16, px * PathStateWords * 16, f->pixels() * 32, px * 32, px * 32, px * 4, px * 4, px * 16,
-		                           px * 32, px * 32, px, px, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), f->pixels() * 4, px * 4,
-		                           px * 3 * ShiftTaskWords * 16, px * 3 * 32, px * 3, px * 3 * 4, px * 4, 16 * sizeof(uint32_t) };
-		for (size_t i = 0; i < wfs.size(); i++) {
-			e = cudaMalloc(wfs[i], wfBytes[i]);
+		for (const WavefrontSlot& ws : wavefrontSlots(f)) {
+			e = cudaMalloc(ws.ptr, ws.bytes);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc wavefront buffer"); }
 		}
-		f->wf.capacity = uint32_t(px);
 		f->ru.capacity = uint32_t(px);
-		e = cudaMemset(f->wf.tailMark, 0, f->pixels() * 4);
+		for (WavefrontView& w : f->wfSet) {
+			w.capacity = uint32_t(px);
+			if (e == cudaSuccess) e = cudaMemset(w.tailMark, 0, f->pixels() * 4);
+		}
 		if (e == cudaSuccess) {   // highest priority: its small kernels must slip in between the blocks of the big pass on `stream`
 			int lo = 0, hi = 0;
 			cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -576,7 +608,8 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 			cudaDeviceGetStreamPriorityRange(&lo, &hi);
 			e = cudaStreamCreateWithPriority(&f->lateStream, cudaStreamNonBlocking, hi);
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, hi);
-			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone })
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->ptSide, cudaStreamNonBlocking, hi);
+			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
 				if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "late stream"); }
 		}
@@ -591,7 +624,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 static void disconnectPeers(RptFrame* f) {
 	for (RptFrame::Peer* p : { &f->up, &f->down }) {
 		if (p->connected && p->ipc) {
-			for (void* q : { (void*)p->grisTemp, (void*)p->diTemp, (void*)p->flags, (void*)p->gris[0], (void*)p->gris[1],
+			for (void* q : { (void*)p->grisTemp, (void*)p->diTemp, (void*)p->flags, (void*)p->gris[0], (void*)p->gris[1], (void*)p->gris[2],
 			                 (void*)p->di[0], (void*)p->di[1], (void*)p->gi[0], (void*)p->gi[1] })
 				if (q) cudaIpcCloseMemHandle(q);
 		}
@@ -613,8 +646,10 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->tailStream) cudaStreamSynchronize(f->tailStream);
 	if (f->lateSide) cudaStreamSynchronize(f->lateSide);
 	if (f->lateStream) cudaStreamSynchronize(f->lateStream);
+	if (f->ptSide) cudaStreamSynchronize(f->ptSide);
 	if (f->stream) cudaStreamSynchronize(f->stream);
-	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone }) if (ev) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone, f->lateHead, f->lateFrameDone[0], f->lateFrameDone[1], f->ptFork, f->ptJoin }) if (ev) cudaEventDestroy(ev);
+	if (f->ptSide) cudaStreamDestroy(f->ptSide);
 	if (f->lateSide) cudaStreamDestroy(f->lateSide);
 	if (f->lateStream) cudaStreamDestroy(f->lateStream);
 	if (f->tailFork) cudaEventDestroy(f->tailFork);
@@ -628,10 +663,10 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->copyStream) { cudaStreamSynchronize(f->copyStream); cudaStreamDestroy(f->copyStream); }
 	for (int i = 0; i < 2; i++) { if (f->postDone[i]) cudaEventDestroy(f->postDone[i]); if (f->copyDone[i]) cudaEventDestroy(f->copyDone[i]); }
 	if (f->rgba8Alt) cudaFree(f->rgba8Alt);
-	for (void** s : frameSlots(f)) if (*s) cudaFree(*s);
+	for (const FrameSlot& sl : frameSlots(f)) if (*sl.ptr) cudaFree(*sl.ptr);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
-	for (void** p : wavefrontSlots(f)) if (*p) cudaFree(*p);
+	for (const WavefrontSlot& ws : wavefrontSlots(f)) if (*ws.ptr) cudaFree(*ws.ptr);
 	drainTiming(f);
 	for (cudaEvent_t e : f->eventPool) cudaEventDestroy(e);
 	if (f->stream) cudaStreamDestroy(f->stream);
@@ -640,7 +675,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 
 RPT_API int rpt_frame_flip(RptFrame* f) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_frame_flip: NULL frame");
-	f->cur ^= 1u;
+	f->flips++;
 	return RPT_OK;
 }
 
@@ -659,21 +694,22 @@ RPT_API int rpt_set_camera(RptFrame* f, const RptCamera* cur, const RptCamera* p
 
 static FrameView makeView(RptFrame* f) {
 	FrameView v{};
-	const uint32_t c = f->cur, p = f->cur ^ 1u;
+	const uint32_t c = f->c2(), p = f->p2(), c3 = f->c3(), p3 = f->p3();
 	v.width = f->width; v.height = f->height; v.rowBegin = f->rowBegin; v.rowEnd = f->rowEnd;
 	v.storeBegin = f->storeBegin; v.storeEnd = f->storeEnd;
 	v.directOutput = f->directOutput; v.indirectOutput = f->indirectOutput;
-	v.depthNormal = f->depthNormal[c]; v.depthNormalPrev = f->depthNormal[p];
-	v.albedoMatId = f->albedoMatId[c]; v.albedoMatIdPrev = f->albedoMatId[p];
-	v.motion = f->motion;
+	v.depthNormal = f->depthNormal[c3]; v.depthNormalPrev = f->depthNormal[p3];
+	v.albedoMatId = f->albedoMatId[c3]; v.albedoMatIdPrev = f->albedoMatId[p3];
+	v.motion = f->motion[c3];
 	v.diThis = f->di[c]; v.diPrev = f->di[p]; v.diTemp = f->diTemp;
 	v.giThis = f->gi[c]; v.giPrev = f->gi[p];
-	v.grisThis = f->gris[c]; v.grisPrev = f->gris[p]; v.grisTemp = f->grisTemp;
+	v.grisThis = f->gris[c3]; v.grisPrev = f->gris[p3]; v.grisTemp = f->grisTemp;
+	v.grisStale = f->gris[f->n3()];   // (what a ping-pong pair would still hold in "this": the reservoirs of two frames ago)
 	v.primaryIsec = f->primaryIsec;
 	v.camera = f->camera; v.prevCamera = f->prevCamera;
 	v.halo = f->halo;
 	v.work = f->work;
-	v.wf = f->wf;
+	v.wf = f->wf();
 	v.ru = f->ru;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
@@ -685,7 +721,7 @@ static FrameView makeView(RptFrame* f) {
 	// the neighbours' final-reservoir buffers of this frame, and the rows whose previous-frame state is therefore valid here:
 	// a connected side contributes its halo rows except the outermost one (the bilinear G-buffer tap of a lookup in row y also
 	// reads row y-1 or y+1; at a film edge the wrap rows are stored, see depthNormalRow)
-	v.peerGrisThisUp = f->up.connected ? f->up.gris[c] : nullptr;     v.peerGrisThisDown = f->down.connected ? f->down.gris[c] : nullptr;
+	v.peerGrisThisUp = f->up.connected ? f->up.gris[c3] : nullptr;    v.peerGrisThisDown = f->down.connected ? f->down.gris[c3] : nullptr;
 	v.peerDiThisUp = f->up.connected ? f->up.di[c] : nullptr;         v.peerDiThisDown = f->down.connected ? f->down.di[c] : nullptr;
 	v.peerGiThisUp = f->up.connected ? f->up.gi[c] : nullptr;         v.peerGiThisDown = f->down.connected ? f->down.gi[c] : nullptr;
 	v.prevRowBegin = f->up.connected ? (f->storeBegin == 0 ? 0 : f->storeBegin + 1) : f->rowBegin;
@@ -706,7 +742,7 @@ static SceneView sceneView(const RptScene* s) {
 	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, name ": a multi-GPU hand-over of an earlier pass timed out on the device (a neighbouring strip died or was not driven in lock step); disconnect the peers to recover"); \
 	CU(f->ctx, cudaSetDevice(f->ctx->device)); \
 	joinTail(f);
-// every pass but the G-buffer and the ReSTIR PT path tracer (PASS_PROLOGUE_EARLY) waits for the previous frame's late passes
+// every pass but the G-buffer and the ReSTIR PT path tracer (PASS_PROLOGUE_EARLY + waitSlotReaders) waits for the late passes in flight
 #define PASS_PROLOGUE(name) \
 	PASS_PROLOGUE_EARLY(name) \
 	joinLate(f);
@@ -724,6 +760,7 @@ static SceneView sceneView(const RptScene* s) {
 // to the previous frame's late passes)
 RPT_API int rpt_gbuffer(RptFrame* f, const RptScene* s) {
 	PASS_PROLOGUE_EARLY("rpt_gbuffer")
+	waitSlotReaders(f);
 	{ PassTimer timer(f, RPT_PASS_GBUFFER); launchGBuffer(makeView(f), sceneView(s), f->stream); }
 	PASS_EPILOGUE("rpt_gbuffer")
 }
@@ -813,7 +850,9 @@ SETTINGS_PASS(rpt_di_spatial, RptDISettings, RPT_PASS_DI_SPATIAL, launchDISpatia
 RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
 	PASS_PROLOGUE_EARLY("rpt_gris_pathtrace")   // (reads the new G-buffer, writes the reservoirs the previous frame read as history)
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_pathtrace: NULL settings");
-	f->wf.epoch++;
+	waitSlotReaders(f);
+	f->lastWfSet = f->flips & 1u;
+	f->wf().epoch++;
 	const FrameView view = makeView(f);
 	const SceneView scene = sceneView(s);
 	{
@@ -821,7 +860,7 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 		FrameKernelClock clock(f);
 		const bool overlap = !f->ctx->traceOneStream;   // A/B switch (profiles/r1_18_*)
 		launchGRISPathTraceBounces(view, scene, *st, 0, WavefrontTailStart - 1, f->stream, f->timing ? &clock : nullptr,
-		                           overlap ? f->tailStream : nullptr, f->tailFork, f->tailDone);
+		                           overlap ? f->ptSide : nullptr, f->ptFork, f->ptJoin);
 	}
 	CU(f->ctx, cudaEventRecord(f->tailFork, f->stream));
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
@@ -843,32 +882,57 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_temporal: NULL settings");
 	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gris_temporal: a multi-GPU hand-over of an earlier pass timed out on the device; disconnect the peers to recover");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	const FrameView view = makeView(f);
+	const SceneView scene = sceneView(s);
+	const bool hadTail = f->tailPending;
+	if (pipelined(f) && !f->ctx->traceOneStream) {
+		// The whole pass goes to the late stream set, behind the previous frame's spatial pass (which wrote this frame's history and
+		// read the buffers this pass writes) and behind everything enqueued on the frame's stream so far (the path tracer).  Three
+		// streams inside: the late stream carries gen / visibility rays / merge of every pixel outside the path tracer's tail; the
+		// tail's pixels — independent of all others in this pass (own reservoir, own history pixel) — take their temporal step right
+		// behind the tail kernel on ITS stream; the pixels whose history sample needs replay rays run as a list kernel on the late
+		// set's side stream.  All three are joined here, because the hand-over signal to neighbouring strips and the spatial pass
+		// (next on the late stream) need every pixel of the pass.
+		LateScope late(f);
+		peerBefore(f, HookGrisTemporal);
+		{
+			PassTimer timer(f, RPT_PASS_GRIS_TEMPORAL);
+			FrameKernelClock clock(f);
+			KernelClock* ck = f->timing ? &clock : nullptr;
+			if (hadTail) {
+				CU(f->ctx, cudaEventRecord(f->lateHead, f->stream));
+				CU(f->ctx, cudaStreamWaitEvent(late.t0, f->lateHead, 0));
+				launchGRISTemporal(view, scene, *st, late.t0, 2, nullptr);
+				CU(f->ctx, cudaEventRecord(late.b0, late.t0));
+			}
+			launchGRISTemporal(view, scene, *st, f->stream, hadTail ? 1 : 0, ck, f->tailStream, f->tailFork);
+			CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
+			if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
+			CU(f->ctx, cudaStreamWaitEvent(f->stream, f->tailDone, 0));
+			if (hadTail) { CU(f->ctx, cudaStreamWaitEvent(f->stream, late.b0, 0)); f->tailPending = false; }
+		}
+		peerAfter(f, HookGrisTemporal);
+		PASS_EPILOGUE("rpt_gris_temporal")
+	}
 	joinLate(f);   // the previous frame's spatial pass wrote this frame's history and read the buffers this pass writes
 	peerBefore(f, HookGrisTemporal);
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_TEMPORAL);
-		const FrameView view = makeView(f);
-		const SceneView scene = sceneView(s);
 		FrameKernelClock clock(f);
 		KernelClock* ck = f->timing ? &clock : nullptr;
-		// Second stream: (a) the pixels of the path-tracing tail — independent of all others in this pass (own reservoir, own
-		// history pixel) — take their temporal step right behind the tail kernel on ITS stream; (b) the pixels whose history
-		// sample needs replay rays follow there as soon as gen has listed them.  The spatial pass (or whatever touches the
-		// frame next) joins that stream; with neighbouring strips connected the join comes at once, because the hand-over
-		// signal below must follow every pixel of the pass.
-		const bool oneStream = f->ctx->traceOneStream;
-		const bool hadTail = f->tailPending;
-		if (hadTail && oneStream) {
-			launchGRISTemporal(view, scene, *st, f->stream, 1, ck);
-			if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
-			joinTail(f);
-			launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
+		if (f->ctx->traceOneStream) {
+			if (hadTail) {
+				launchGRISTemporal(view, scene, *st, f->stream, 1, ck);
+				if (ck) ck->tick(RPT_KERNEL_TAIL_WAIT);
+				joinTail(f);
+				launchGRISTemporal(view, scene, *st, f->stream, 2, ck);
+			}
+			else launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
 		}
-		else if (oneStream) launchGRISTemporal(view, scene, *st, f->stream, 0, ck);
 		else {
+			// one frame at a time (RPT_NO_FRAME_OVERLAP): the same three streams, joined by the next pass (at once when neighbouring
+			// strips are connected: the hand-over signal below must follow every pixel of the pass)
 			if (hadTail) launchGRISTemporal(view, scene, *st, f->tailStream, 2, nullptr);
-			// (b) goes to a stream of its own — the late set's side stream, idle here: this pass has joined the previous frame's
-			// late passes — so that the two latency-bound kernels run next to each other, not one behind the other
 			cudaStream_t listStream = f->lateSide ? f->lateSide : f->tailStream;
 			launchGRISTemporal(view, scene, *st, f->stream, hadTail ? 1 : 0, ck, listStream, f->tailFork);
 			if (listStream != f->tailStream) {
@@ -884,14 +948,21 @@ RPT_API int rpt_gris_temporal(RptFrame* f, const RptScene* s, const RptGRISSetti
 	PASS_EPILOGUE("rpt_gris_temporal")
 }
 RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
-	PASS_PROLOGUE("rpt_gris_spatial")
+	if (!f || !s) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_gris_spatial: NULL argument");
+	if (f->ctx != s->ctx) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_spatial: frame and scene belong to different contexts");
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_spatial: NULL settings");
+	if (f->hostError && *reinterpret_cast<volatile uint32_t*>(f->hostError)) return fail(f->ctx, RPT_ERR_PEER, "rpt_gris_spatial: a multi-GPU hand-over of an earlier pass timed out on the device; disconnect the peers to recover");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	// (late stream set: in order behind the temporal pass; the frame's stream is not held up — it may already carry the next frame)
+	if (!pipelined(f)) { joinTail(f); joinLate(f); }
+	const bool tailOnMainSet = f->tailPending;   // a tail (or a temporal pass run on the frame's streams) not joined yet
+	cudaEvent_t mainTailDone = f->tailDone;
 	LateScope late(f);
+	if (late.on && tailOnMainSet) { CU(f->ctx, cudaStreamWaitEvent(f->stream, mainTailDone, 0)); f->tailPending = false; }
 	peerBefore(f, HookGrisSpatial);
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
 		FrameKernelClock clock(f);
-		joinTail(f);   // (the tail stream and its events are free again from here)
 		const bool side = !f->ctx->spatialOneStream;   // A/B switch
 		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
 		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone);
@@ -1052,11 +1123,13 @@ RPT_API int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out) {
 	CU(f->ctx, handle(out->grisTempHandle, f->grisTemp));
 	CU(f->ctx, handle(out->diTempHandle, f->diTemp));
 	CU(f->ctx, handle(out->flagsHandle, f->flags));
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < 3; i++) {
 		CU(f->ctx, handle(out->grisHandle[i], f->gris[i]));
+		out->grisPtr[i] = reinterpret_cast<uint64_t>(f->gris[i]);
+	}
+	for (int i = 0; i < 2; i++) {
 		CU(f->ctx, handle(out->diHandle[i], f->di[i]));
 		CU(f->ctx, handle(out->giHandle[i], f->gi[i]));
-		out->grisPtr[i] = reinterpret_cast<uint64_t>(f->gris[i]);
 		out->diPtr[i] = reinterpret_cast<uint64_t>(f->di[i]);
 		out->giPtr[i] = reinterpret_cast<uint64_t>(f->gi[i]);
 	}
@@ -1066,14 +1139,14 @@ RPT_API int rpt_frame_export_peer(RptFrame* f, RptPeerInfo* out) {
 	out->pid = uint64_t(getpid());
 	out->device = f->ctx->device;
 	out->rowBegin = f->rowBegin; out->rowEnd = f->rowEnd; out->storeBegin = f->storeBegin; out->storeEnd = f->storeEnd;
-	out->cur = f->cur;
+	out->cur = f->flips;
 	return RPT_OK;
 }
 
 static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
 	p = RptFrame::Peer{};
 	if (!info) return RPT_OK;
-	void* q[9] = {};
+	void* q[10] = {};
 	if (info->pid == uint64_t(getpid())) {
 		// same process: plain pointers, peer access enabled when the neighbour lives on another device
 		if (info->device != f->ctx->device) {
@@ -1084,14 +1157,14 @@ static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
 			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(f->ctx, e, "cudaDeviceEnablePeerAccess");
 			cudaGetLastError();
 		}
-		const uint64_t raw[9] = { info->grisTempPtr, info->diTempPtr, info->flagsPtr, info->grisPtr[0], info->grisPtr[1],
-		                          info->diPtr[0], info->diPtr[1], info->giPtr[0], info->giPtr[1] };
-		for (int i = 0; i < 9; i++) q[i] = reinterpret_cast<void*>(raw[i]);
+		const uint64_t raw[10] = { info->grisTempPtr, info->diTempPtr, info->flagsPtr, info->grisPtr[0], info->grisPtr[1], info->grisPtr[2],
+		                           info->diPtr[0], info->diPtr[1], info->giPtr[0], info->giPtr[1] };
+		for (int i = 0; i < 10; i++) q[i] = reinterpret_cast<void*>(raw[i]);
 	}
 	else {
-		const uint8_t* h[9] = { info->grisTempHandle, info->diTempHandle, info->flagsHandle, info->grisHandle[0], info->grisHandle[1],
-		                        info->diHandle[0], info->diHandle[1], info->giHandle[0], info->giHandle[1] };
-		for (int i = 0; i < 9; i++) {
+		const uint8_t* h[10] = { info->grisTempHandle, info->diTempHandle, info->flagsHandle, info->grisHandle[0], info->grisHandle[1], info->grisHandle[2],
+		                         info->diHandle[0], info->diHandle[1], info->giHandle[0], info->giHandle[1] };
+		for (int i = 0; i < 10; i++) {
 			cudaError_t e = cudaIpcOpenMemHandle(&q[i], *reinterpret_cast<const cudaIpcMemHandle_t*>(h[i]), cudaIpcMemLazyEnablePeerAccess);
 			if (e != cudaSuccess) {
 				for (int k = 0; k < i; k++) cudaIpcCloseMemHandle(q[k]);
@@ -1101,12 +1174,13 @@ static int connectOne(RptFrame* f, RptFrame::Peer& p, const RptPeerInfo* info) {
 		p.ipc = true;
 	}
 	p.grisTemp = static_cast<RptGRISReservoir*>(q[0]); p.diTemp = static_cast<RptDIReservoir*>(q[1]); p.flags = static_cast<uint32_t*>(q[2]);
-	// index the neighbour's ping-pong buffers by OUR phase: both frames flip once per frame from here on
-	const uint32_t phase = (info->cur ^ f->cur) & 1u;
+	// index the neighbour's buffers by OUR phases: both frames flip once per frame from here on
+	const uint32_t phase2 = (info->cur ^ f->flips) & 1u;
+	const uint32_t phase3 = (info->cur % 3u + 3u - f->flips % 3u) % 3u;   // its slot = (ours + phase3) mod 3
+	for (uint32_t i = 0; i < 3; i++) p.gris[i] = static_cast<RptGRISReservoir*>(q[3 + (i + phase3) % 3u]);
 	for (uint32_t i = 0; i < 2; i++) {
-		p.gris[i] = static_cast<RptGRISReservoir*>(q[3 + (i ^ phase)]);
-		p.di[i] = static_cast<RptDIReservoir*>(q[5 + (i ^ phase)]);
-		p.gi[i] = static_cast<RptGIReservoir*>(q[7 + (i ^ phase)]);
+		p.di[i] = static_cast<RptDIReservoir*>(q[6 + (i ^ phase2)]);
+		p.gi[i] = static_cast<RptGIReservoir*>(q[8 + (i ^ phase2)]);
 	}
 	p.storeBegin = info->storeBegin;
 	p.connected = true;
@@ -1308,7 +1382,7 @@ RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
 	joinTail(f);
 	joinLate(f);
 	CU(f->ctx, syncFrame(f));
-	CU(f->ctx, cudaMemcpy(out64, f->wf.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CU(f->ctx, cudaMemcpy(out64, f->wfSet[f->lastWfSet].counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return RPT_OK;
 }
 

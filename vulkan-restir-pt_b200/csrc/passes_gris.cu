@@ -617,9 +617,16 @@ __global__ void __launch_bounds__(ShadeBlock) grisBeginKernel(const __grid_const
 	const uint32_t x = (tile % tilesX) * 8u + (within & 7u), y = f.rowBegin + (tile / tilesX) * 4u + (within >> 3);
 	if (x >= f.width || y >= f.rowEnd) return;
 	const Primary p = loadPrimary(f, x, y);
-	if (!p.valid) return;   // background pixels keep their old reservoir (gris_path_trace.glsl:54-56)
 	const uint32_t pix = uint32_t(f.index(x, y));
 	RptGRISReservoir* slot = f.grisThis + pix;
+	if (!p.valid) {
+		// background pixels keep their old reservoir (gris_path_trace.glsl:54-56) — in the reference's ping-pong pair that is the
+		// reservoir of two frames ago; here the final reservoirs rotate through three buffers, so it is carried over
+		const float4* old = reinterpret_cast<const float4*>(f.grisStale + pix);
+		float4* q = reinterpret_cast<float4*>(slot);
+		for (int i = 0; i < 6; i++) q[i] = old[i];
+		return;
+	}
 
 	PathState st;
 	st.dir = p.ray.dir;

@@ -127,6 +127,7 @@ struct FrameView {
 	RptDIReservoir* diThis;  const RptDIReservoir* diPrev;  RptDIReservoir* diTemp;
 	RptGIReservoir* giThis;  const RptGIReservoir* giPrev;
 	RptGRISReservoir* grisThis;  const RptGRISReservoir* grisPrev;  RptGRISReservoir* grisTemp;
+	const RptGRISReservoir* grisStale;   // the reservoirs of two frames ago (background pixels of the path-tracing pass keep them)
 	RptIntersection* primaryIsec;
 	RptCamera camera, prevCamera;
 

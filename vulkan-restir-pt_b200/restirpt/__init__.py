@@ -101,9 +101,9 @@ class Counters(C.Structure):
 
 class PeerInfo(C.Structure):
     _fields_ = [("grisTempHandle", C.c_uint8 * 64), ("diTempHandle", C.c_uint8 * 64), ("flagsHandle", C.c_uint8 * 64),
-                ("grisHandle", C.c_uint8 * 64 * 2), ("diHandle", C.c_uint8 * 64 * 2), ("giHandle", C.c_uint8 * 64 * 2),
+                ("grisHandle", C.c_uint8 * 64 * 3), ("diHandle", C.c_uint8 * 64 * 2), ("giHandle", C.c_uint8 * 64 * 2),
                 ("grisTempPtr", C.c_uint64), ("diTempPtr", C.c_uint64), ("flagsPtr", C.c_uint64),
-                ("grisPtr", C.c_uint64 * 2), ("diPtr", C.c_uint64 * 2), ("giPtr", C.c_uint64 * 2), ("pid", C.c_uint64),
+                ("grisPtr", C.c_uint64 * 3), ("diPtr", C.c_uint64 * 2), ("giPtr", C.c_uint64 * 2), ("pid", C.c_uint64),
                 ("device", C.c_int32), ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32), ("storeBegin", C.c_uint32),
                 ("storeEnd", C.c_uint32), ("cur", C.c_uint32), ("pad", C.c_uint32 * 2)]
 
