@@ -10,10 +10,10 @@ sequence) over the C ABI of include/restirpt.h.
 Workload (BASELINE.json config 3): VeachAjar (the reference's shipped scene; a synthetic 380 k-triangle stand-in
 room when the asset is absent), 1920x1080 per GPU, indirect = ResampledPT {Hybrid, rrScale 1, temporal 1,
 spatial 1, cap 20}, direct = None, per-frame seed hash2(frame + 1), static camera.
-N > 1: weak scaling — the film grows to N x (1920x1080) pixels (N = 4 is exactly the 3840x2160 film of config 4) and is
-split into N horizontal strips, one process per GPU, scene + BVH replicated, temporal-pass reservoirs of the 21
+N > 1: weak scaling — the film shows the same view with N x (1920x1080) pixels (2720x1530, 3840x2160 = the film of config 4,
+5432x3056) and is split into N horizontal strips, one process per GPU, scene + BVH replicated, temporal-pass reservoirs of the 21
 boundary rows pushed into the neighbours' halo rows over NVLink peer memory each frame.  `value` is in
-1080p-equivalent frames/s summed over the GPUs (= film frames/s x N).
+1080p-equivalent frames/s summed over the GPUs (= film frames/s x film pixels / 1080p pixels).
 
 `--impl reference` times the CPU oracle (oracle/liboracle.so: the C++ restatement of the reference shaders, all
 host threads) on a bounded sample of the same workload — the reference itself cannot run here (Windows-only build,
@@ -42,18 +42,13 @@ UNIT = "frames/s (1080p-equivalent)"
 
 
 def film_for(n_gpus):
-    """N x 1080p pixels: 1 -> 1920x1080, 2 -> 1920x2160, 4 -> 3840x2160 (4K), 8 -> 3840x4320"""
-    w, h, k = TILE_W, TILE_H, n_gpus
-    grow_h = True
-    while k > 1:
-        if k % 2:
-            raise SystemExit("--gpus must be a power of two")
-        if grow_h:
-            h *= 2
-        else:
-            w *= 2
-        grow_h = not grow_h
-        k //= 2
+    """The SAME view at N x the pixels of 1920x1080 (16:9 kept, so every GPU count renders the same picture and a pixel costs the
+    same at every N): 1 -> 1920x1080, 2 -> 2720x1530, 4 -> 3840x2160 (the 4K film of config 4), 8 -> 5432x3056 (width = multiple of
+    8 nearest to 1920 sqrt(N)).  The pixel count is N x 1080p to within 0.7 %; `value` scales by the exact ratio."""
+    if n_gpus < 1:
+        raise SystemExit("--gpus must be positive")
+    w = 8 * int(round(TILE_W * n_gpus ** 0.5 / 8.0))
+    h = 2 * int(round(w * TILE_H / float(TILE_W) / 2.0))
     return w, h
 
 
@@ -350,9 +345,12 @@ class Arm:
         dev_ms = self.max_over_ranks(e0.elapsed_time(e1))
         # the per-pass / per-kernel breakdown comes from a second run of the same frames with the library's event timing on (about
         # 40 timing events per frame, which cost a little and are therefore kept out of the region above)
+        # and ONE FRAME AT A TIME (rpt_frame_join after every frame: the next frame's G-buffer and path tracer then wait for this frame's
+        # reuse passes instead of running next to them), so that a kernel's time is its own and not that of whatever shared the GPU
         dev_lib.rpt_frame_timing(frame, 1)
         for _ in range(steps):
             draw(None)
+            dev_lib.rpt_frame_join(frame)
         self.barrier(frame)
         stats = PassStats()
         dev_lib.rpt_frame_pass_stats(frame, C.byref(stats))
@@ -680,6 +678,9 @@ def run_cuda(args):
                        "mrays_per_s_per_gpu": total_rays / 1e6 * fps,
                        "rays_per_pixel": total_rays / px,
                        "pass_ms": per_pass_ms, "kernels": kernels,
+                       "kernel_timing": "pass_ms / kernels / roofline.kernel_ms: CUDA events around every launch in a second run of the same frames, ONE FRAME AT "
+                                        "A TIME (rpt_frame_join after each), so a kernel's time is its own; the headline regions run two frames in flight "
+                                        "(reuse passes of frame k next to G-buffer + path tracer of frame k+1) and are therefore shorter than the sum of pass_ms",
                        "tail_wait_ms_per_frame": (tail_wait["ms_per_frame"] if tail_wait else 0.0),
                        "strong_4k": strong_4k, "strip_image_equal": strip_check},
             "e2e": {"value": 1000.0 * args.steps / e2e_ms * equiv, "unit": UNIT,

@@ -77,6 +77,25 @@ def main():
     perm = rng.permutation(bounce.shape[0])
     sets = {"bounce/pixel-order": (bounce, 0), "bounce/shuffled": (bounce[perm], 0),
             "shadow/pixel-order": (shadow, 1), "shadow/shuffled": (shadow[perm], 1)}
+    if len(sys.argv) > 1 and sys.argv[1] == "sorted":
+        # what would sorting the queues buy?  (octant = the three direction signs; cell = Morton code of the origin on a 2^k grid)
+        def octant(r):
+            return ((r[:, 4] < 0).astype(np.int64) | ((r[:, 5] < 0).astype(np.int64) << 1) | ((r[:, 6] < 0).astype(np.int64) << 2))
+        def morton(r, bits):
+            o = r[:, 0:3].astype(np.float64)
+            lo, hi = o.min(0), o.max(0)
+            q = np.minimum(((o - lo) / (hi - lo + 1e-9) * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+            m = np.zeros(len(r), dtype=np.int64)
+            for i in range(bits):
+                for a in range(3):
+                    m |= ((q[:, a] >> i) & 1) << (3 * i + a)
+            return m
+        for tag, rays, any_hit in (("bounce", bounce, 0), ("shadow", shadow, 1), ("bounce-shuffled", bounce[perm], 0)):
+            oc = octant(rays)
+            sets[f"{tag}/by-octant(stable)"] = (rays[np.argsort(oc, kind="stable")], any_hit)
+            sets[f"{tag}/by-octant+cell5"] = (rays[np.lexsort((morton(rays, 5), oc))], any_hit)
+            sets[f"{tag}/by-cell5+octant"] = (rays[np.lexsort((oc, morton(rays, 5)))], any_hit)
+            sets[f"{tag}/by-cell7+octant"] = (rays[np.lexsort((oc, morton(rays, 7)))], any_hit)
     lib = dev.lib
     for name, (rays, any_hit) in sets.items():
         rays = np.ascontiguousarray(rays)
@@ -95,7 +114,7 @@ def main():
         lib.rpt_trace_bench(dev.ctx, b.scene, rays.ctypes.data_as(P), n, any_hit, 1, 1, C.byref(ms), None, None)
         c = Counters(); lib.rpt_counters_read(dev.ctx, C.byref(c)); lib.rpt_counters_enable(dev.ctx, 0)
         nr = (c.closestRays + c.shadowRays) or 1
-        print(f"{name:20s} n={n/1e6:.2f}M  per-thread {res[0][0]:7.3f} ms = {n/res[0][0]/1e3:7.1f} Mrays/s | queue {res[1][0]:7.3f} ms = "
+        print(f"{name:32s} n={n/1e6:.2f}M  per-thread {res[0][0]:7.3f} ms = {n/res[0][0]/1e3:7.1f} Mrays/s | queue {res[1][0]:7.3f} ms = "
               f"{n/res[1][0]/1e3:7.1f} Mrays/s | x{res[0][0]/res[1][0]:.2f} | identical={same} | nodes/ray {c.nodeVisits/nr:.1f} tris/ray {c.triTests/nr:.1f}")
 
 

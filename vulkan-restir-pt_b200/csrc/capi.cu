@@ -25,6 +25,8 @@ struct RptCtx {
 	bool countersOn = false;
 	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
 	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false, noFrameOverlap = false;
+	bool noShadeFromTask = false;
+	int priorityMode = 0;   // stream priorities (profiles/r2_20_*): 0 = late set, tail and path-tracer side stream above the frame's stream; 1 = all equal; 2 = frame's stream + its side stream above the late set
 };
 
 struct RptScene {
@@ -245,6 +247,8 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	ctx->wavefrontTail = getenv("RPT_WAVEFRONT_TAIL") != nullptr;
 	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
 	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
+	ctx->noShadeFromTask = getenv("RPT_NO_SHADE_FROM_TASK") != nullptr;   // A/B switch (profiles/r2_21_*)
+	if (const char* pm = getenv("RPT_PRIORITY_MODE")) ctx->priorityMode = atoi(pm);
 	*out = ctx;
 	return RPT_OK;
 }
@@ -569,7 +573,11 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	f->storeBegin = rowBegin > halo ? rowBegin - halo : 0;
 	f->storeEnd = std::min(fullHeight, rowEnd + halo);
 	f->halo = halo;
-	cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+	int prLo = 0, prHi = 0;
+	cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+	const int pm = ctx->priorityMode;
+	const int prMain = pm == 2 ? prHi : prLo, prPtSide = pm == 1 ? prLo : prHi, prTail = pm == 1 ? prLo : prHi, prLate = pm == 0 ? prHi : prLo;
+	cudaError_t e = cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, prMain);
 	if (e != cudaSuccess) { delete f; return cudaFail(ctx, e, "cudaStreamCreate"); }
 	for (const FrameSlot& sl : frameSlots(f)) {
 		e = cudaMalloc(sl.ptr, slotBytes(f, sl));
@@ -596,19 +604,15 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 			if (e == cudaSuccess) e = cudaMemset(w.tailMark, 0, f->pixels() * 4);
 		}
 		if (e == cudaSuccess) {   // highest priority: its small kernels must slip in between the blocks of the big pass on `stream`
-			int lo = 0, hi = 0;
-			cudaDeviceGetStreamPriorityRange(&lo, &hi);
-			e = cudaStreamCreateWithPriority(&f->tailStream, cudaStreamNonBlocking, hi);
+			e = cudaStreamCreateWithPriority(&f->tailStream, cudaStreamNonBlocking, prTail);
 		}
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailFork, cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->tailDone, cudaEventDisableTiming);
 		if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "tail stream"); }
 		{
-			int lo = 0, hi = 0;
-			cudaDeviceGetStreamPriorityRange(&lo, &hi);
-			e = cudaStreamCreateWithPriority(&f->lateStream, cudaStreamNonBlocking, hi);
-			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, hi);
-			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->ptSide, cudaStreamNonBlocking, hi);
+			e = cudaStreamCreateWithPriority(&f->lateStream, cudaStreamNonBlocking, prLate);
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, prLate);
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->ptSide, cudaStreamNonBlocking, prPtSide);
 			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
 				if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "late stream"); }
@@ -711,6 +715,7 @@ static FrameView makeView(RptFrame* f) {
 	v.work = f->work;
 	v.wf = f->wf();
 	v.ru = f->ru;
+	v.ru.noShadeFromTask = f->ctx->noShadeFromTask ? 1u : 0u;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
 	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;

@@ -63,10 +63,12 @@ RT_DEV uint32_t withRcVertexId(uint32_t fl, uint32_t id) { return (fl & 0xffffff
 RT_DEV uint32_t withPathLength(uint32_t fl, uint32_t id) { return (fl & 0xffff00ffu) | ((id & 0xffu) << 8); }
 RT_DEV uint32_t withRcVertexType(uint32_t fl, uint32_t t) { return (fl & 0xff00ffffu) | ((t & 0xffu) << 16); }
 
-RT_DEV void grisMerge(GRISResv& resv, GRISResv& rhs, float r) {   // gris_reservoir.glsl:114-123
+RT_DEV bool grisMerge(GRISResv& resv, GRISResv& rhs, float r) {   // gris_reservoir.glsl:114-123; true: rhs's sample was taken
 	resv.sampleCount() += rhs.sampleCount();
 	resv.resampleWeight() += rhs.resampleWeight();
-	if (r * resv.resampleWeight() < rhs.resampleWeight()) resv.copySample(rhs);
+	const bool take = r * resv.resampleWeight() < rhs.resampleWeight();
+	if (take) resv.copySample(rhs);
+	return take;
 }
 RT_DEV void grisCap(GRISResv& resv, float cap) {   // :131-136
 	if (resv.sampleCount() > cap) {
@@ -973,6 +975,26 @@ RT_DEV float3 spatialShade(const SceneView& s, const RptGRISSettings& st, const 
 	return clampColor(radiance);
 }
 
+// The same shading from the reconnection data a shift left behind (the reference's GRISReconnectionData, layouts.glsl:158-164,
+// which its unfinished retrace pass was to store once per sample, gris_retrace.glsl:238-320): when the selected sample is a
+// neighbour's, the shift that brought it to this pixel has already replayed its prefix HERE — same primary surface, same flags,
+// same random numbers as the replay of spatialShade — and its ShiftTask holds the result: both ends of the reconnection segment,
+// rcPrevWo and rcPrevThroughput.  (A task only wins a merge if its status was TaskRay and its ray unoccluded, so the replay found a
+// vertex.)  Same functions on the same operands: the same bits as spatialShade, without replay rays or surface fetches.
+RT_DEV float3 spatialShadeFromTask(const SceneView& s, const ShiftTask& t, GRISResv& resv) {
+	float3 radiance = f3(0.0f);
+	if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid()) {
+		RcData rc;
+		rc.prevInstance = 0; rc.prevTriangle = 0; rc.prevBary = make_float2(0.f, 0.f);
+		rc.rcPrevWo = t.rcPrevWo; rc.rcPrevThroughput = t.rcPrevThroughput;
+		const Mat rcPrevMat = loadMaterial(s, t.rcPrevSurf.matIndex);
+		const float3 wi = normalize(t.rcSurf.pos - t.rcPrevSurf.pos);
+		const float3 Li = reconnectionLi(s, resv, rc, t.rcPrevSurf, t.rcSurf, rcPrevMat, wi, resv.rcPrevSamplePdf());
+		if (!isBlack(Li) && !hasNan(Li)) radiance = Li / luminance(Li) * resv.resampleWeight() / resv.sampleCount();
+	}
+	return clampColor(radiance);
+}
+
 // the sequential per-pixel form (gris_resample_spatial.glsl:11-134), used for the redo list
 RT_DEV void grisSpatialPixel(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t x, uint32_t y) {
 	const Primary p = loadPrimary(f, x, y);
@@ -1078,6 +1100,7 @@ __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialMer
 		const size_t idx = f.index(x, y);
 		uint32_t rng = makeSeed(f.camera.seed, x, y) ^ 2u;
 		GRISResv resv = loadGRIS(f.grisTemp + idx);
+		int winner = -1;   // the neighbour whose sample the reservoir holds in the end (-1: the pixel's own)
 		if (st.spatialReuse) {
 			for (uint32_t i = 0; i < 3; i++) {
 				sample2f(rng);   // the two numbers that placed neighbour i
@@ -1090,17 +1113,24 @@ __global__ void __launch_bounds__(ReuseBlock, RT_REUSE_MINBLOCKS) grisSpatialMer
 					f.ru.redoList[atomicAdd(f.ru.counters + 1, 1u)] = o;
 					return;
 				}
-				grisMerge(resv, nr, sample1f(rng));
+				if (grisMerge(resv, nr, sample1f(rng))) winner = int(i);
 				grisCap(resv, float(st.cap));
 			}
 		}
 		if (!resv.valid()) resv.reset();
 		spatialStore(f, x, y, idx, resv);
-		if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid() && flagsRcVertexId(resv.flags()) != 1u) {
-			f.ru.shadeList[atomicAdd(f.ru.counters + 0, 1u)] = o;   // shading needs replay rays: grisSpatialShadeListKernel
-			return;
+		if (winner >= 0 && !f.ru.noShadeFromTask) {   // a neighbour's sample: its shift has left the reconnection data of this pixel behind
+			ShiftTask t;
+			loadShiftTask(f.ru, uint32_t(winner), o, t);
+			radiance = spatialShadeFromTask(s, t, resv);
 		}
-		radiance = spatialShade<false>(s, st, p, primarySurface(p), resv);   // rcVertexId == 1: the replay is the primary hit itself, no ray
+		else {
+			if (resv.valid() && resv.sampleCount() > 0 && resv.sampleValid() && flagsRcVertexId(resv.flags()) != 1u) {
+				f.ru.shadeList[atomicAdd(f.ru.counters + 0, 1u)] = o;   // shading needs replay rays: grisSpatialShadeListKernel
+				return;
+			}
+			radiance = spatialShade<false>(s, st, p, primarySurface(p), resv);   // rcVertexId == 1: the replay is the primary hit itself, no ray
+		}
 	}
 	accumulate(f.indirectOutput, f, x, y, radiance);
 }

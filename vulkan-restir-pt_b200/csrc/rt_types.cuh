@@ -111,6 +111,7 @@ struct ReuseView {
 	uint32_t* redoList;               // ... and pixels whose speculated random-number sequence did not hold (very rare)
 	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head, [3] spatial shift replay list size
 	uint32_t capacity;                // owned pixels
+	uint32_t noShadeFromTask;         // A/B switch (RPT_NO_SHADE_FROM_TASK): the spatial pass replays every selected sample for its final shading
 };
 
 struct FrameView {
