@@ -309,6 +309,7 @@ class Arm:
                         dev_lib.rpt_frame_timing(frame, 1)
                     if host.rh_renderer_draw_frame(r, restirpt.hash2(1000 + i), None) != 0:
                         raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
+                    dev_lib.rpt_frame_join(frame)      # (one frame at a time: a pass's time is then its own cost)
                 st = PassStats()
                 dev_lib.rpt_frame_pass_stats(frame, C.byref(st))
                 cost = sum(st.ms[i] for i in range(12))

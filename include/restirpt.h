@@ -289,14 +289,16 @@ int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeight,
                      uint32_t rowBegin, uint32_t rowEnd, uint32_t halo, RptFrame** out);
 void rpt_frame_destroy(RptFrame* frame);
 int rpt_frame_clear(RptFrame* frame);            /* zero every buffer, reset ping-pong */
-int rpt_frame_flip(RptFrame* frame);             /* mCurFrame ^= 1, reference src/Renderer.cpp:567 */
+int rpt_frame_flip(RptFrame* frame);             /* mCurFrame ^= 1, reference src/Renderer.cpp:567 (THIS becomes PREV) */
 void* rpt_frame_stream(RptFrame* frame);         /* cudaStream_t the passes run on (for event timing) */
-/* Frames overlap (new; the reference keeps one frame in flight, HostDevice.h:7): the last passes of a ReSTIR PT frame —
- * rpt_gris_spatial and the post-process that follows it — run on a second stream set, next to rpt_gbuffer and rpt_gris_pathtrace
- * of the NEXT frame, which touch none of their buffers; every other call joins them first, so results do not change.
- * rpt_frame_join makes the frame's stream wait (on the device, the host does not block) for everything enqueued on the frame's
- * other streams so far: an event recorded on rpt_frame_stream() after it covers all of the frame's work.  Environment
- * RPT_NO_FRAME_OVERLAP=1 keeps every pass on the one stream. */
+/* Frames overlap (new; the reference keeps one frame in flight, HostDevice.h:7): the reuse passes of a ReSTIR PT frame —
+ * rpt_gris_temporal, rpt_gris_spatial and the post-process that follows — run on a second stream set, in order, next to
+ * rpt_gbuffer and rpt_gris_pathtrace of the NEXT frame, which touch none of their buffers (the G-buffer, motion and GRIS
+ * reservoir buffers rotate through three slots, the path tracer's queues exist twice); the frame's stream is at most one
+ * frame ahead.  Every other call joins them first, so results do not change and buffers read between passes hold what the
+ * pass wrote.  rpt_frame_join makes the frame's stream wait (on the device, the host does not block) for everything enqueued
+ * on the frame's other streams so far: an event recorded on rpt_frame_stream() after it covers all of the frame's work.
+ * Environment RPT_NO_FRAME_OVERLAP=1 keeps one frame at a time. */
 int rpt_frame_join(RptFrame* frame);
 
 /* 2 x 352-byte Camera upload, reference src/Renderer.cpp:358-361 */

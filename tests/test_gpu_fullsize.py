@@ -84,17 +84,18 @@ def test_full_hd_film_strips_and_reservoir_invariants(bench_scene):
 
 
 def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
-    """The paths alive after bounce 6 are finished by one in-line kernel (grisTailKernel); RPT_WAVEFRONT_TAIL=1 runs them
-    through nine more wavefront rounds instead.  Same stage functions, so the reservoirs must agree bit for bit — at full
-    size, where the tail holds tens of thousands of paths."""
+    """The paths alive after bounce 6 run through nine more wavefront rounds on the tail stream; RPT_INLINE_TAIL=1 finishes them
+    in one kernel with in-line traversal instead (grisTailKernel, the default before the reuse passes moved one frame behind
+    the path tracer).  Same stage functions, so the reservoirs must agree bit for bit — at full size, where the tail holds tens
+    of thousands of paths."""
     w, h = 960, 540
     gs = GRISSettings(2, 1.0, 1, 1, 20)
     out = {}
     for mode in ("inline", "wavefront"):
-        if mode == "wavefront":
-            monkeypatch.setenv("RPT_WAVEFRONT_TAIL", "1")
+        if mode == "inline":
+            monkeypatch.setenv("RPT_INLINE_TAIL", "1")
         else:
-            monkeypatch.delenv("RPT_WAVEFRONT_TAIL", raising=False)
+            monkeypatch.delenv("RPT_INLINE_TAIL", raising=False)
         dev = restirpt.Device(0)      # (the switches are read when the context is created)
         b = Backend("cuda", bench_scene, w, h, dev)
         drv = FrameDriver(bench_scene.camera(w, h))
@@ -148,10 +149,41 @@ def test_two_stream_frame_equals_one_stream_frame(bench_scene, monkeypatch, meth
     assert bitwise_mismatch(out["two"][1], out["one"][1]) == 0
 
 
+def test_shading_from_the_shifts_reconnection_data_equals_replay_shading(bench_scene, monkeypatch):
+    """The spatial pass shades a neighbour's winning sample from the reconnection data its shift left in the ShiftTask
+    (spatialShadeFromTask, the reference's GRISReconnectionData idea, gris_retrace.glsl:238-320); RPT_NO_SHADE_FROM_TASK=1 replays
+    every selected sample again as the shader does (gris_resample_spatial.glsl:88-131).  Same functions on the same operands:
+    the film must be the same bits — on VeachAjar, whose glass makes thousands of samples reconnect beyond the first bounce."""
+    w, h = 960, 540
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+    out = {}
+    for mode in ("task", "replay"):
+        if mode == "replay":
+            monkeypatch.setenv("RPT_NO_SHADE_FROM_TASK", "1")
+        else:
+            monkeypatch.delenv("RPT_NO_SHADE_FROM_TASK", raising=False)
+        dev = restirpt.Device(0)      # (the switches are read when the context is created)
+        b = Backend("cuda", bench_scene, w, h, dev)
+        drv = FrameDriver(bench_scene.camera(w, h))
+        for i in range(3):
+            cur, prev = drv.begin_frame(move=(0.003 * i, 0.0, 0.001))
+            b.set_camera(cur, prev)
+            for name in ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"):
+                b.run(name, None if name == "gbuffer" else gs)
+            b.flip()
+        out[mode] = (b.read("GRIS_PREV"), b.read("INDIRECT_OUTPUT"))
+        b.close()
+        dev.close()
+    assert out["task"][1][..., :3].mean() > 0
+    assert bitwise_mismatch(out["task"][0], out["replay"][0]) == 0
+    assert bitwise_mismatch(out["task"][1], out["replay"][1]) == 0
+
+
 def test_overlapped_frames_equal_serial_frames(bench_scene, monkeypatch):
-    """Two frames in flight: rpt_gris_spatial and the post-process run on the frame's second stream set while rpt_gbuffer and
-    rpt_gris_pathtrace of the next frame are already running on the first (capi.cu, LateScope); RPT_NO_FRAME_OVERLAP=1 keeps every
-    pass on the one stream.  Six frames with a camera dolly and NO read or synchronisation in between (any read would join the
+    """Two frames in flight: the reuse passes of frame k (rpt_gris_temporal, rpt_gris_spatial, the post-process) run on the frame's
+    late stream set while rpt_gbuffer and rpt_gris_pathtrace of frame k+1 are already running on the frame's stream (capi.cu,
+    LateScope; three-slot rotation of G-buffer / motion / GRIS reservoirs, two sets of wavefront state); RPT_NO_FRAME_OVERLAP=1 keeps
+    one frame at a time.  Six frames with a camera dolly and NO read or synchronisation in between (any read would join the
     streams), at a film size where the passes really overlap: reservoirs, accumulated film and every tone-mapped image must be
     the same bits either way."""
     w, h = 1920, 1080

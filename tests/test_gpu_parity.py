@@ -182,6 +182,23 @@ def test_restir_pt_gris_bit_exact(pair, shift, temporal, spatial):
     assert (r["rcIsec"]["instanceIdx"] != 0xffffffff).mean() > 0.05
 
 
+def test_background_pixels_keep_the_reservoir_of_two_frames_ago(pair):
+    """gris_path_trace.glsl:54-56 returns early on a background pixel, so in the reference's ping-pong pair that pixel's "this"
+    reservoir still holds what the frame before last left there.  The CUDA side rotates its final reservoirs through THREE buffers
+    (frame pipeline) and has to carry that reservoir over — checked here with a camera that moves far enough for
+    surface pixels to turn into background and back, six frames, every buffer of every pass."""
+    name, sc, gpu, cpu = pair
+    moves = [(0.0, 0.0, 0.0), (0.6, 0.25, 0.0), (0.6, 0.25, 0.0), (-0.9, -0.3, 0.0), (-0.9, -0.3, 0.0), (0.6, 0.1, 0.0)]
+    shots = _compare_method(pair, "gris", 6, moves=moves, gris=GRISSettings(2, 1.0, 1, 1, 20))
+    valid = [shots[(i, "gbuffer", "DEPTH_NORMAL")][..., 0] > 0 for i in range(6)]
+    turned_background = sum(int((valid[i - 2] & ~valid[i]).sum()) for i in range(2, 6))
+    if not any((~v).any() for v in valid):
+        pytest.skip(f"{name}: a closed scene, no background pixels")
+    assert turned_background > 0, f"{name}: the camera move never turned a surface pixel into background"
+    # and the stale reservoirs are really there (not zeros): some background pixel holds a reservoir with history after the pass
+    assert any((shots[(i, "gris_pathtrace", "GRIS_THIS")]["sampleCount"][~valid[i]] > 0).any() for i in range(2, 6))
+
+
 def test_postprocess_within_one_lsb(pair):
     name, sc, gpu, cpu = pair
     cam = sc.camera(gpu.w, gpu.h)

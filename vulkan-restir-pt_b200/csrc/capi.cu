@@ -244,7 +244,10 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	CU(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
 	CU(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
 	ctx->traceOneStream = getenv("RPT_TRACE_ONE_STREAM") != nullptr;
-	ctx->wavefrontTail = getenv("RPT_WAVEFRONT_TAIL") != nullptr;
+	// the path tracer's tail (bounces >= WavefrontTailStart, on the tail stream) as further wavefront rounds — the default since the
+	// reuse passes run one frame behind the path tracer and the tail's latency is off the frame's critical path: what counts then is
+	// instructions, and the in-line tail kernel (RPT_INLINE_TAIL=1) spends four times as many at 3.5 lanes (profiles/r2_21_*)
+	ctx->wavefrontTail = getenv("RPT_INLINE_TAIL") == nullptr;
 	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
 	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
 	ctx->noShadeFromTask = getenv("RPT_NO_SHADE_FROM_TASK") != nullptr;   // A/B switch (profiles/r2_21_*)
