@@ -10,7 +10,7 @@ sequence) over the C ABI of include/restirpt.h.
 Workload (BASELINE.json config 3): VeachAjar (the reference's shipped scene; a synthetic 380 k-triangle stand-in
 room when the asset is absent), 1920x1080 per GPU, indirect = ResampledPT {Hybrid, rrScale 1, temporal 1,
 spatial 1, cap 20}, direct = None, per-frame seed hash2(frame + 1), static camera.
-N > 1: weak scaling — the film shows the same view with N x (1920x1080) pixels (2720x1530, 3840x2160 = the film of config 4,
+N > 1: weak scaling — the film shows the same view with N x (1920x1080) pixels (2712x1526, 3840x2160 = the film of config 4,
 5432x3056) and is split into N horizontal strips, one process per GPU, scene + BVH replicated, temporal-pass reservoirs of the 21
 boundary rows pushed into the neighbours' halo rows over NVLink peer memory each frame.  `value` is in
 1080p-equivalent frames/s summed over the GPUs (= film frames/s x film pixels / 1080p pixels).
@@ -43,7 +43,7 @@ UNIT = "frames/s (1080p-equivalent)"
 
 def film_for(n_gpus):
     """The SAME view at N x the pixels of 1920x1080 (16:9 kept, so every GPU count renders the same picture and a pixel costs the
-    same at every N): 1 -> 1920x1080, 2 -> 2720x1530, 4 -> 3840x2160 (the 4K film of config 4), 8 -> 5432x3056 (width = multiple of
+    same at every N): 1 -> 1920x1080, 2 -> 2712x1526, 4 -> 3840x2160 (the 4K film of config 4), 8 -> 5432x3056 (width = multiple of
     8 nearest to 1920 sqrt(N)).  The pixel count is N x 1080p to within 0.7 %; `value` scales by the exact ratio."""
     if n_gpus < 1:
         raise SystemExit("--gpus must be positive")
@@ -302,20 +302,28 @@ class Arm:
             bounds = multigpu.partition(fh, world)
             rounds = 0 if world == 1 or self.args.no_balance else 4
             for _ in range(rounds):
-                r, frame, link = self.open_strip(fw, fh, *bounds[rank])
-                for i in range(6):
-                    if i == 2:
-                        dev_lib.rpt_sync(frame)
-                        dev_lib.rpt_frame_timing(frame, 1)
+                # The cost of a strip = its frame time on a GPU of its own, frames pipelined as in the timed regions, NOT connected to
+                # its neighbours (their halo rows stay empty: a few pixels' work changes, the cost does not) — what the strip would
+                # do if it never had to wait.  (The sum of the per-pass device times of a connected strip, used before, weighs the
+                # latency chains of the reuse passes in full although the pipeline hides them: strips balanced that way differed by
+                # 12 % in their pipelined frame times, profiles/r2_23_*.)
+                r, frame, link = self.open_strip(fw, fh, *bounds[rank], connect=False)
+                cal_stream = torch.cuda.ExternalStream(dev_lib.rpt_frame_stream(frame), device=torch.device("cuda", self.local_rank))
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cal_frames = 8
+                for i in range(3 + cal_frames):
+                    if i == 3:
+                        dev_lib.rpt_frame_join(frame)
+                        c0.record(cal_stream)
                     if host.rh_renderer_draw_frame(r, restirpt.hash2(1000 + i), None) != 0:
                         raise SystemExit("draw_frame failed: " + host.rh_last_error().decode())
-                    dev_lib.rpt_frame_join(frame)      # (one frame at a time: a pass's time is then its own cost)
-                st = PassStats()
-                dev_lib.rpt_frame_pass_stats(frame, C.byref(st))
-                cost = sum(st.ms[i] for i in range(12))
+                dev_lib.rpt_frame_join(frame)
+                c1.record(cal_stream)
+                dev_lib.rpt_sync(frame)
+                cost = c0.elapsed_time(c1) / cal_frames
                 costs = [None] * world
                 self.dist.all_gather_object(costs, cost)
-                balance_log.append({"rows": [b[1] - b[0] for b in bounds], "ms_per_frame": [round(c / 4, 3) for c in costs]})
+                balance_log.append({"rows": [b[1] - b[0] for b in bounds], "ms_per_frame": [round(c, 3) for c in costs]})
                 bounds = multigpu.balanced_partition(bounds, costs, min_rows=max(2 * HALO, 64))
                 self.close_strip(r, link)
         r, frame, link = self.open_strip(fw, fh, *bounds[rank])

@@ -409,6 +409,11 @@ int rpt_trace_bench(RptCtx* ctx, const RptScene* s, const float* rays, uint32_t 
 /* queue sizes of the last wavefront path-tracing pass (new; diagnostics): out64[4*b + 0] = extension rays traced
  * for bounce b, out64[4*b + 1] = shadow rays of bounce b; implicit sync */
 int rpt_wavefront_counters(RptFrame* f, uint32_t* out64);
+/* list sizes of the last spatial-reuse pass (new, diagnostics): out[0] = pixels whose final shading needed replay rays, out[1] =
+ * pixels recomputed sequentially, out[3] = (pixel, neighbour) pairs replayed by the in-line list kernel, out[5] = ... by the
+ * replay wavefront.  The library reads the same numbers back asynchronously to pick the replay form for the next frame: the
+ * wavefront pays a fixed latency per bounce and wins when the list is long (RPT_RW_MIN_LIST, default 80000 pairs). */
+int rpt_reuse_counters(RptFrame* f, uint32_t* out16);
 
 /* memory-system microbenchmark (new): all SMs read a buffer of `bytes` bytes `iterations` times with 16-byte
  * loads -> GB/s (a buffer that fits B200's 126 MB L2 gives the L2 bandwidth, the roof of the traversal kernels on an L2-resident

@@ -225,9 +225,13 @@ def test_png_writer_roundtrip(tmp_path, built):
 def test_film_layout_and_partition():
     import bench
     from restirpt.multigpu import partition, storage_rows
-    assert bench.film_for(1) == (1920, 1080) and bench.film_for(2) == (1920, 2160)
-    assert bench.film_for(4) == (3840, 2160) and bench.film_for(8) == (3840, 4320)
-    for h, n in [(1080, 1), (2160, 4), (4320, 8), (1081, 4)]:
+    # weak scaling: the same 16:9 view with N x the pixels of 1920x1080 (N = 4 is the 4K film of BASELINE config 4)
+    assert bench.film_for(1) == (1920, 1080) and bench.film_for(2) == (2712, 1526)
+    assert bench.film_for(4) == (3840, 2160) and bench.film_for(8) == (5432, 3056)
+    for n in (1, 2, 4, 8):
+        w, h = bench.film_for(n)
+        assert abs(w * h / (1920.0 * 1080.0) - n) < 0.01 * n and abs(w / h - 16.0 / 9.0) < 2e-3
+    for h, n in [(1080, 1), (2160, 4), (3056, 8), (1081, 4)]:
         parts = partition(h, n)
         assert parts[0][0] == 0 and parts[-1][1] == h and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     assert storage_rows(0, 270, 2160, 21) == (0, 291) and storage_rows(270, 540, 2160, 21) == (249, 561)

@@ -179,6 +179,45 @@ def test_shading_from_the_shifts_reconnection_data_equals_replay_shading(bench_s
     assert bitwise_mismatch(out["task"][1], out["replay"][1]) == 0
 
 
+def test_replay_wavefront_equals_inline_replay(bench_scene, monkeypatch):
+    """The prefixes the reuse passes have to replay (samples that reconnect beyond the first bounce) run as a wavefront of their
+    own — one queue-traversal launch and one rwStepKernel per bounce; RPT_NO_REPLAY_WAVEFRONT=1 replays them one thread per
+    prefix with in-line traversal (the list kernels).  Both call replayVertex (gris_retrace.glsl:62-135) in the same order on
+    the same operands, so reservoirs and film must be the same bits — on VeachAjar, where thousands of samples per frame take
+    this way."""
+    w, h = 960, 540
+    gs = GRISSettings(2, 1.0, 1, 1, 20)
+    out = {}
+    for mode in ("wavefront", "inline"):
+        if mode == "inline":
+            monkeypatch.setenv("RPT_NO_REPLAY_WAVEFRONT", "1")
+            monkeypatch.delenv("RPT_RW_MIN_LIST", raising=False)
+        else:
+            monkeypatch.delenv("RPT_NO_REPLAY_WAVEFRONT", raising=False)
+            monkeypatch.setenv("RPT_RW_MIN_LIST", "0")      # (by default the wavefront is only used when the last frame's list was long)
+        dev = restirpt.Device(0)      # (the switches are read when the context is created)
+        b = Backend("cuda", bench_scene, w, h, dev)
+        drv = FrameDriver(bench_scene.camera(w, h))
+        for i in range(4):
+            cur, prev = drv.begin_frame(move=(0.003 * i, 0.001, 0.0))
+            b.set_camera(cur, prev)
+            for name in ("gbuffer", "gris_pathtrace", "gris_temporal", "gris_spatial"):
+                b.run(name, None if name == "gbuffer" else gs)
+            b.flip()
+        prevr = b.read("GRIS_PREV")
+        rc = (C.c_uint32 * 16)()
+        dev.lib.rpt_reuse_counters(b.frame, rc)
+        out[mode] = (prevr, b.read("GRIS_TEMP"), b.read("INDIRECT_OUTPUT"), list(rc))
+        b.close()
+        dev.close()
+    flags = out["wavefront"][0]["flags"]
+    valid = out["wavefront"][0]["rcIsec"]["instanceIdx"] != 0xffffffff
+    assert (valid & ((flags & 0xff) > 1)).sum() > 1000, "the scene must have samples that reconnect beyond the first bounce"
+    for k in range(3):
+        assert bitwise_mismatch(out["wavefront"][k], out["inline"][k]) == 0, k
+    assert out["wavefront"][3][5] > 1000 and out["inline"][3][5] == 0, "rpt_reuse_counters: the replays must have taken the way under test"
+
+
 def test_overlapped_frames_equal_serial_frames(bench_scene, monkeypatch):
     """Two frames in flight: the reuse passes of frame k (rpt_gris_temporal, rpt_gris_spatial, the post-process) run on the frame's
     late stream set while rpt_gbuffer and rpt_gris_pathtrace of frame k+1 are already running on the frame's stream (capi.cu,

@@ -25,7 +25,8 @@ struct RptCtx {
 	bool countersOn = false;
 	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
 	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false, noFrameOverlap = false;
-	bool noShadeFromTask = false;
+	bool noShadeFromTask = false, noReplayWavefront = false;
+	uint32_t rwMinList = 80000;    // replay pairs per spatial pass from which the replay wavefront is used (profiles/r2_24_*)
 	int priorityMode = 0;   // stream priorities (profiles/r2_20_*): 0 = late set, tail and path-tracer side stream above the frame's stream; 1 = all equal; 2 = frame's stream + its side stream above the late set
 };
 
@@ -88,14 +89,15 @@ struct RptFrame {
 	// other set of wavefront queues.  The frame's stream is at most one frame ahead: before the G-buffer of frame k+2 reuses the
 	// slots of frame k-1 it waits for the late passes of frame k (lateFrameDone[k & 1]), the last readers of those slots.  Any other
 	// pass, read-back or query joins everything first.
-	cudaStream_t lateStream = nullptr, lateSide = nullptr;
-	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr, lateHead = nullptr;
+	cudaStream_t lateStream = nullptr, lateSide = nullptr, lateSide2 = nullptr;
+	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr, lateSide2Done = nullptr, lateHead = nullptr;
 	cudaEvent_t lateFrameDone[2] = { nullptr, nullptr };
 	bool latePending = false;
 	// the path tracer's paired launches (any-hit next to closest-hit) have a side stream of their own: the tail stream still
 	// carries the previous frame's tail when the next path tracer starts
 	cudaStream_t ptSide = nullptr;
 	cudaEvent_t ptFork = nullptr, ptJoin = nullptr;
+	uint32_t* hostReuseCounters = nullptr;     // pinned: the list sizes of the last spatial pass, copied back asynchronously
 	uint32_t lastWfSet = 0;                    // the wavefront set of the last path-tracing pass (rpt_wavefront_counters)
 	struct Peer {
 		bool connected = false, ipc = false;
@@ -251,6 +253,8 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
 	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
 	ctx->noShadeFromTask = getenv("RPT_NO_SHADE_FROM_TASK") != nullptr;   // A/B switch (profiles/r2_21_*)
+	ctx->noReplayWavefront = getenv("RPT_NO_REPLAY_WAVEFRONT") != nullptr;   // A/B switch (profiles/r2_24_*)
+	if (const char* m = getenv("RPT_RW_MIN_LIST")) ctx->rwMinList = uint32_t(strtoul(m, nullptr, 10));
 	if (const char* pm = getenv("RPT_PRIORITY_MODE")) ctx->priorityMode = atoi(pm);
 	*out = ctx;
 	return RPT_OK;
@@ -549,7 +553,9 @@ static std::vector<WavefrontSlot> wavefrontSlots(RptFrame* f) {
 		                    { (void**)&w.counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t) }, { (void**)&w.tailMark, f->pixels() * 4 }, { (void**)&w.tailList, px * 4 } });
 	}
 	v.insert(v.end(), { { (void**)&f->ru.task, px * 3 * ShiftTaskWords * 16 }, { (void**)&f->ru.rays, px * 3 * 32 }, { (void**)&f->ru.occluded, px * 3 }, { (void**)&f->ru.shadeList, px * 3 * 4 },
-	                    { (void**)&f->ru.redoList, px * 4 }, { (void**)&f->ru.counters, 16 * sizeof(uint32_t) } });
+	                    { (void**)&f->ru.redoList, px * 4 }, { (void**)&f->ru.counters, 16 * sizeof(uint32_t) },
+	                    { (void**)&f->ru.rwRays[0], px * 32 }, { (void**)&f->ru.rwRays[1], px * 32 }, { (void**)&f->ru.rwState[0], px * 32 }, { (void**)&f->ru.rwState[1], px * 32 },
+	                    { (void**)&f->ru.rwHits, px * 16 }, { (void**)&f->ru.rwRc, px * 48 }, { (void**)&f->ru.rwList, px * 4 }, { (void**)&f->ru.rwCounters, 64 * sizeof(uint32_t) } });
 	return v;
 }
 
@@ -591,6 +597,8 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaMalloc peer flags"); }
 	if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&f->hostError), sizeof(uint32_t), cudaHostAllocMapped);
 	if (e == cudaSuccess) { *f->hostError = 0u; e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&f->hostErrorDev), f->hostError, 0); }
+	if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&f->hostReuseCounters), 16 * sizeof(uint32_t), cudaHostAllocDefault);
+	if (e == cudaSuccess) std::memset(f->hostReuseCounters, 0, 16 * sizeof(uint32_t));
 	if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "cudaHostAlloc peer error word"); }
 	e = cudaMalloc(&f->work, WorkCounterCount * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(f->work, 0, WorkCounterCount * sizeof(uint32_t));
@@ -615,8 +623,9 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 		{
 			e = cudaStreamCreateWithPriority(&f->lateStream, cudaStreamNonBlocking, prLate);
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, prLate);
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide2, cudaStreamNonBlocking, prLate);
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->ptSide, cudaStreamNonBlocking, prPtSide);
-			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
+			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateSide2Done, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
 				if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "late stream"); }
 		}
@@ -651,12 +660,14 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (!f) return;
 	cudaSetDevice(f->ctx->device);
 	if (f->tailStream) cudaStreamSynchronize(f->tailStream);
+	if (f->lateSide2) cudaStreamSynchronize(f->lateSide2);
 	if (f->lateSide) cudaStreamSynchronize(f->lateSide);
 	if (f->lateStream) cudaStreamSynchronize(f->lateStream);
 	if (f->ptSide) cudaStreamSynchronize(f->ptSide);
 	if (f->stream) cudaStreamSynchronize(f->stream);
-	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone, f->lateHead, f->lateFrameDone[0], f->lateFrameDone[1], f->ptFork, f->ptJoin }) if (ev) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone, f->lateSide2Done, f->lateHead, f->lateFrameDone[0], f->lateFrameDone[1], f->ptFork, f->ptJoin }) if (ev) cudaEventDestroy(ev);
 	if (f->ptSide) cudaStreamDestroy(f->ptSide);
+	if (f->lateSide2) cudaStreamDestroy(f->lateSide2);
 	if (f->lateSide) cudaStreamDestroy(f->lateSide);
 	if (f->lateStream) cudaStreamDestroy(f->lateStream);
 	if (f->tailFork) cudaEventDestroy(f->tailFork);
@@ -667,6 +678,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->gatherImageOwned) cudaFree(f->gatherImageOwned);
 	if (f->gatherFlagsOwned) cudaFree(f->gatherFlagsOwned);
 	if (f->hostError) cudaFreeHost(f->hostError);
+	if (f->hostReuseCounters) cudaFreeHost(f->hostReuseCounters);
 	if (f->copyStream) { cudaStreamSynchronize(f->copyStream); cudaStreamDestroy(f->copyStream); }
 	for (int i = 0; i < 2; i++) { if (f->postDone[i]) cudaEventDestroy(f->postDone[i]); if (f->copyDone[i]) cudaEventDestroy(f->copyDone[i]); }
 	if (f->rgba8Alt) cudaFree(f->rgba8Alt);
@@ -719,6 +731,7 @@ static FrameView makeView(RptFrame* f) {
 	v.wf = f->wf();
 	v.ru = f->ru;
 	v.ru.noShadeFromTask = f->ctx->noShadeFromTask ? 1u : 0u;
+	v.ru.noReplayWavefront = f->ctx->noReplayWavefront ? 1u : 0u;
 	v.striped = f->rowBegin != 0 || f->rowEnd != f->height;
 	v.peerGrisUp = f->up.connected ? f->up.grisTemp : nullptr;
 	v.peerDiUp = f->up.connected ? f->up.diTemp : nullptr;
@@ -972,8 +985,15 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
 		FrameKernelClock clock(f);
 		const bool side = !f->ctx->spatialOneStream;   // A/B switch
-		launchGRISSpatial(makeView(f), sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
-		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone);
+		FrameView view = makeView(f);
+		// The replays of this pass as a wavefront or as in-line chains?  The wavefront pays a fixed latency per bounce (its longest
+		// ray), the in-line list kernel a time that grows with the list: the size of the last pass's list decides (read back
+		// asynchronously — a frame or two stale, never waited for; both forms produce the same bits).
+		const volatile uint32_t* hc = f->hostReuseCounters;
+		if (hc[3] + hc[5] < f->ctx->rwMinList) view.ru.noReplayWavefront = 1u;
+		launchGRISSpatial(view, sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
+		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone, side ? f->lateSide2 : nullptr, f->lateSide2Done);
+		CU(f->ctx, cudaMemcpyAsync(f->hostReuseCounters, f->ru.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
 	}
 	peerAfter(f, HookGrisSpatial);
 	PASS_EPILOGUE("rpt_gris_spatial")
@@ -1391,6 +1411,14 @@ RPT_API int rpt_wavefront_counters(RptFrame* f, uint32_t* out64) {
 	joinLate(f);
 	CU(f->ctx, syncFrame(f));
 	CU(f->ctx, cudaMemcpy(out64, f->wfSet[f->lastWfSet].counters, size_t(WavefrontMaxBounces) * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return RPT_OK;
+}
+
+RPT_API int rpt_reuse_counters(RptFrame* f, uint32_t* out16) {
+	if (!f || !out16) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_reuse_counters: NULL argument");
+	CU(f->ctx, cudaSetDevice(f->ctx->device));
+	CU(f->ctx, syncFrame(f));
+	std::memcpy(out16, f->hostReuseCounters, 16 * sizeof(uint32_t));
 	return RPT_OK;
 }
 

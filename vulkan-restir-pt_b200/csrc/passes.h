@@ -25,8 +25,10 @@ void launchGRISPathTraceTail(const FrameView& f, const SceneView& s, const RptGR
 void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, int tailMode = 0, KernelClock* clock = nullptr,
                         cudaStream_t side = nullptr, cudaEvent_t fork = nullptr);
 // side / fork / join: a second stream and two events for the kernel that runs next to the main sequence (all NULL: one stream)
+// (side2 / join2: a third stream for the replay wavefront, so that it runs next to the in-line replay list as well)
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock = nullptr,
-                       cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
+                       cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr,
+                       cudaStream_t side2 = nullptr, cudaEvent_t join2 = nullptr);
 void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
 
 // wavefront traversal (trace_queue.cu): rays[2i] = {o, tmin}, rays[2i+1] = {d, tmax}; the ray count is read from

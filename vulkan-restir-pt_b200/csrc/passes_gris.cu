@@ -90,7 +90,44 @@ struct RcData {   // GRISReconnectionData (layouts.glsl:158-164), only ever a lo
 };
 
 // gris_retrace.glsl:42-136: replay the BSDF chain from the destination's primary hit with the source path's
-// random numbers, consuming them in lock-step with tracePath, up to the vertex before the reconnection vertex
+// random numbers, consuming them in lock-step with tracePath, up to the vertex before the reconnection vertex.
+// replayVertex is one iteration of that loop from the point where the vertex's surface is known (:62-135); it is shared by the
+// in-line form (traceReplayPath: one thread walks the whole prefix) and the wavefront form (rwStepKernel: one kernel per bounce
+// around the queue traversal kernel).  Returns ReplayContinue (ray / wo / throughput / rng advanced to the next vertex),
+// ReplayFound (rc filled: this is the vertex before the reconnection vertex) or ReplayFailed (rc untouched).
+constexpr int ReplayContinue = 0, ReplayFound = 1, ReplayFailed = 2;
+RT_DEV int replayVertex(const RptGRISSettings& st, int bounce, uint32_t targetId, const Surface& surf, const Mat& mat, uint32_t curInst, uint32_t curTri,
+                        float2 curBary, float3& throughput, float3& wo, uint32_t& rng, Ray& ray, RcData& rc) {
+	const bool isThisVertexConnectible = isBSDFConnectible(mat);
+	sample1f(rng);
+	if (surf.isLight) return ReplayFailed;
+	if (uint32_t(bounce) == targetId - 1u) {
+		if (!isThisVertexConnectible) return ReplayFailed;
+		rc.prevInstance = curInst; rc.prevTriangle = curTri; rc.prevBary = curBary;
+		rc.rcPrevWo = wo; rc.rcPrevThroughput = throughput;
+		return ReplayFound;
+	}
+	sample4f(rng);
+	sample1f(rng);
+	if (bounce > 4) {
+		const float pdfTerminate = max_(1.0f - luminance(throughput) * st.rrScale, 0.0f);
+		if (sample1f(rng) < pdfTerminate) return ReplayFailed;
+		throughput /= (1.0f - pdfTerminate);
+	}
+	const float3 r3 = sample3f(rng);
+	BSDFSample bs = emptyBSDFSample();
+	if (!sampleBSDF(mat, surf.albedo, surf.norm, wo, r3, bs) || bs.pdf < 1e-6f) return ReplayFailed;
+	const float cosTheta = isSampleTypeDelta(bs.type) ? 1.0f : absDot(surf.norm, bs.wi);
+	throughput *= bs.bsdf * cosTheta / bs.pdf;
+	wo = -bs.wi;
+	ray.dir = bs.wi;
+	ray.ori = surf.pos + ray.dir * 1e-4f;
+	return ReplayContinue;
+}
+RT_DEV void resetRcData(RcData& rc) {
+	rc.prevInstance = InvalidHitIndex; rc.prevTriangle = 0; rc.prevBary = make_float2(0.f, 0.f);
+	rc.rcPrevWo = f3(0.0f); rc.rcPrevThroughput = f3(0.0f);
+}
 // CanTrace = false: only the rcVertexId == 1 case (no ray needed) is compiled in
 template <bool CanTrace = true>
 RT_DEV void traceReplayPath(const SceneView& s, const RptGRISSettings& st, const Surface& primarySurf, float2 primaryUv, Ray ray,
@@ -99,9 +136,7 @@ RT_DEV void traceReplayPath(const SceneView& s, const RptGRISSettings& st, const
 	float3 wo = -ray.dir;
 	Surface surf = primarySurf;
 	Mat mat = loadMaterial(s, surf.matIndex);
-	BSDFSample bs = emptyBSDFSample();
-	rc.prevInstance = InvalidHitIndex; rc.prevTriangle = 0; rc.prevBary = make_float2(0.f, 0.f);
-	rc.rcPrevWo = f3(0.0f); rc.rcPrevThroughput = f3(0.0f);
+	resetRcData(rc);
 	uint32_t curInst = SpecialHitIndex, curTri = 0;
 	float2 curBary = primaryUv;
 	const uint32_t targetId = flagsRcVertexId(targetFlags);
@@ -119,30 +154,7 @@ RT_DEV void traceReplayPath(const SceneView& s, const RptGRISSettings& st, const
 			loadSurfaceInfo(s, h, surf);
 			mat = loadMaterial(s, surf.matIndex);
 		}
-		const bool isThisVertexConnectible = isBSDFConnectible(mat);
-		sample1f(rng);
-		if (surf.isLight) break;
-		if (uint32_t(bounce) == targetId - 1u) {
-			if (isThisVertexConnectible) {
-				rc.prevInstance = curInst; rc.prevTriangle = curTri; rc.prevBary = curBary;
-				rc.rcPrevWo = wo; rc.rcPrevThroughput = throughput;
-			}
-			break;
-		}
-		sample4f(rng);
-		sample1f(rng);
-		if (bounce > 4) {
-			const float pdfTerminate = max_(1.0f - luminance(throughput) * st.rrScale, 0.0f);
-			if (sample1f(rng) < pdfTerminate) break;
-			throughput /= (1.0f - pdfTerminate);
-		}
-		const float3 r3 = sample3f(rng);
-		if (!sampleBSDF(mat, surf.albedo, surf.norm, wo, r3, bs) || bs.pdf < 1e-6f) break;
-		const float cosTheta = isSampleTypeDelta(bs.type) ? 1.0f : absDot(surf.norm, bs.wi);
-		throughput *= bs.bsdf * cosTheta / bs.pdf;
-		wo = -bs.wi;
-		ray.dir = bs.wi;
-		ray.ori = surf.pos + ray.dir * 1e-4f;
+		if (replayVertex(st, bounce, targetId, surf, mat, curInst, curTri, curBary, throughput, wo, rng, ray, rc) != ReplayContinue) break;
 	}
 }
 
@@ -175,13 +187,9 @@ struct ShiftTask {
 	float3 rcPrevWo, rcPrevThroughput;
 };
 
-template <bool CanTrace = true>
-RT_DEV void shiftPrepare(const SceneView& s, const RptGRISSettings& st, const Surface& dstPrimarySurf, float2 dstUv, const Ray& primaryRay,
-                         const GRISResv& src, ShiftTask& t) {
+// the part of shiftPrepare after the replay (:156-184): reconnection geometry and validity tests from the replay's result
+RT_DEV void shiftPrepareFromRc(const SceneView& s, const Surface& dstPrimarySurf, const GRISResv& src, const RcData& rc, ShiftTask& t) {
 	t.status = TaskInvalid;
-	if (!src.sampleValid()) return;
-	RcData rc;
-	traceReplayPath<CanTrace>(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
 	if (rc.prevInstance == InvalidHitIndex) return;
 	if (rc.prevInstance == SpecialHitIndex) t.rcPrevSurf = dstPrimarySurf;
 	else loadSurfaceInfo(s, rc.prevInstance, rc.prevTriangle, rc.prevBary, t.rcPrevSurf);
@@ -194,6 +202,15 @@ RT_DEV void shiftPrepare(const SceneView& s, const RptGRISSettings& st, const Su
 	const float dstJacobian = abs_(cosTheta) / square(dist);
 	const float jacobian = dstJacobian / src.q3.w;
 	if (dist > GRISDistanceThreshold && cosTheta > 0 && !isnan_(jacobian) && src.q3.w > 0 && isBSDFConnectible(rcPrevMat)) t.status = TaskRay;
+}
+template <bool CanTrace = true>
+RT_DEV void shiftPrepare(const SceneView& s, const RptGRISSettings& st, const Surface& dstPrimarySurf, float2 dstUv, const Ray& primaryRay,
+                         const GRISResv& src, ShiftTask& t) {
+	t.status = TaskInvalid;
+	if (!src.sampleValid()) return;
+	RcData rc;
+	traceReplayPath<CanTrace>(s, st, dstPrimarySurf, dstUv, primaryRay, src.flags(), src.primaryRng(), rc);
+	shiftPrepareFromRc(s, dstPrimarySurf, src, rc, t);
 }
 
 // the visibility ray of traceVisibility(rcPrevSurf.pos, rcSurf.pos), ray_query.glsl:27-38
@@ -945,6 +962,106 @@ __global__ void __launch_bounds__(PassBlockX* PassBlockY, 8) grisTemporalListKer
 	}
 }
 
+// -------- replay wavefront ---------------------------------------------------------------------------------------------
+// A sample that reconnects beyond the first bounce (paths through glass, mirrors) can only be shifted to another pixel after
+// its prefix has been replayed FROM that pixel (gris_retrace.glsl:42-136): up to 14 dependent closest-hit rays with a surface
+// fetch and a BSDF sample between them.  One thread per replay with in-line traversal (the list kernels below) runs at 6-7 of 32
+// lanes and a quarter of the GPU's warps, and where such samples are dense — the rows of VeachAjar's door, one strip of a
+// multi-GPU film — those kernels ARE the pass (profiles/r2_23_*: 4.5 of the 5.8 ms of the spatial pass of the strip that holds
+// the door).  So the replays are a wavefront of their own, shaped like the path tracer's: rwBegin*Kernel takes the first vertex
+// (the pixel's primary hit, no ray), then per bounce one launch of the queue traversal kernel and one rwStepKernel (surface
+// fetch + replayVertex, next ray into the next round's queue), and rwFinish*Kernel does what follows the replay in the shader
+// (reconnection geometry, validity tests, visibility ray).  replayVertex is the same function the in-line form calls, in the same
+// order on the same operands: the same bits.  Reconnection vertices 2..RwRounds+1 take this way (all but a handful per frame); the
+// rest, and whatever exceeds the list's capacity, stay with the in-line list kernels.
+constexpr int RwRounds = 6;
+static_assert(RwRounds * 4 + 8 <= 64, "rwCounters holds [round][4] words");
+
+RT_DEV void rwStoreRc(const ReuseView& ru, uint32_t k, const RcData& rc) {
+	ru.rwRc[k] = make_float4(__uint_as_float(rc.prevInstance), __uint_as_float(rc.prevTriangle), rc.prevBary.x, rc.prevBary.y);
+	ru.rwRc[size_t(ru.capacity) + k] = make_float4(rc.rcPrevWo.x, rc.rcPrevWo.y, rc.rcPrevWo.z, rc.rcPrevThroughput.x);
+	ru.rwRc[2 * size_t(ru.capacity) + k] = make_float4(rc.rcPrevThroughput.y, rc.rcPrevThroughput.z, 0.f, 0.f);
+}
+RT_DEV RcData rwLoadRc(const ReuseView& ru, uint32_t k) {
+	const float4 a = ru.rwRc[k], b = ru.rwRc[size_t(ru.capacity) + k], c = ru.rwRc[2 * size_t(ru.capacity) + k];
+	RcData rc;
+	rc.prevInstance = __float_as_uint(a.x); rc.prevTriangle = __float_as_uint(a.y); rc.prevBary = make_float2(a.z, a.w);
+	rc.rcPrevWo = make_float3(b.x, b.y, b.z); rc.rcPrevThroughput = make_float3(b.w, c.x, c.y);
+	return rc;
+}
+// the replay of list position k goes on to `round`: its ray into that round's queue
+RT_DEV void rwEnqueue(const ReuseView& ru, int round, uint32_t k, uint32_t targetId, const Ray& ray, float3 throughput, uint32_t rng) {
+	const uint32_t slot = queueAppend(ru.rwCounters + 4 * round);
+	float4* rq = ru.rwRays[round & 1] + 2 * size_t(slot);
+	rq[0] = make_float4(ray.ori.x, ray.ori.y, ray.ori.z, MinRayDistance);
+	rq[1] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, MaxRayDistance);
+	float4* sq = ru.rwState[round & 1] + 2 * size_t(slot);
+	sq[0] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng));
+	sq[1] = make_float4(__uint_as_float(k), __uint_as_float(targetId), 0.f, 0.f);
+}
+// first vertex of a replay (the destination pixel's primary hit: no ray)
+RT_DEV void rwBegin(const FrameView& f, const SceneView& s, const RptGRISSettings& st, uint32_t k, uint32_t o, uint32_t targetFlags, uint32_t rng) {
+	const Primary p = loadPrimary(f, o % f.width, f.rowBegin + o / f.width);
+	const Surface surf = primarySurface(p);
+	const Mat mat = loadMaterial(s, surf.matIndex);
+	float3 throughput = f3(1.0f), wo = -p.ray.dir;
+	Ray ray = p.ray;
+	RcData rc;
+	resetRcData(rc);
+	const uint32_t targetId = flagsRcVertexId(targetFlags);
+	if (replayVertex(st, 0, targetId, surf, mat, SpecialHitIndex, 0u, p.uv, throughput, wo, rng, ray, rc) == ReplayContinue) rwEnqueue(f.ru, 1, k, targetId, ray, throughput, rng);
+	else rwStoreRc(f.ru, k, rc);   // (ended at its first vertex: invalid)
+}
+__global__ void __launch_bounds__(ShadeBlock, RT_REUSE_MINBLOCKS) rwStepKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st, int round) {
+	const uint32_t n = f.ru.rwCounters[4 * round];
+	for (uint32_t slot = blockIdx.x * ShadeBlock + threadIdx.x; slot < n; slot += gridDim.x * ShadeBlock) {
+		const float4 a = f.ru.rwState[round & 1][2 * size_t(slot)], b = f.ru.rwState[round & 1][2 * size_t(slot) + 1];
+		const uint32_t k = __float_as_uint(b.x), targetId = __float_as_uint(b.y);
+		const RptIntersection hit = f.ru.rwHits[slot];
+		RcData rc;
+		resetRcData(rc);
+		if (hit.instanceIdx != InvalidHitIndex) {
+			float3 throughput = f3(a);
+			uint32_t rng = __float_as_uint(a.w);
+			Ray ray;
+			ray.ori = f3(0.0f);
+			ray.dir = f3(f.ru.rwRays[round & 1][2 * size_t(slot) + 1]);
+			float3 wo = -ray.dir;
+			Surface surf;
+			loadSurfaceInfo(s, hit, surf);
+			const Mat mat = loadMaterial(s, surf.matIndex);
+			const int res = replayVertex(st, round, targetId, surf, mat, hit.instanceIdx, hit.triangleIdx, make_float2(hit.bary[0], hit.bary[1]), throughput, wo, rng, ray, rc);
+			if (res == ReplayContinue && round < RwRounds) { rwEnqueue(f.ru, round + 1, k, targetId, ray, throughput, rng); continue; }
+			if (res != ReplayFound) resetRcData(rc);
+		}
+		rwStoreRc(f.ru, k, rc);
+	}
+}
+// spatial pass: (pixel, neighbour) pairs of the wavefront replay list
+__global__ void __launch_bounds__(ShadeBlock, RT_REUSE_MINBLOCKS) rwBeginShiftKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = min(f.ru.counters[5], f.ru.capacity);
+	for (uint32_t k = blockIdx.x * ShadeBlock + threadIdx.x; k < n; k += gridDim.x * ShadeBlock) {
+		const uint32_t e = f.ru.rwList[k], o = e % f.ru.capacity;
+		const uint32_t srcPixel = __float_as_uint(f.ru.task[2 * size_t(f.ru.capacity) * 3 + size_t(e)].w) & 0x3fffffffu;
+		const float4* q = reinterpret_cast<const float4*>(f.grisTemp + srcPixel);
+		rwBegin(f, s, st, k, o, __float_as_uint(q[2].w), __float_as_uint(q[4].w));
+	}
+}
+__global__ void __launch_bounds__(ShadeBlock, RT_REUSE_MINBLOCKS) rwFinishShiftKernel(const __grid_constant__ FrameView f, const __grid_constant__ SceneView s, const RptGRISSettings st) {
+	const uint32_t n = min(f.ru.counters[5], f.ru.capacity);
+	for (uint32_t k = blockIdx.x * ShadeBlock + threadIdx.x; k < n; k += gridDim.x * ShadeBlock) {
+		const uint32_t e = f.ru.rwList[k], i = e / f.ru.capacity, o = e % f.ru.capacity;
+		const uint32_t srcPixel = __float_as_uint(f.ru.task[2 * size_t(f.ru.capacity) * 3 + size_t(e)].w) & 0x3fffffffu;
+		const GRISResv nr = loadGRIS(f.grisTemp + srcPixel);
+		const Primary p = loadPrimary(f, o % f.width, f.rowBegin + o / f.width);
+		ShiftTask t;
+		t.status = TaskInvalid;
+		if (nr.sampleValid()) shiftPrepareFromRc(s, primarySurface(p), nr, rwLoadRc(f.ru, k), t);
+		storeShiftTask(f.ru, i, o, t, srcPixel);
+		storeVisibilityRay(f.ru, i, o, &t);
+	}
+}
+
 // -------- spatial -------------------------------------------------------------------------------------------------------
 RT_DEV bool spatialCandidate(const FrameView& f, const Primary& p, uint32_t& rng, Neighbor& nb) {   // gris_resample_spatial.glsl:62-84
 	const float texelX = 1.0f / float(f.width), texelY = 1.0f / float(f.height);
@@ -1047,7 +1164,13 @@ __global__ void __launch_bounds__(ReuseBlock) grisSpatialPickKernel(const __grid
 				// a source sample that reconnects beyond the first bounce needs replay rays: grisSpatialShiftListKernel
 				const bool replay = __float_as_uint(q[0].z) != InvalidHitIndex && flagsRcVertexId(__float_as_uint(q[2].w)) != 1u;
 				packed = uint32_t(nb.pixel) | ((replay ? TaskReplay : TaskPending) << 30);
-				if (replay) f.ru.shadeList[atomicAdd(f.ru.counters + 3, 1u)] = i * f.ru.capacity + o;
+				if (replay) {
+					const uint32_t id = flagsRcVertexId(__float_as_uint(q[2].w));
+					uint32_t place = 0xffffffffu;
+					if (!f.ru.noReplayWavefront && id <= uint32_t(RwRounds) + 1u) place = atomicAdd(f.ru.counters + 5, 1u);
+					if (place < f.ru.capacity) f.ru.rwList[place] = i * f.ru.capacity + o;                 // replay wavefront
+					else f.ru.shadeList[atomicAdd(f.ru.counters + 3, 1u)] = i * f.ru.capacity + o;       // in-line list kernel
+				}
 				sample1f(rng);   // the merge's random number, assumed drawn (verified in the merge kernel)
 			}
 		}
@@ -1219,7 +1342,7 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 	if (side == nullptr || fork == nullptr) grisTemporalListKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock,
-                       cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+                       cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, cudaStream_t side2, cudaEvent_t join2) {
 	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
 	const bool twoStreams = side != nullptr && fork != nullptr && join != nullptr;
 	// next to the dense kernel the list kernel gets a part of every SM (blocks of 128 threads x 128 registers: a quarter of
@@ -1235,14 +1358,31 @@ void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSett
 	const int shiftListBlocks = twoStreams ? shiftListPart : shiftListFull;
 	const uint32_t n = f.ru.capacity, blocks = (n + ReuseBlock - 1) / ReuseBlock;
 	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	cudaMemsetAsync(f.ru.rwCounters, 0, 64 * sizeof(uint32_t), st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
 	grisSpatialPickKernel<<<blocks, ReuseBlock, 0, st>>>(f, p);
-	// the replay list (latency-bound: a few long dependent chains) next to the dense shift kernel
+	// the replays (wavefront rounds, then the few long ones as in-line chains) next to the dense shift kernel
 	if (twoStreams) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
+	// (with a third stream the wavefront rounds and the few long in-line chains run next to each other as well)
+	const bool threeStreams = twoStreams && side2 != nullptr && join2 != nullptr;
+	if (threeStreams) cudaStreamWaitEvent(side2, fork, 0);
+	cudaStream_t rs = threeStreams ? side2 : (twoStreams ? side : st);
+	if (!f.ru.noReplayWavefront) {
+		static const int rwBlocks = persistentBlocks(reinterpret_cast<const void*>(rwStepKernel), ShadeBlock);
+		rwBeginShiftKernel<<<rwBlocks, ShadeBlock, 0, rs>>>(f, s, p);
+		for (int round = 1; round <= RwRounds; round++) {
+			uint32_t* c = f.ru.rwCounters + 4 * round;
+			launchTraceQueueClosest(s, f.ru.rwRays[round & 1], c + 0, 0, c + 2, f.ru.rwHits, rs);
+			rwStepKernel<<<rwBlocks, ShadeBlock, 0, rs>>>(f, s, p, round);
+		}
+		rwFinishShiftKernel<<<rwBlocks, ShadeBlock, 0, rs>>>(f, s, p);
+	}
+	if (threeStreams) cudaEventRecord(join2, side2);
 	grisSpatialShiftListKernel<<<shiftListBlocks, ReuseBlock, 0, twoStreams ? side : st>>>(f, s, p);
 	if (twoStreams) cudaEventRecord(join, side);
 	grisSpatialShiftKernel<<<dim3(blocks, 3), ReuseBlock, 0, st>>>(f, s, p);
 	if (twoStreams) cudaStreamWaitEvent(st, join, 0);
+	if (threeStreams) cudaStreamWaitEvent(st, join2, 0);
 	if (clock) clock->tick(RPT_KERNEL_TRACE_ANY);
 	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);

@@ -109,8 +109,17 @@ struct ReuseView {
 	uint32_t* shadeList;              // pixels whose final shading needs a replay ray (rare) ...  (3 * capacity entries: the spatial
 	                                  // pass first uses it for the (pixel, neighbour) pairs whose shift needs replay rays, counter [3])
 	uint32_t* redoList;               // ... and pixels whose speculated random-number sequence did not hold (very rare)
-	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head, [3] spatial shift replay list size
+	uint32_t* counters;               // [0] shade list size, [1] redo list size, [2] ray queue head, [3] spatial shift replay list size (in-line kernel),
+	                                  // [4] temporal replay list size, [5] wavefront replay list size
+	// wavefront replay (passes_gris.cu, "replay wavefront"): the path prefixes the reuse passes have to replay, one queue per bounce
+	float4* rwRays[2];                // [round & 1]: {o, tmin}, {d, tmax} per slot
+	float4* rwState[2];               // [round & 1]: {throughput, rng}, {entry, reconnection vertex id, -, -} per slot
+	RptIntersection* rwHits;          // closest hit of each slot of the current round
+	float4* rwRc;                     // result per list position: 3 float4 planes of `capacity` (the reference's GRISReconnectionData)
+	uint32_t* rwList;                 // the replays of this pass: (candidate * capacity + pixel) entries, at most `capacity`
+	uint32_t* rwCounters;             // [round][4]: queue size, -, traversal head, -
 	uint32_t capacity;                // owned pixels
+	uint32_t noReplayWavefront;       // A/B switch (RPT_NO_REPLAY_WAVEFRONT): every replay in the in-line list kernels
 	uint32_t noShadeFromTask;         // A/B switch (RPT_NO_SHADE_FROM_TASK): the spatial pass replays every selected sample for its final shading
 };
 

@@ -227,6 +227,7 @@ DEVICE_API = {
     "rpt_trace_shadow": (C.c_int, [P, P, P, C.c_uint32, P]),
     "rpt_trace_bench": (C.c_int, [P, P, P, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), P, P]),
     "rpt_wavefront_counters": (C.c_int, [P, C.POINTER(C.c_uint32)]),
+    "rpt_reuse_counters": (C.c_int, [P, C.POINTER(C.c_uint32)]),
     "rpt_membench": (C.c_int, [P, C.c_size_t, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rpt_counters_enable": (C.c_int, [P, C.c_int]),
     "rpt_counters_reset": (C.c_int, [P]),
