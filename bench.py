@@ -352,6 +352,10 @@ class Arm:
         e1.record(stream)
         self.barrier(frame)
         dev_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        # (the clocks are sampled during the region above only: every nvidia-smi query holds a driver lock for a few milliseconds, which
+        # the device-resident region does not feel — the host runs frames ahead — but the end-to-end regions below, where the host
+        # waits for an image every frame, lost 5-10 % in one run out of two to it, profiles/r2_25_*)
+        clock_info = clocks.stop() if clocks else None
         # the per-pass / per-kernel breakdown comes from a second run of the same frames with the library's event timing on (about
         # 40 timing events per frame, which cost a little and are therefore kept out of the region above)
         # and ONE FRAME AT A TIME (rpt_frame_join after every frame: the next frame's G-buffer and path tracer then wait for this frame's
@@ -368,14 +372,14 @@ class Arm:
         # ---- timed region 2: end to end through the host Renderer with the RGBA8 strip read back every frame -----------
         # Every frame: camera upload (2 x 352 B, H2D) and the tone-mapped RGBA8 strip read back to pinned host memory (D2H).
         # The read-back is pipelined (Renderer::drawFrameAsync): frame i's copy runs on a copy stream while frame i+1 renders;
-        # the host collects frame i-1's image before it issues frame i+1, and the LAST image before the region ends.
+        # the host collects frame i-3's image before it issues frame i (whose image goes to the same host buffer), and the LAST images before the region ends.
         strip_bytes = fw * rows * 4
-        pinned = [torch.empty(strip_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        pinned = [torch.empty(strip_bytes, dtype=torch.uint8).pin_memory() for _ in range(3)]
         ticket = C.c_uint64()
 
         def draw_async(i):
             frame_no[0] += 1
-            if host.rh_renderer_draw_frame_async(r, restirpt.hash2(frame_no[0]), P(pinned[i & 1].data_ptr()), C.byref(ticket)) != 0:
+            if host.rh_renderer_draw_frame_async(r, restirpt.hash2(frame_no[0]), P(pinned[i % 3].data_ptr()), C.byref(ticket)) != 0:
                 raise SystemExit("draw_frame_async failed: " + host.rh_last_error().decode())
             return ticket.value
 
@@ -383,15 +387,16 @@ class Arm:
             if host.rh_renderer_wait_readback(r, t) != 0:
                 raise SystemExit("wait_readback failed: " + host.rh_last_error().decode())
 
+        collect(draw_async(0))     # untimed: the first pipelined read-back creates the copy stream and the device images
         self.barrier(frame)
         e0.record(stream)
-        prev = None
+        tickets = []
         for i in range(steps):
-            t = draw_async(i)
-            if prev is not None:
-                collect(prev)
-            prev = t
-        collect(prev)          # the last image is in host memory before the end event is recorded
+            if i >= 3:
+                collect(tickets[i - 3])      # (frame i is about to reuse that image's host buffer; the host stays two frames ahead of the
+            tickets.append(draw_async(i))    #  image it waits for: the reuse passes of frame i-1 run behind the path tracer of frame i)
+        for t in tickets[-3:]:
+            collect(t)         # the last images are in host memory before the end event is recorded
         e1.record(stream)
         self.barrier(frame)
         e2e_ms = self.max_over_ranks(e0.elapsed_time(e1))
@@ -404,7 +409,6 @@ class Arm:
         e1.record(stream)
         self.barrier(frame)
         e2e_blocking_ms = self.max_over_ranks(e0.elapsed_time(e1))
-        clock_info = clocks.stop() if clocks else None
         return {"r": r, "frame": frame, "link": link, "bounds": bounds, "rows": rows, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "e2e_blocking_ms": e2e_blocking_ms,
                 "stats": stats, "strip_bytes": strip_bytes, "clocks": clock_info, "balance_log": balance_log, "film": (fw, fh)}
 
@@ -695,8 +699,8 @@ def run_cuda(args):
             "e2e": {"value": 1000.0 * args.steps / e2e_ms * equiv, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * 352, "d2h_bytes_per_step": strip_bytes,
                     "how": "host Renderer, camera upload + RGBA8 strip read back to pinned host memory every frame; the read-back is "
-                           "pipelined (copy stream, two device images): frame i's image is collected while frame i+1 renders, the "
-                           "last one inside the timed region",
+                           "pipelined (copy stream, three device images, three host buffers): frame i-3's image is collected before frame i is "
+                           "issued, the last ones inside the timed region",
                     "blocking_readback_value": 1000.0 * args.steps / m["e2e_blocking_ms"] * equiv},
             "gpu_launches": launches,
             "roofline": roofline,

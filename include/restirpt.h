@@ -324,7 +324,8 @@ int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out);
 /* The same pass with a pipelined read-back (new; the reference presents from the GPU and only reads back for a screenshot,
  * src/Renderer.cpp:758-793): returns at once with a ticket; the image travels to rgba8Out (pinned host memory, for the copy to
  * be asynchronous) on a copy stream while the next frame renders.  rpt_readback_wait(ticket) blocks until rgba8Out is complete.
- * Two read-backs may be in flight; use a different rgba8Out for consecutive tickets. */
+ * Three read-backs may be in flight (the host should stay two frames ahead of the image it waits for: the reuse passes of a frame
+ * run behind the next frame's path tracer); rotate through three rgba8Out buffers. */
 int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out, uint64_t* ticket);
 int rpt_readback_wait(RptFrame* f, uint64_t ticket);
 

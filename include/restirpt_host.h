@@ -69,7 +69,7 @@ void rh_renderer_set_halo_exchange(RhRenderer* r, RhHaloExchangeFn fn, void* use
 int rh_renderer_update_instances(RhRenderer* r, const RhScene* s);
 int rh_renderer_draw_frame(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out);   /* 0 ok, -1 error */
 /* the same frame with a pipelined read-back (rpt_postprocess_async): returns when the frame is enqueued; rgba8Out (pinned host
- * memory; alternate between two buffers) is complete after rh_renderer_wait_readback(ticket) */
+ * memory; rotate through three buffers) is complete after rh_renderer_wait_readback(ticket) */
 int rh_renderer_draw_frame_async(RhRenderer* r, uint32_t seed, uint8_t* rgba8Out, uint64_t* ticket);
 int rh_renderer_wait_readback(RhRenderer* r, uint64_t ticket);
 /* One frame on all strips of a film that live in this process (connected with rpt_frame_connect_peers): stage by stage —

@@ -262,7 +262,7 @@ def test_overlapped_frames_equal_serial_frames(bench_scene, monkeypatch):
 
 
 def test_pipelined_readback_delivers_the_blocking_calls_images(built):
-    """Renderer::drawFrameAsync (rpt_postprocess_async: two device images, a copy stream, tickets) against Renderer::drawFrame
+    """Renderer::drawFrameAsync (rpt_postprocess_async: three device images, a copy stream, tickets) against Renderer::drawFrame
     (rpt_postprocess with a host pointer) on the same seeds: the same RGBA8 image for every frame, also when the host collects
     a frame's image only after the next frame has been issued, and when blocking and pipelined calls are mixed"""
     import ctypes as C

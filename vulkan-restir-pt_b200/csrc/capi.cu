@@ -65,10 +65,11 @@ struct RptFrame {
 	RptIntersection* primaryIsec = nullptr;
 	uchar4* rgba8 = nullptr;
 	// pipelined read-back (rpt_postprocess_async): a second device image, a copy stream, one event pair per image
-	uchar4* rgba8Alt = nullptr;
+	static constexpr int ReadbackDepth = 3;    // images in flight: with the reuse passes one frame behind the path tracer the host
+	uchar4* rgba8Ring[ReadbackDepth - 1] = {}; // has to run two frames ahead of the image it waits for (profiles/r2_25_*); ring = f->rgba8 + these
 	cudaStream_t copyStream = nullptr;
-	cudaEvent_t postDone[2] = { nullptr, nullptr }, copyDone[2] = { nullptr, nullptr };
-	uint64_t asyncTicket = 0;                  // read-backs issued so far; ticket t used image / events [t & 1]
+	cudaEvent_t postDone[ReadbackDepth] = {}, copyDone[ReadbackDepth] = {};
+	uint64_t asyncTicket = 0;                  // read-backs issued so far; ticket t used image / events [t % ReadbackDepth]
 	RptCamera camera{}, prevCamera{};
 	size_t pixels() const { return size_t(width) * (storeEnd - storeBegin); }
 
@@ -680,8 +681,8 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->hostError) cudaFreeHost(f->hostError);
 	if (f->hostReuseCounters) cudaFreeHost(f->hostReuseCounters);
 	if (f->copyStream) { cudaStreamSynchronize(f->copyStream); cudaStreamDestroy(f->copyStream); }
-	for (int i = 0; i < 2; i++) { if (f->postDone[i]) cudaEventDestroy(f->postDone[i]); if (f->copyDone[i]) cudaEventDestroy(f->copyDone[i]); }
-	if (f->rgba8Alt) cudaFree(f->rgba8Alt);
+	for (int i = 0; i < RptFrame::ReadbackDepth; i++) { if (f->postDone[i]) cudaEventDestroy(f->postDone[i]); if (f->copyDone[i]) cudaEventDestroy(f->copyDone[i]); }
+	for (uchar4* img : f->rgba8Ring) if (img) cudaFree(img);
 	for (const FrameSlot& sl : frameSlots(f)) if (*sl.ptr) cudaFree(*sl.ptr);
 	if (f->flags) cudaFree(f->flags);
 	if (f->work) cudaFree(f->work);
@@ -1018,7 +1019,7 @@ RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgb
 	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
 	if (f->latePending && !rgba8Out) late.l = new LateScope(f);
 	else joinLate(f);
-	if (f->asyncTicket) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[(f->asyncTicket - 1) & 1], 0));   // (f->rgba8 may still be being read back)
+	if (f->asyncTicket) for (cudaEvent_t ev : f->copyDone) CU(f->ctx, cudaStreamWaitEvent(f->stream, ev, 0));   // (f->rgba8 may still be being read back)
 	const int rc = postprocessInto(f, st, f->rgba8);
 	if (rc != RPT_OK) return rc;
 	if (rgba8Out) {
@@ -1030,27 +1031,27 @@ RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgb
 
 // The same pass with the read-back taken off the frame's stream: the image goes to one of two device buffers, a copy stream
 // carries it to (pinned) host memory while the frame's stream is already rendering the next frame, and the caller collects it
-// with rpt_readback_wait(ticket).  At most two read-backs are in flight: issuing ticket t waits (on the device) for the copy of
-// ticket t - 2, which used the same device image — the caller must have collected that one, or not care about it.
+// with rpt_readback_wait(ticket).  At most three read-backs are in flight: issuing ticket t waits (on the device) for the copy of
+// ticket t - 3, which used the same device image — the caller must have collected that one, or not care about it.
 RPT_API int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_t* rgba8Out, uint64_t* ticket) {
 	if (!f || !st || !rgba8Out || !ticket) return fail(f ? f->ctx : nullptr, RPT_ERR_INVALID, "rpt_postprocess_async: NULL argument");
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
 	const size_t bytes = size_t(f->width) * (f->rowEnd - f->rowBegin) * 4;
 	if (!f->copyStream) {
 		CU(f->ctx, cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; i++) {
+		for (int i = 0; i < RptFrame::ReadbackDepth; i++) {
 			CU(f->ctx, cudaEventCreateWithFlags(&f->postDone[i], cudaEventDisableTiming));
 			CU(f->ctx, cudaEventCreateWithFlags(&f->copyDone[i], cudaEventDisableTiming));
 		}
-		CU(f->ctx, cudaMalloc(reinterpret_cast<void**>(&f->rgba8Alt), std::max<size_t>(bytes, 4)));
+		for (uchar4*& img : f->rgba8Ring) CU(f->ctx, cudaMalloc(reinterpret_cast<void**>(&img), std::max<size_t>(bytes, 4)));
 	}
 	const uint64_t t = f->asyncTicket;
-	const int slot = int(t & 1);
-	uchar4* image = slot ? f->rgba8Alt : f->rgba8;
+	const int slot = int(t % RptFrame::ReadbackDepth);
+	uchar4* image = slot ? f->rgba8Ring[slot - 1] : f->rgba8;
 	// after a late spatial pass the post-process follows it there (it reads what that pass accumulated); otherwise the frame's stream
 	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
 	if (f->latePending) late.l = new LateScope(f);
-	if (t >= 2) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[slot], 0));
+	if (t >= uint64_t(RptFrame::ReadbackDepth)) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[slot], 0));
 	const int rc = postprocessInto(f, st, image);
 	if (rc != RPT_OK) return rc;
 	CU(f->ctx, cudaEventRecord(f->postDone[slot], f->stream));
@@ -1065,9 +1066,10 @@ RPT_API int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_
 RPT_API int rpt_readback_wait(RptFrame* f, uint64_t ticket) {
 	if (!f) return fail(nullptr, RPT_ERR_INVALID, "rpt_readback_wait: NULL frame");
 	if (ticket >= f->asyncTicket) return fail(f->ctx, RPT_ERR_INVALID, "rpt_readback_wait: no such read-back");
-	if (ticket + 2 < f->asyncTicket) return RPT_OK;   // its device image has been reused since: that copy completed long ago
+	// (if its device image has been handed to a later read-back since, the event below stands for that later copy: waiting for it
+	// covers this one, the copies of one image being ordered on the copy stream)
 	CU(f->ctx, cudaSetDevice(f->ctx->device));
-	CU(f->ctx, cudaEventSynchronize(f->copyDone[ticket & 1]));
+	CU(f->ctx, cudaEventSynchronize(f->copyDone[ticket % RptFrame::ReadbackDepth]));
 	return RPT_OK;
 }
 
