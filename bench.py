@@ -71,7 +71,7 @@ class ClockSampler:
         self.lines = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -595,7 +595,10 @@ def run_cuda(args):
                                        "launches_per_frame": first["launches_per_frame"] + 2 * pair["launches_per_frame"]}, **kernels}
         # (the spatial pass's pick / shift / shift-list kernels share the reuse_gen span and its merge / shade-list / redo-list
         # kernels the reuse_merge span: + 4 launches per frame)
-        launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 4) * steps)
+        # (+ the temporal pass's replay-list kernel and the tail's temporal step: 2; + the path tracer's tail as wavefront rounds on
+        # frames of 1.5 M pixels and more: bounces 7..15 = 26 launches instead of the one counted above)
+        wavefront_tail = fw * (m["rows"]) >= 1500000
+        launches = int((sum(v["launches_per_frame"] for v in kernels.values()) + 4 + 2 + (25 if wavefront_tail else 0)) * steps)
         timed = {k: v for k, v in kernels.items() if k != "gris_tail"}
         dom = max(timed, key=lambda k: timed[k]["ms_per_frame"])
         tail = kernels.pop("gris_tail", None)

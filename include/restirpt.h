@@ -182,6 +182,10 @@ typedef struct RptSceneDesc {
  * unique mesh, and rpt_scene_update_instances only rebuilds the TLAS. */
 typedef enum RptSceneFlags { RPT_SCENE_TWO_LEVEL = 1 } RptSceneFlags;
 
+/* "current frame" / THIS = what this frame's passes have written since the last rpt_frame_flip; PREV = what the previous frame
+ * left.  THIS is only defined once the frame's own pass has written it (the reference's ping-pong pair would show the frame
+ * before last there; the G-buffer, motion and GRIS buffers of this library rotate through three slots).  The one place the
+ * pipeline itself depends on such old content — background pixels of gris_path_trace keep their reservoir — is reproduced. */
 typedef enum RptBufferId {
 	RPT_BUF_DIRECT_OUTPUT = 0,    /* float4 / px   (layouts.glsl:180)      */
 	RPT_BUF_INDIRECT_OUTPUT = 1,  /* float4 / px   (layouts.glsl:181)      */

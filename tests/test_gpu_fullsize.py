@@ -84,9 +84,9 @@ def test_full_hd_film_strips_and_reservoir_invariants(bench_scene):
 
 
 def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
-    """The paths alive after bounce 6 run through nine more wavefront rounds on the tail stream; RPT_INLINE_TAIL=1 finishes them
-    in one kernel with in-line traversal instead (grisTailKernel, the default before the reuse passes moved one frame behind
-    the path tracer).  Same stage functions, so the reservoirs must agree bit for bit — at full size, where the tail holds tens
+    """The paths alive after bounce 6 run through nine more wavefront rounds on the tail stream (RPT_WAVEFRONT_TAIL=1; the default
+    for frames of 1.5 M pixels and more) or are finished by one kernel with in-line traversal (grisTailKernel, RPT_INLINE_TAIL=1;
+    the default for smaller frames, where the rounds' latency is on the critical path).  Same stage functions, so the reservoirs must agree bit for bit — at full size, where the tail holds tens
     of thousands of paths."""
     w, h = 960, 540
     gs = GRISSettings(2, 1.0, 1, 1, 20)
@@ -94,8 +94,10 @@ def test_inline_tail_kernel_equals_wavefront_tail(bench_scene, monkeypatch):
     for mode in ("inline", "wavefront"):
         if mode == "inline":
             monkeypatch.setenv("RPT_INLINE_TAIL", "1")
+            monkeypatch.delenv("RPT_WAVEFRONT_TAIL", raising=False)
         else:
             monkeypatch.delenv("RPT_INLINE_TAIL", raising=False)
+            monkeypatch.setenv("RPT_WAVEFRONT_TAIL", "1")     # (by default the form follows the frame's size)
         dev = restirpt.Device(0)      # (the switches are read when the context is created)
         b = Backend("cuda", bench_scene, w, h, dev)
         drv = FrameDriver(bench_scene.camera(w, h))

@@ -24,7 +24,8 @@ struct RptCtx {
 	unsigned long long* counters = nullptr;
 	bool countersOn = false;
 	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
-	bool traceOneStream = false, wavefrontTail = false, spatialOneStream = false, noFrameOverlap = false;
+	bool traceOneStream = false, spatialOneStream = false, noFrameOverlap = false;
+	int tailForm = 0;   // 0: by the frame's size, 1: in-line tail kernel, 2: wavefront rounds
 	bool noShadeFromTask = false, noReplayWavefront = false;
 	uint32_t rwMinList = 80000;    // replay pairs per spatial pass from which the replay wavefront is used (profiles/r2_24_*)
 	int priorityMode = 0;   // stream priorities (profiles/r2_20_*): 0 = late set, tail and path-tracer side stream above the frame's stream; 1 = all equal; 2 = frame's stream + its side stream above the late set
@@ -99,6 +100,7 @@ struct RptFrame {
 	cudaStream_t ptSide = nullptr;
 	cudaEvent_t ptFork = nullptr, ptJoin = nullptr;
 	uint32_t* hostReuseCounters = nullptr;     // pinned: the list sizes of the last spatial pass, copied back asynchronously
+	bool wavefrontTail = true;                 // the path tracer's tail as wavefront rounds (see rpt_ctx_create)
 	uint32_t lastWfSet = 0;                    // the wavefront set of the last path-tracing pass (rpt_wavefront_counters)
 	struct Peer {
 		bool connected = false, ipc = false;
@@ -247,10 +249,13 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	CU(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
 	CU(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
 	ctx->traceOneStream = getenv("RPT_TRACE_ONE_STREAM") != nullptr;
-	// the path tracer's tail (bounces >= WavefrontTailStart, on the tail stream) as further wavefront rounds — the default since the
-	// reuse passes run one frame behind the path tracer and the tail's latency is off the frame's critical path: what counts then is
-	// instructions, and the in-line tail kernel (RPT_INLINE_TAIL=1) spends four times as many at 3.5 lanes (profiles/r2_21_*)
-	ctx->wavefrontTail = getenv("RPT_INLINE_TAIL") == nullptr;
+	// The path tracer's tail (bounces >= WavefrontTailStart, on the tail stream): further wavefront rounds, or one kernel that runs
+	// every surviving path to its end with in-line traversal.  The rounds spend a quarter of the instructions (the in-line kernel
+	// runs at 3.5 lanes) but take 1.7 ms end to end against 1.1 ms.  Since the reuse passes run one frame behind the path tracer
+	// the tail's latency only matters where the reuse passes are the longer chain: small strips of a multi-GPU film (4K / 8:
+	// in-line 5.13 ms per strip, rounds 5.30 ms); on a 1080p film the rounds win (8.81 against 8.89 ms; profiles/r2_21_*, r2_26_*).
+	// Chosen per frame by its pixel count; RPT_INLINE_TAIL=1 / RPT_WAVEFRONT_TAIL=1 force one form (A/B, tests).
+	ctx->tailForm = getenv("RPT_INLINE_TAIL") ? 1 : (getenv("RPT_WAVEFRONT_TAIL") ? 2 : 0);
 	ctx->spatialOneStream = getenv("RPT_SPATIAL_ONE_STREAM") != nullptr;
 	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
 	ctx->noShadeFromTask = getenv("RPT_NO_SHADE_FROM_TASK") != nullptr;   // A/B switch (profiles/r2_21_*)
@@ -583,6 +588,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 	f->storeBegin = rowBegin > halo ? rowBegin - halo : 0;
 	f->storeEnd = std::min(fullHeight, rowEnd + halo);
 	f->halo = halo;
+	f->wavefrontTail = ctx->tailForm == 2 || (ctx->tailForm == 0 && size_t(fullWidth) * (rowEnd - rowBegin) >= 1500000u);
 	int prLo = 0, prHi = 0;
 	cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
 	const int pm = ctx->priorityMode;
@@ -888,7 +894,7 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	if (f->timing) { t0 = takeEvent(f); t1 = takeEvent(f); cudaEventRecord(t0, f->tailStream); }
-	if (f->ctx->wavefrontTail) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
+	if (f->wavefrontTail) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
 	else launchGRISPathTraceTail(view, scene, *st, f->tailStream);
 	if (f->timing) { cudaEventRecord(t1, f->tailStream); f->pending.push_back({ RPT_PASS_COUNT + RPT_KERNEL_GRIS_TAIL, t0, t1, true }); }
 	CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
