@@ -26,7 +26,7 @@ struct RptCtx {
 	// A/B switches of the measurements in profiles/, read from the environment ONCE at context creation (never in a pass)
 	bool traceOneStream = false, spatialOneStream = false, noFrameOverlap = false;
 	int tailForm = 0;   // 0: by the frame's size, 1: in-line tail kernel, 2: wavefront rounds
-	bool noShadeFromTask = false, noReplayWavefront = false;
+	bool noShadeFromTask = false, noReplayWavefront = false, noShadeApart = false;
 	uint32_t rwMinList = 80000;    // replay pairs per spatial pass from which the replay wavefront is used (profiles/r2_24_*)
 	int priorityMode = 0;   // stream priorities (profiles/r2_20_*): 0 = late set, tail and path-tracer side stream above the frame's stream; 1 = all equal; 2 = frame's stream + its side stream above the late set
 };
@@ -95,6 +95,10 @@ struct RptFrame {
 	cudaEvent_t lateFork = nullptr, lateDone = nullptr, lateSideFork = nullptr, lateSideDone = nullptr, lateSide2Done = nullptr, lateHead = nullptr;
 	cudaEvent_t lateFrameDone[2] = { nullptr, nullptr };
 	bool latePending = false;
+	// the spatial pass's shade list and the post-process behind it run on the late set's third stream, next to the NEXT frame's
+	// temporal pass (they gate nothing but the image); the next spatial pass and every join wait for shadeDone
+	cudaEvent_t shadeFork = nullptr, shadeDone = nullptr;
+	bool shadePending = false;
 	// the path tracer's paired launches (any-hit next to closest-hit) have a side stream of their own: the tail stream still
 	// carries the previous frame's tail when the next path tracer starts
 	cudaStream_t ptSide = nullptr;
@@ -141,6 +145,7 @@ static void joinTail(RptFrame* f) {
 // G-buffer and path-tracing passes touches the frame
 static void joinLate(RptFrame* f) {
 	if (f->latePending) { cudaStreamWaitEvent(f->stream, f->lateDone, 0); f->latePending = false; }
+	if (f->shadePending) { cudaStreamWaitEvent(f->stream, f->shadeDone, 0); f->shadePending = false; }
 }
 static cudaError_t syncFrame(RptFrame* f) {
 	joinTail(f);
@@ -163,6 +168,20 @@ struct LateScope {
 		cudaEventRecord(f->lateFrameDone[f->flips & 1u], f->stream);
 		f->stream = s0; f->tailStream = t0; f->tailFork = a0; f->tailDone = b0;
 		f->latePending = true;
+	}
+};
+// the post-process after a spatial pass whose shade list runs on the third stream follows it THERE (inside a LateScope)
+struct ShadeScope {
+	RptFrame* f; bool on; cudaStream_t s0 = nullptr;
+	ShadeScope(RptFrame* f_, bool inLateScope) : f(f_), on(inLateScope && f_->shadePending) {
+		if (!on) return;
+		s0 = f->stream;
+		f->stream = f->lateSide2;
+	}
+	~ShadeScope() {
+		if (!on) return;
+		cudaEventRecord(f->shadeDone, f->stream);
+		f->stream = s0;
 	}
 };
 static bool pipelined(const RptFrame* f) { return f->lateStream != nullptr && !f->ctx->noFrameOverlap; }
@@ -260,6 +279,7 @@ RPT_API int rpt_ctx_create(int cudaDevice, RptCtx** out) {
 	ctx->noFrameOverlap = getenv("RPT_NO_FRAME_OVERLAP") != nullptr;   // A/B switch (profiles/r2_16_*)
 	ctx->noShadeFromTask = getenv("RPT_NO_SHADE_FROM_TASK") != nullptr;   // A/B switch (profiles/r2_21_*)
 	ctx->noReplayWavefront = getenv("RPT_NO_REPLAY_WAVEFRONT") != nullptr;   // A/B switch (profiles/r2_24_*)
+	ctx->noShadeApart = getenv("RPT_NO_SHADE_APART") != nullptr;             // A/B switch (profiles/r2_28_*)
 	if (const char* m = getenv("RPT_RW_MIN_LIST")) ctx->rwMinList = uint32_t(strtoul(m, nullptr, 10));
 	if (const char* pm = getenv("RPT_PRIORITY_MODE")) ctx->priorityMode = atoi(pm);
 	*out = ctx;
@@ -632,7 +652,7 @@ RPT_API int rpt_frame_create(RptCtx* ctx, uint32_t fullWidth, uint32_t fullHeigh
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide, cudaStreamNonBlocking, prLate);
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->lateSide2, cudaStreamNonBlocking, prLate);
 			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&f->ptSide, cudaStreamNonBlocking, prPtSide);
-			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateSide2Done, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
+			for (cudaEvent_t* ev : { &f->lateFork, &f->lateDone, &f->lateSideFork, &f->lateSideDone, &f->lateSide2Done, &f->shadeFork, &f->shadeDone, &f->lateHead, &f->lateFrameDone[0], &f->lateFrameDone[1], &f->ptFork, &f->ptJoin })
 				if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 			if (e != cudaSuccess) { rpt_frame_destroy(f); return cudaFail(ctx, e, "late stream"); }
 		}
@@ -672,7 +692,7 @@ RPT_API void rpt_frame_destroy(RptFrame* f) {
 	if (f->lateStream) cudaStreamSynchronize(f->lateStream);
 	if (f->ptSide) cudaStreamSynchronize(f->ptSide);
 	if (f->stream) cudaStreamSynchronize(f->stream);
-	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone, f->lateSide2Done, f->lateHead, f->lateFrameDone[0], f->lateFrameDone[1], f->ptFork, f->ptJoin }) if (ev) cudaEventDestroy(ev);
+	for (cudaEvent_t ev : { f->lateFork, f->lateDone, f->lateSideFork, f->lateSideDone, f->lateSide2Done, f->shadeFork, f->shadeDone, f->lateHead, f->lateFrameDone[0], f->lateFrameDone[1], f->ptFork, f->ptJoin }) if (ev) cudaEventDestroy(ev);
 	if (f->ptSide) cudaStreamDestroy(f->ptSide);
 	if (f->lateSide2) cudaStreamDestroy(f->lateSide2);
 	if (f->lateSide) cudaStreamDestroy(f->lateSide);
@@ -987,6 +1007,9 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 	cudaEvent_t mainTailDone = f->tailDone;
 	LateScope late(f);
 	if (late.on && tailOnMainSet) { CU(f->ctx, cudaStreamWaitEvent(f->stream, mainTailDone, 0)); f->tailPending = false; }
+	// (the previous frame's shade list and post-process read the lists and write the outputs this pass is about to overwrite)
+	if (late.on && f->shadePending) { CU(f->ctx, cudaStreamWaitEvent(f->stream, f->shadeDone, 0)); f->shadePending = false; }
+	const bool shadeApart = late.on && !f->ctx->spatialOneStream && !f->ctx->noShadeApart;
 	peerBefore(f, HookGrisSpatial);
 	{
 		PassTimer timer(f, RPT_PASS_GRIS_SPATIAL);
@@ -999,7 +1022,9 @@ RPT_API int rpt_gris_spatial(RptFrame* f, const RptScene* s, const RptGRISSettin
 		const volatile uint32_t* hc = f->hostReuseCounters;
 		if (hc[3] + hc[5] < f->ctx->rwMinList) view.ru.noReplayWavefront = 1u;
 		launchGRISSpatial(view, sceneView(s), *st, f->stream, f->timing ? &clock : nullptr,
-		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone, side ? f->lateSide2 : nullptr, f->lateSide2Done);
+		                  side ? f->tailStream : nullptr, f->tailFork, f->tailDone, side ? f->lateSide2 : nullptr, f->lateSide2Done,
+		                  shadeApart ? f->lateSide2 : nullptr, f->shadeFork, f->shadeDone);
+		if (shadeApart) f->shadePending = true;
 		CU(f->ctx, cudaMemcpyAsync(f->hostReuseCounters, f->ru.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
 	}
 	peerAfter(f, HookGrisSpatial);
@@ -1025,6 +1050,7 @@ RPT_API int rpt_postprocess(RptFrame* f, const RptPostSettings* st, uint8_t* rgb
 	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
 	if (f->latePending && !rgba8Out) late.l = new LateScope(f);
 	else joinLate(f);
+	ShadeScope shade(f, late.l != nullptr && late.l->on);
 	if (f->asyncTicket) for (cudaEvent_t ev : f->copyDone) CU(f->ctx, cudaStreamWaitEvent(f->stream, ev, 0));   // (f->rgba8 may still be being read back)
 	const int rc = postprocessInto(f, st, f->rgba8);
 	if (rc != RPT_OK) return rc;
@@ -1057,6 +1083,7 @@ RPT_API int rpt_postprocess_async(RptFrame* f, const RptPostSettings* st, uint8_
 	// after a late spatial pass the post-process follows it there (it reads what that pass accumulated); otherwise the frame's stream
 	struct MaybeLate { LateScope* l = nullptr; ~MaybeLate() { delete l; } } late;
 	if (f->latePending) late.l = new LateScope(f);
+	ShadeScope shade(f, late.l != nullptr && late.l->on);
 	if (t >= uint64_t(RptFrame::ReadbackDepth)) CU(f->ctx, cudaStreamWaitEvent(f->stream, f->copyDone[slot], 0));
 	const int rc = postprocessInto(f, st, image);
 	if (rc != RPT_OK) return rc;

@@ -28,7 +28,8 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 // (side2 / join2: a third stream for the replay wavefront, so that it runs next to the in-line replay list as well)
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock = nullptr,
                        cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr,
-                       cudaStream_t side2 = nullptr, cudaEvent_t join2 = nullptr);
+                       cudaStream_t side2 = nullptr, cudaEvent_t join2 = nullptr,
+                       cudaStream_t shadeStream = nullptr, cudaEvent_t shadeFork = nullptr, cudaEvent_t shadeDone = nullptr);
 void launchTraceRays(const SceneView& s, const float4* rays, uint32_t n, RptIntersection* out, uint8_t* occluded, cudaStream_t st);
 
 // wavefront traversal (trace_queue.cu): rays[2i] = {o, tmin}, rays[2i+1] = {d, tmax}; the ray count is read from

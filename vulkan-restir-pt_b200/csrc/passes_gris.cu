@@ -1325,7 +1325,7 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 		return;
 	}
 	const uint32_t n = f.ru.capacity, dense = (n + ReuseBlock - 1) / ReuseBlock;
-	cudaMemsetAsync(f.ru.counters, 0, 16 * sizeof(uint32_t), st);
+	cudaMemsetAsync(f.ru.counters + 2, 0, 3 * sizeof(uint32_t), st);   // ([0], [1]: the previous frame's shade list may still be running)
 	if (clock) clock->tick(RPT_KERNEL_REUSE_GEN);
 	grisTemporalGenKernel<<<dense, ReuseBlock, 0, st>>>(f, s, p, tailMode);
 	// the deferred pixels (replay chains) on the second stream, next to the visibility rays and the merge of all others; the
@@ -1342,7 +1342,8 @@ void launchGRISTemporal(const FrameView& f, const SceneView& s, const RptGRISSet
 	if (side == nullptr || fork == nullptr) grisTemporalListKernel<<<blocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 }
 void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSettings& p, cudaStream_t st, KernelClock* clock,
-                       cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, cudaStream_t side2, cudaEvent_t join2) {
+                       cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, cudaStream_t side2, cudaEvent_t join2,
+                       cudaStream_t shadeStream, cudaEvent_t shadeFork, cudaEvent_t shadeDone) {
 	static const int listBlocks = persistentBlocks(reinterpret_cast<const void*>(grisSpatialRedoKernel), PassBlockX * PassBlockY);
 	const bool twoStreams = side != nullptr && fork != nullptr && join != nullptr;
 	// next to the dense kernel the list kernel gets a part of every SM (blocks of 128 threads x 128 registers: a quarter of
@@ -1387,8 +1388,17 @@ void launchGRISSpatial(const FrameView& f, const SceneView& s, const RptGRISSett
 	launchTraceQueueAny(s, f.ru.rays, nullptr, 3 * n, f.ru.counters + 2, f.ru.occluded, st);
 	if (clock) clock->tick(RPT_KERNEL_REUSE_MERGE);
 	grisSpatialMergeKernel<<<blocks, ReuseBlock, 0, st>>>(f, s, p);
-	grisSpatialShadeListKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 	grisSpatialRedoKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
+	// The shade list — the selected samples whose final shading needs replay rays: a latency chain — gates nothing but the image:
+	// the reservoirs are complete after the merge.  With a stream to itself it runs next to whatever follows the pass on `st` (the
+	// next frame's temporal pass); the caller orders the post-process and the next spatial pass behind `shadeDone`.
+	if (shadeStream != nullptr && shadeFork != nullptr && shadeDone != nullptr) {
+		cudaEventRecord(shadeFork, st);
+		cudaStreamWaitEvent(shadeStream, shadeFork, 0);
+		grisSpatialShadeListKernel<<<listBlocks, PassBlockX * PassBlockY, 0, shadeStream>>>(f, s, p);
+		cudaEventRecord(shadeDone, shadeStream);
+	}
+	else grisSpatialShadeListKernel<<<listBlocks, PassBlockX * PassBlockY, 0, st>>>(f, s, p);
 }
 
 } // namespace rt
