@@ -432,3 +432,26 @@ def test_per_instance_motion_vectors(device, two_level):
     still = gpu.read("MOTION")
     assert bitwise_mismatch(still, cpu.read("MOTION")) == 0 and np.abs(still).max() < 1e-3
     gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "room"])
+def test_restir_pt_bit_exact_with_the_wavefront_forms_forced(built, monkeypatch, scene_name):
+    """The library picks the form of two latency chains by size — the path tracer's tail (in-line kernel below 1.5 M pixels,
+    wavefront rounds above) and the spatial pass's replays (in-line list kernel for short lists, replay wavefront from 80 k pairs) —
+    so on the small parity films the wavefront forms would never run.  Here they are forced (RPT_WAVEFRONT_TAIL=1,
+    RPT_RW_MIN_LIST=0; the switches are read when the context is created) and held to the same bar: every buffer of every pass
+    equals the oracle bit for bit over four frames with a dolly."""
+    import ctypes as C
+    monkeypatch.setenv("RPT_WAVEFRONT_TAIL", "1")
+    monkeypatch.setenv("RPT_RW_MIN_LIST", "0")
+    dev = restirpt.Device(0)
+    sc = SCENES[scene_name]()
+    gpu, cpu = Backend("cuda", sc, 96, 54, dev), Backend("oracle", sc, 96, 54)
+    try:
+        _compare_method((scene_name, sc, gpu, cpu), "gris", 4, moves=DOLLY, gris=GRISSettings(2, 1.0, 1, 1, 20))
+        rc = (C.c_uint32 * 16)()
+        gpu.lib.rpt_reuse_counters(gpu.frame, rc)
+        assert rc[3] + rc[5] == 0 or rc[5] > 0, "replays took the in-line list although the wavefront was forced"
+    finally:
+        gpu.close(); cpu.close()
+        dev.close()
