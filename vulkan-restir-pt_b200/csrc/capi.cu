@@ -894,7 +894,8 @@ SETTINGS_PASS(rpt_di_temporal, RptDISettings, RPT_PASS_DI_TEMPORAL, launchDITemp
 SETTINGS_PASS(rpt_di_spatial, RptDISettings, RPT_PASS_DI_SPATIAL, launchDISpatial, HookDiSpatial)
 
 // GRISReSTIR::render step 1.  Bounces 0..WavefrontTailStart-1 (all but a few percent of the rays) run on the frame's
-// stream; the long tail of the few paths that live on is enqueued on the tail stream and joined by the next pass.
+// stream, with a side stream of their own for the paired any-hit launches; the long tail of the few paths that live on is
+// enqueued on the tail stream and joined by the temporal pass (its pixels' temporal step follows it there).
 RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSettings* st) {
 	PASS_PROLOGUE_EARLY("rpt_gris_pathtrace")   // (reads the new G-buffer, writes the reservoirs the previous frame read as history)
 	if (!st) return fail(f->ctx, RPT_ERR_INVALID, "rpt_gris_pathtrace: NULL settings");
@@ -914,7 +915,7 @@ RPT_API int rpt_gris_pathtrace(RptFrame* f, const RptScene* s, const RptGRISSett
 	CU(f->ctx, cudaStreamWaitEvent(f->tailStream, f->tailFork, 0));
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	if (f->timing) { t0 = takeEvent(f); t1 = takeEvent(f); cudaEventRecord(t0, f->tailStream); }
-	if (f->wavefrontTail) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // A/B: the tail as a wavefront
+	if (f->wavefrontTail) launchGRISPathTraceBounces(view, scene, *st, WavefrontTailStart, 15, f->tailStream);   // (form by frame size: rpt_ctx_create)
 	else launchGRISPathTraceTail(view, scene, *st, f->tailStream);
 	if (f->timing) { cudaEventRecord(t1, f->tailStream); f->pending.push_back({ RPT_PASS_COUNT + RPT_KERNEL_GRIS_TAIL, t0, t1, true }); }
 	CU(f->ctx, cudaEventRecord(f->tailDone, f->tailStream));
