@@ -235,3 +235,111 @@ def test_film_layout_and_partition():
         parts = partition(h, n)
         assert parts[0][0] == 0 and parts[-1][1] == h and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     assert storage_rows(0, 270, 2160, 21) == (0, 291) and storage_rows(270, 540, 2160, 21) == (249, 561)
+
+
+def _tri_soup(sc, with_normals=True):
+    """world-independent triangle soup of a scene's object geometry: sorted (positions[, normals]) of every triangle corner"""
+    d = sc.desc
+    verts = np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (d.numVertices, 8))
+    idx = np.ctypeslib.as_array(C.cast(d.indices, C.POINTER(C.c_uint32)), (d.numIndices,))
+    tris = verts[idx].reshape(-1, 3, 8)
+    cols = [0, 1, 2, 4, 5, 6] if with_normals else [0, 1, 2]
+    rows = [tuple(np.round(t[:, cols].reshape(-1), 5)) for t in tris]
+    # a triangle may start at any of its corners: rotate so that the smallest corner comes first (winding kept)
+    out = []
+    for t in tris:
+        c = [tuple(np.round(t[k, cols], 5)) for k in range(3)]
+        k = min(range(3), key=lambda j: c[j])
+        out.append(c[k] + c[(k + 1) % 3] + c[(k + 2) % 3])
+    return sorted(out), len(rows)
+
+
+def test_ply_and_stl_models_equal_the_obj_model(tmp_path, built):
+    """The reference hands every <modelInstance path> to assimp (src/Resource.cpp:100-181).  Besides OBJ the host library reads
+    PLY (ascii, binary little / big endian, polygons, optional normals and texture coordinates) and STL (binary, ascii): the same
+    cube through each must give the same triangles as through the OBJ reader — positions and winding always, normals where the
+    file carries them — and generated smooth normals where it does not (aiProcess_GenSmoothNormals)."""
+    import struct
+    P = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    quads = [((0, 3, 2, 1), (0, 0, -1)), ((4, 5, 6, 7), (0, 0, 1)), ((0, 1, 5, 4), (0, -1, 0)),
+             ((2, 3, 7, 6), (0, 1, 0)), ((1, 2, 6, 5), (1, 0, 0)), ((0, 4, 7, 3), (-1, 0, 0))]
+    m = tmp_path / "m"
+    m.mkdir()
+    # OBJ with per-face normals (what the other files with normals must reproduce)
+    obj = "".join(f"v {x} {y} {z}\n" for x, y, z in P) + "".join(f"vn {x} {y} {z}\n" for _, (x, y, z) in quads)
+    obj += "".join("f " + " ".join(f"{v + 1}//{k + 1}" for v in q) + "\n" for k, (q, _) in enumerate(quads))
+    (m / "cube.obj").write_text(obj)
+    # PLY with normals needs one vertex per (position, normal): 24 vertices
+    pv, pf = [], []
+    for q, n in quads:
+        base = len(pv)
+        pv += [P[v] + n + (0.25 * i, 0.5) for i, v in enumerate(q)]
+        pf.append([base, base + 1, base + 2, base + 3])
+    hdr = ("ply\nformat {fmt} 1.0\ncomment made by the test\nelement vertex 24\nproperty float x\nproperty float y\nproperty float z\n"
+           "property float nx\nproperty float ny\nproperty float nz\nproperty float s\nproperty float t\n"
+           "element face 6\nproperty list uchar int vertex_indices\nend_header\n")
+    (m / "cube_ascii.ply").write_text(hdr.format(fmt="ascii") + "".join(" ".join(str(c) for c in v) + "\n" for v in pv)
+                                      + "".join("4 " + " ".join(map(str, f)) + "\n" for f in pf))
+    for name, e in (("cube_le.ply", "<"), ("cube_be.ply", ">")):
+        body = b"".join(struct.pack(e + "8f", *v) for v in pv) + b"".join(struct.pack(e + "B4i", 4, *f) for f in pf)
+        (m / name).write_bytes(hdr.format(fmt="binary_little_endian" if e == "<" else "binary_big_endian").encode() + body)
+    # PLY without normals, shared vertices, double coordinates, an extra per-vertex property and an extra element
+    (m / "cube_shared.ply").write_text(
+        "ply\nformat ascii 1.0\nelement vertex 8\nproperty double x\nproperty double y\nproperty double z\nproperty uchar red\n"
+        "element face 6\nproperty list uchar uint vertex_index\nelement edge 1\nproperty int a\nproperty int b\nend_header\n"
+        + "".join(f"{x} {y} {z} 200\n" for x, y, z in P) + "".join("4 " + " ".join(map(str, q)) + "\n" for q, _ in quads) + "0 1\n")
+    # STL: triangles with facet normals
+    tris = []
+    for q, n in quads:
+        tris += [(n, (P[q[0]], P[q[1]], P[q[2]])), (n, (P[q[0]], P[q[2]], P[q[3]]))]
+    (m / "cube_bin.stl").write_bytes(b"solid made by the test".ljust(80, b" ") + struct.pack("<I", len(tris))
+                                     + b"".join(struct.pack("<12fH", *n, *t[0], *t[1], *t[2], 0) for n, t in tris))
+    (m / "cube_ascii.stl").write_text("solid cube\n" + "".join(
+        f"facet normal {n[0]} {n[1]} {n[2]}\n outer loop\n" + "".join(f"  vertex {v[0]} {v[1]} {v[2]}\n" for v in t) + " endloop\nendfacet\n"
+        for n, t in tris) + "endsolid cube\n")
+    (m / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 0 1 3\nvn 0 0 -1\nf 1//1 3//1 2//1\n")
+
+    def scene(model, kind="object"):
+        xml = tmp_path / (model.replace(".", "_") + ".xml")
+        xml.write_text(f"""<?xml version="1.0"?><scene name="t"><integrator type="path"><size width="32" height="32" /></integrator>
+<camera type="thinLens"><position value="0.5 -3 0.5" /><lookAt value="0.5 0 0.5" /><fov value="40" /></camera><modelInstances>
+ <modelInstance path="m/light.obj" name="l" type="light"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" /><radiance value="5 5 5" /></modelInstance>
+ <modelInstance path="m/{model}" name="a" type="{kind}"><transform translate="0 0 0" scale="1 1 1" rotate="0 0 0" />{'<radiance value="1 1 1" />' if kind == 'light' else ''}</modelInstance>
+</modelInstances></scene>""")
+        return restirpt.HostScene.xml(str(xml))
+
+    want, n = _tri_soup(scene("cube.obj"))
+    assert n == 12
+    for model in ("cube_ascii.ply", "cube_le.ply", "cube_be.ply", "cube_bin.stl", "cube_ascii.stl"):
+        got, k = _tri_soup(scene(model))
+        assert k == 12 and got == want, model
+    # texture coordinates of the PLY: s kept, t flipped (aiProcess_FlipUVs)
+    d = scene("cube_le.ply").desc
+    verts = np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (d.numVertices, 8))
+    assert np.allclose(sorted(set(np.round(verts[:, 3], 5))), [0, 0.25, 0.5, 0.75]) and np.allclose(verts[:, 7], 0.5)
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), (d.numMaterials, 8))
+    assert np.allclose(mats[1, :3], 0.6)      # assimp's default material
+    # shared vertices without normals: same positions / winding, smooth normals = normalised sum of the three faces at a corner
+    want_pos, _ = _tri_soup(scene("cube.obj"), with_normals=False)
+    sc = scene("cube_shared.ply")
+    got_pos, k = _tri_soup(sc, with_normals=False)
+    assert k == 12 and got_pos == want_pos
+    d = sc.desc
+    verts = np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (d.numVertices, 8))
+    assert d.numVertices == 8
+    for v in verts:
+        outward = (v[0:3] * 2 - 1) / np.sqrt(3.0)
+        assert np.allclose(v[4:7], outward, atol=1e-5)
+    # as a light without normals: flat normals (aiProcess_GenNormals), 12 triangle lights
+    assert scene("cube_shared.ply", "light").desc.numTriangleLights == 1 + 12
+    # errors are reported, not crashes
+    (m / "bad.ply").write_text("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                               "element face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 7\n")
+    with pytest.raises(Exception, match="vertex that does not exist"):
+        scene("bad.ply")
+    (m / "bad.stl").write_bytes(b"x" * 100)
+    with pytest.raises(Exception):
+        scene("bad.stl")
+    (m / "cube.fbx").write_bytes(b"whatever")
+    with pytest.raises(Exception, match="unsupported model format"):
+        scene("cube.fbx")

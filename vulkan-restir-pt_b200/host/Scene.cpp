@@ -1,4 +1,5 @@
 #include "Scene.h"
+#include "MeshFormats.h"
 #include "XmlLite.h"
 
 #include <algorithm>
@@ -163,6 +164,27 @@ uint32_t Scene::addModelFromTriangles(const std::vector<RptMeshVertex>& verts, c
 	}
 	models[L].push_back(model);
 	return uint32_t(models[L].size() - 1);
+}
+
+// Any model file (reference Resource::createNewModelInstance hands the path to assimp): OBJ by the reader below, PLY and STL by
+// MeshFormats.cpp; one mesh, assimp's default material (diffuse 0.6)
+uint32_t Scene::addModelFromFile(const std::string& modelPath, bool isLight) {
+	std::string ext;
+	const size_t dot = modelPath.find_last_of('.');
+	if (dot != std::string::npos) ext = modelPath.substr(dot + 1);
+	for (char& c : ext) c = char(std::tolower(static_cast<unsigned char>(c)));
+	if (ext == "obj") return addModelFromOBJ(modelPath, isLight);
+	RawMesh raw;
+	if (ext == "ply") readPLY(modelPath, raw);
+	else if (ext == "stl") readSTL(modelPath, raw);
+	else throw std::runtime_error("Scene: " + modelPath + ": unsupported model format (OBJ, PLY and STL are read)");
+	std::vector<RptMeshVertex> verts;
+	std::vector<uint32_t> idx;
+	triangulateRawMesh(raw, isLight, verts, idx);
+	fixInfacingNormals(verts, idx);
+	const uint32_t id = addModelFromTriangles(verts, idx, isLight, vec3(0.6f));
+	models[isLight ? 1 : 0][id].path = modelPath;
+	return id;
 }
 
 // One material of an OBJ file's material list (assimp ObjFile::Material: diffuse defaults to 0.6)
@@ -617,7 +639,7 @@ void Scene::load(const std::string& xmlPath) {
 			if (const XmlNode* r = inst->child("radiance")) power = parseVec3(r->attr("value"));
 			isLight = true;
 		}
-		uint32_t id = addModelFromOBJ(dir + "/" + inst->attr("path"), isLight);
+		uint32_t id = addModelFromFile(dir + "/" + inst->attr("path"), isLight);
 		ModelInstance& model = models[isLight ? 1 : 0][id];
 		model.name = inst->attr("name");
 		if (const XmlNode* t = inst->child("transform")) {

@@ -51,6 +51,7 @@ public:
 	// programmatic construction (procedural scenes, tests): same bookkeeping as the XML path
 	// returns model index into models[isLight]
 	uint32_t addModelFromOBJ(const std::string& objPath, bool isLight);
+	uint32_t addModelFromFile(const std::string& modelPath, bool isLight);   // by extension: .obj, .ply, .stl
 	uint32_t addModelFromTriangles(const std::vector<RptMeshVertex>& verts, const std::vector<uint32_t>& localIndices,
 	                               bool isLight, vec3 defaultDiffuse = vec3(0.6f));
 	// finalises instance `modelIdx` (transform already set on the ModelInstance): appends an ObjectInstance or
