@@ -707,7 +707,7 @@ def run_cuda(args):
                     "blocking_readback_value": 1000.0 * args.steps / m["e2e_blocking_ms"] * equiv},
             "gpu_launches": launches,
             "roofline": roofline,
-            "clocks": clock_info,
+            "clocks": dict(clock_info or {}, region="sampled every 50 ms during the device-resident timed region (`value`); the end-to-end regions run right after it"),
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(scene)
